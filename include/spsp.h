@@ -1,0 +1,146 @@
+/*
+ * spsp.h -- C ABI of the B200 device layer of supersampler_b200.
+ *
+ * The reference (TimRouze/supersampler) has no library / FFI surface: its hot
+ * path lives inside two executables.  This header is the boundary the
+ * north star asks for ("C++ host code calls CUDA through a thin C-ABI
+ * layer"): each entry point names the reference code it replaces, so a
+ * maintainer of the reference can swap the body of that function for one call.
+ * Plain pointers and sizes only; no C++/torch types; no exceptions cross it.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; the message of the
+ *     last error on the calling thread is spsp_last_error().
+ *   - the caller owns every host pointer; the library owns device memory,
+ *     except for the *_device entry points which work on caller-owned device
+ *     buffers (used for the device-resident benchmark and for NCCL plumbing).
+ *   - one context per (host thread group, GPU); calls on one (context, slot)
+ *     pair must be serialised by the caller; different slots map to different
+ *     CUDA streams and may be driven from different host threads.
+ *   - there is NO CPU fallback: without a CUDA device spsp_create fails.
+ *
+ * Packed sequence format ("2-bit"): bases A=0 C=1 T=2 G=3 (reference
+ * utils.cpp:13-16, code = (c>>1)&3), 16 bases per little-endian uint32 word,
+ * first base in the two most significant bits.  Buffers handed to the scan must
+ * be readable up to spsp_packed_words(n_bases) words (zero padded).
+ */
+#ifndef SPSP_H
+#define SPSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPSP_ABI_VERSION 1
+
+typedef struct spsp_ctx spsp_ctx;
+
+/* One selected m-mer ("hit"): an m-mer whose canonical form hashes <= T.
+ * 16 bytes.  pos = index of the m-mer's first base in the scanned buffer. */
+typedef struct {
+    uint64_t pos;
+    uint32_t canon;   /* canonical m-mer value = min(fw, revcomp)           */
+    uint32_t rev;     /* 1 when canon != forward m-mer (reference is_rev)  */
+} spsp_hit;
+
+/* Scan kernel selector (spsp_scan_config). */
+enum {
+    SPSP_SCAN_AUTO = 0,    /* q-gram filter kernel when profitable, else dense */
+    SPSP_SCAN_DENSE = 1,   /* full XXH64 at every position                    */
+    SPSP_SCAN_FILTER = 2   /* shared-memory aligned q-gram filter + exact verify */
+};
+
+int spsp_abi_version(void);
+const char *spsp_last_error(void);
+int spsp_device_count(int *n);
+
+/* Words (uint32) a packed buffer of n_bases must provide to the scan,
+ * including the zero padding the kernels may read. */
+uint64_t spsp_packed_words(uint64_t n_bases);
+
+/* Pinned host memory for the async copies (cudaHostAlloc / cudaFreeHost). */
+int spsp_host_alloc(void **p, size_t bytes);
+int spsp_host_free(void *p);
+
+/* Context: fixes (k, m, T) like the reference's Subsampler constructor
+ * (SubSampler.h:63-88); threshold is compute_threshold's value
+ * (SubSampler.cpp:622-631) evaluated by the host.  n_slots = number of
+ * independent streams (>=1). */
+int spsp_create(int device, int k, int m, uint64_t threshold, int n_slots, spsp_ctx **ctx);
+int spsp_destroy(spsp_ctx *ctx);
+int spsp_scan_config(spsp_ctx *ctx, int mode);
+
+/* ---- sketch stage ------------------------------------------------------
+ * Replaces the per-base loop of Subsampler::parse_fasta_test
+ * (SubSampler.cpp:367-440: updateM/updateRCM :36-53, canonical m-mer,
+ * unrevhash -> XXHash64::hash(&x,8,1312) :64-67, threshold test :405/:443)
+ * by its closed form: report every position whose canonical m-mer hashes
+ * <= T.  The exact state-machine replay over this sparse list is host code
+ * (supersampler_b200/csrc/host/postpass.cpp).
+ *
+ * submit: async H2D of `packed` (pinned recommended) + kernel + async D2H of
+ *         the hits into an internal pinned buffer; returns immediately.
+ * collect: waits for the slot, copies the hits (unordered) to hits_out.
+ *          If n_hits > cap the call fails with -2 and *n_hits holds the
+ *          needed capacity (call again with a larger buffer). */
+int spsp_scan_submit(spsp_ctx *ctx, int slot, const uint32_t *packed, uint64_t n_bases);
+int spsp_scan_collect(spsp_ctx *ctx, int slot, spsp_hit *hits_out, uint64_t cap, uint64_t *n_hits);
+
+/* Device-resident variant: d_packed / d_hits / d_count are device pointers
+ * owned by the caller; d_count (uint64) is zeroed by the call; launches on the
+ * slot's stream and returns without synchronising (spsp_sync to wait).
+ * Hits beyond cap are counted but not stored. */
+int spsp_scan_device(spsp_ctx *ctx, int slot, const uint32_t *d_packed, uint64_t n_bases,
+                     spsp_hit *d_hits, uint64_t cap, uint64_t *d_count);
+int spsp_sync(spsp_ctx *ctx, int slot);
+/* Time of the last scan kernel(s) launched on the slot, CUDA events on the
+ * slot's stream (milliseconds); valid after spsp_sync / collect. */
+int spsp_scan_last_kernel_ms(spsp_ctx *ctx, int slot, float *ms);
+/* Raw stream handle of a slot (cudaStream_t as void*), for callers that
+ * interleave their own work (NCCL through torch.distributed). */
+int spsp_stream(spsp_ctx *ctx, int slot, void **stream);
+
+/* ---- compare stage -----------------------------------------------------
+ * Replaces Comparator::compare_sketches' N-way merge + count_intersection +
+ * compute_scores (Comparator.cpp:39-74, :177-287): for every pair of
+ * sketches the number of (minimizer bucket, canonical k-mer) entries they
+ * share.  The host decodes sketch files (strDecompressor / inject_minimizer /
+ * canonize, Comparator.cpp:78-92, :97-154) into per-sketch element lists.
+ *
+ * Elements of a sketch: distinct (minimizer, canonical k-mer) pairs, sorted by
+ * minimizer (any order inside a bucket).  kmer_hi is NULL when k <= 32.
+ * sketch_off has n_sketches+1 entries (element offsets into the arrays).
+ * load replaces all previously loaded sketches. */
+int spsp_cmp_load(spsp_ctx *ctx, uint32_t n_sketches, const uint64_t *sketch_off,
+                  const uint32_t *minimizer, const uint64_t *kmer_lo, const uint64_t *kmer_hi);
+/* Same with device-resident arrays (after an NCCL all-gather): the context
+ * keeps the pointers, the caller keeps them alive until the next load. */
+int spsp_cmp_load_device(spsp_ctx *ctx, uint32_t n_sketches, const uint64_t *sketch_off_host,
+                         const uint32_t *d_minimizer, const uint64_t *d_kmer_lo,
+                         const uint64_t *d_kmer_hi);
+/* Intersections for rows [row_begin,row_end) x columns [col_begin,col_end):
+ * out[(i-row_begin)*ld + (j-col_begin)] += |K_i ∩ K_j| (row-major uint32,
+ * ld >= col_end-col_begin, zeroed by the caller).  With symmetric != 0 only
+ * tiles on or above the diagonal are computed (entries with i < j are valid).
+ * tile_rank / tile_ranks deal the tile list round-robin for multi-GPU runs
+ * (0 / 1 for a single GPU).  out is HOST memory (synchronous call). */
+int spsp_cmp_run(spsp_ctx *ctx, uint32_t row_begin, uint32_t row_end, uint32_t col_begin,
+                 uint32_t col_end, int symmetric, uint32_t tile_rank, uint32_t tile_ranks,
+                 uint32_t *out, uint64_t ld);
+/* Device-output variant: d_out is a device pointer (not zeroed by the call),
+ * launches on slot 0's stream without synchronising. */
+int spsp_cmp_run_device(spsp_ctx *ctx, uint32_t row_begin, uint32_t row_end, uint32_t col_begin,
+                        uint32_t col_end, int symmetric, uint32_t tile_rank, uint32_t tile_ranks,
+                        uint32_t *d_out, uint64_t ld);
+int spsp_cmp_last_kernel_ms(spsp_ctx *ctx, float *ms);
+
+/* Number of kernels this library launched on the context since creation. */
+int spsp_launch_count(spsp_ctx *ctx, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPSP_H */

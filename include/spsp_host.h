@@ -1,0 +1,72 @@
+/*
+ * spsp_host.h -- C entry points of the C++ host layer (libspsp_host.so).
+ *
+ * The host layer mirrors the reference's two classes (Subsampler,
+ * Comparator) and its two main() functions; these wrappers exist so that the
+ * drop-in CLIs, the tests and bench.py (ctypes) all run the same code.
+ * Functions marked [cpu] need no GPU (host logic only); everything else needs
+ * a CUDA device and fails loudly without one.
+ * Buffers returned through out-pointers are malloc'ed: release with spsph_free.
+ */
+#ifndef SPSP_HOST_H
+#define SPSP_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "spsp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *spsph_last_error(void);
+void spsph_free(void *p);
+
+/* The reference's executables as functions (SubSampler.cpp:667-803,
+ * Comparator.cpp:464-521): same flags, defaults, outputs in the CWD. */
+int spsph_sub_sampler_main(int argc, char **argv);
+int spsph_comparator_main(int argc, char **argv);
+
+/* [cpu] compute_threshold (SubSampler.cpp:622-631); s is the float-parsed -s. */
+uint64_t spsph_threshold(int k, int m, double s);
+
+/* [cpu] getLineFasta + clean_dna + 2-bit packing of records >= min_len.
+ * words has spsp_packed_words(n_bases) entries, rec_off n_rec+1 entries. */
+int spsph_pack_fasta(const uint8_t *fasta, size_t n, uint32_t min_len, uint32_t **words, uint64_t *n_bases,
+                     uint64_t **rec_off, uint64_t *n_rec);
+
+/* [cpu] Exact post-pass: hits (any order) on a packed buffer -> sketch bytes
+ * (before gzip).  The GPU path feeds it the scan kernel's output. */
+int spsph_postpass(const uint32_t *packed, const uint64_t *rec_off, uint64_t n_rec, const spsp_hit *hits,
+                   uint64_t n_hits, int k, int m, double s, unsigned abundance, uint8_t **out, size_t *out_len,
+                   uint64_t *selected_kmers);
+
+/* [cpu] Sketch bytes -> distinct (minimizer, canonical k-mer) elements. */
+int spsph_decode_sketch(const uint8_t *sketch, size_t n, int *k, int *m, uint64_t *n_elems, uint32_t **minimizer,
+                        uint64_t **kmer_lo, uint64_t **kmer_hi);
+
+/* [cpu] CSV text of print_containment (jaccard=0) / print_jaccard (jaccard=1).
+ * inter is row-major with leading dimension n; full_rows=0: pair (i<j) at
+ * inter[i*n+j]; full_rows=1: row i complete. */
+int spsph_format_csv(const char *const *names, uint32_t n, uint32_t query_size, const uint32_t *inter, int full_rows,
+                     const uint64_t *sizes, int jaccard, unsigned precision, double min_threshold, uint8_t **out,
+                     size_t *out_len);
+
+/* GPU: sketch n FASTA texts held in memory with `threads` host workers on
+ * `device`; out[i]/out_len[i] receive the sketch bytes (before gzip).
+ * timings (may be NULL): [0]=pack s, [1]=scan s (submit..collect), [2]=post-pass s,
+ * summed over inputs; launches (may be NULL) = kernels launched. */
+int spsph_sketch_buffers(int device, int k, int m, double s, unsigned abundance, int scan_mode, uint32_t n,
+                         const uint8_t *const *fasta, const size_t *len, int threads, uint8_t **out, size_t *out_len,
+                         double *timings, uint64_t *launches);
+
+/* GPU: all-vs-all (query_size == n) or query-vs-all compare of n sketches held
+ * in memory.  inter: rows x n uint32 (rows = n or query_size), sizes: n. */
+int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size, const uint8_t *const *sketch, const size_t *len,
+                          uint32_t *inter, uint64_t *sizes, int *full_rows, float *kernel_ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPSP_HOST_H */

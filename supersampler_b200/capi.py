@@ -1,0 +1,328 @@
+"""ctypes bindings of include/spsp.h (device C ABI) and include/spsp_host.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(PKG, "lib")
+BIN_DIR = os.path.join(PKG, "bin")
+CSRC = os.path.join(PKG, "csrc")
+
+HIT_DTYPE = np.dtype([("pos", "<u8"), ("canon", "<u4"), ("rev", "<u4")])
+
+SCAN_AUTO, SCAN_DENSE, SCAN_FILTER = 0, 1, 2
+
+
+class SpspError(RuntimeError):
+    pass
+
+
+def build(force: bool = False) -> None:
+    """Compile the CUDA device layer (sm_100a), the host layer and the CLIs in-tree."""
+    args = ["make", "-C", CSRC, "all", "-j4"]
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise SpspError("build failed:\n" + r.stdout[-4000:])
+
+
+_dev = None
+_host = None
+
+
+def _need(path: str) -> str:
+    if not os.path.exists(path):
+        raise SpspError(f"{path} is missing: run supersampler_b200.build() (needs nvcc); there is no fallback path")
+    return path
+
+
+def device_lib():
+    global _dev
+    if _dev is None:
+        L = C.CDLL(_need(os.path.join(LIB_DIR, "libspsp_b200.so")), mode=C.RTLD_GLOBAL)
+        L.spsp_last_error.restype = C.c_char_p
+        L.spsp_packed_words.restype = C.c_uint64
+        L.spsp_packed_words.argtypes = [C.c_uint64]
+        L.spsp_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        L.spsp_destroy.argtypes = [C.c_void_p]
+        L.spsp_scan_config.argtypes = [C.c_void_p, C.c_int]
+        L.spsp_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.spsp_host_free.argtypes = [C.c_void_p]
+        L.spsp_scan_submit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.spsp_scan_collect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.spsp_scan_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.spsp_sync.argtypes = [C.c_void_p, C.c_int]
+        L.spsp_scan_last_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        L.spsp_stream.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.spsp_cmp_load.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.spsp_cmp_load_device.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.spsp_cmp_run.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.spsp_cmp_run_device.argtypes = L.spsp_cmp_run.argtypes
+        L.spsp_cmp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.spsp_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        _dev = L
+    return _dev
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        device_lib()
+        L = C.CDLL(_need(os.path.join(LIB_DIR, "libspsp_host.so")))
+        L.spsph_last_error.restype = C.c_char_p
+        L.spsph_free.argtypes = [C.c_void_p]
+        L.spsph_threshold.restype = C.c_uint64
+        L.spsph_threshold.argtypes = [C.c_int, C.c_int, C.c_double]
+        L.spsph_sub_sampler_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.spsph_comparator_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.spsph_pack_fasta.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.spsph_postpass.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
+                                     C.c_double, C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_uint64)]
+        L.spsph_decode_sketch.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p)]
+        L.spsph_format_csv.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_int, C.c_uint, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.spsph_sketch_buffers.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.c_uint32,
+                                           C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_uint64)]
+        L.spsph_compare_buffers.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p),
+                                            C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                            C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        _host = L
+    return _host
+
+
+def _hcheck(rc: int, what: str) -> None:
+    if rc != 0:
+        raise SpspError(f"{what}: {host_lib().spsph_last_error().decode()}")
+
+
+def _dcheck(rc: int, what: str) -> None:
+    if rc != 0:
+        raise SpspError(f"{what}: {device_lib().spsp_last_error().decode()} (rc={rc})")
+
+
+def _f32(s: float) -> float:
+    """The reference parses -s with stof (SubSampler.cpp:699)."""
+    return float(np.float32(s))
+
+
+def packed_words(n_bases: int) -> int:
+    return int(device_lib().spsp_packed_words(n_bases))
+
+
+def threshold(k: int, m: int, s: float) -> int:
+    return int(host_lib().spsph_threshold(k, m, _f32(s)))
+
+
+def _take(ptr: C.c_void_p, nbytes: int, dtype) -> np.ndarray:
+    out = np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).copy() if nbytes else np.zeros(0, dtype)
+    host_lib().spsph_free(ptr)
+    return out
+
+
+def pack_fasta(fasta: bytes, min_len: int) -> Tuple[np.ndarray, int, np.ndarray]:
+    """[cpu] FASTA text -> (packed words, n_bases, record offsets)."""
+    L = host_lib()
+    w, ro = C.c_void_p(), C.c_void_p()
+    nb, nr = C.c_uint64(), C.c_uint64()
+    _hcheck(L.spsph_pack_fasta(fasta, len(fasta), min_len, C.byref(w), C.byref(nb), C.byref(ro), C.byref(nr)), "pack_fasta")
+    words = _take(w, packed_words(nb.value) * 4, np.uint32)
+    offs = _take(ro, (nr.value + 1) * 8, np.uint64)
+    return words, int(nb.value), offs
+
+
+def postpass(words: np.ndarray, rec_off: np.ndarray, hits: np.ndarray, k: int, m: int, s: float,
+             abundance: int = 1) -> Tuple[bytes, int]:
+    """[cpu] hit list -> sketch bytes (before gzip), selected k-mer occurrences."""
+    L = host_lib()
+    words = np.ascontiguousarray(words, np.uint32)
+    rec_off = np.ascontiguousarray(rec_off, np.uint64)
+    hits = np.ascontiguousarray(hits, HIT_DTYPE)
+    out, n, sel = C.c_void_p(), C.c_size_t(), C.c_uint64()
+    _hcheck(L.spsph_postpass(words.ctypes.data, rec_off.ctypes.data, rec_off.size - 1, hits.ctypes.data, hits.size,
+                             k, m, _f32(s), abundance, C.byref(out), C.byref(n), C.byref(sel)), "postpass")
+    return _take(out, n.value, np.uint8).tobytes(), int(sel.value)
+
+
+def decode_sketch(sketch: bytes):
+    """[cpu] sketch bytes -> (k, m, minimizer u32[], kmer_lo u64[], kmer_hi u64[] or None)."""
+    L = host_lib()
+    k, m, n = C.c_int(), C.c_int(), C.c_uint64()
+    a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _hcheck(L.spsph_decode_sketch(sketch, len(sketch), C.byref(k), C.byref(m), C.byref(n), C.byref(a), C.byref(b),
+                                  C.byref(c)), "decode_sketch")
+    mn = _take(a, n.value * 4, np.uint32)
+    lo = _take(b, n.value * 8, np.uint64)
+    hi = _take(c, n.value * 8, np.uint64) if c.value else None
+    return k.value, m.value, mn, lo, hi
+
+
+def format_csv(names: Sequence[str], query_size: int, inter: np.ndarray, full_rows: bool, sizes: np.ndarray,
+               jaccard: bool, precision: int = 6, min_threshold: float = 0.0) -> bytes:
+    L = host_lib()
+    n = len(names)
+    arr = (C.c_char_p * n)(*[x.encode() for x in names])
+    inter = np.ascontiguousarray(inter, np.uint32)
+    sizes = np.ascontiguousarray(sizes, np.uint64)
+    out, ln = C.c_void_p(), C.c_size_t()
+    _hcheck(L.spsph_format_csv(arr, n, query_size, inter.ctypes.data, int(full_rows), sizes.ctypes.data, int(jaccard),
+                               precision, min_threshold, C.byref(out), C.byref(ln)), "format_csv")
+    return _take(out, ln.value, np.uint8).tobytes()
+
+
+def sketch_buffers(fastas: Sequence[bytes], k: int = 31, m: int = 11, s: float = 1000.0, abundance: int = 1,
+                   device: int = 0, threads: int = 8, scan_mode: int = SCAN_AUTO, info: Optional[dict] = None) -> List[bytes]:
+    """GPU: FASTA texts -> sketch bytes (before gzip), through Subsampler + the C ABI."""
+    L = host_lib()
+    n = len(fastas)
+    arr = (C.c_char_p * n)(*fastas)
+    lens = (C.c_size_t * n)(*[len(f) for f in fastas])
+    outs = (C.c_void_p * n)()
+    olens = (C.c_size_t * n)()
+    tim = (C.c_double * 3)()
+    nl = C.c_uint64()
+    _hcheck(L.spsph_sketch_buffers(device, k, m, _f32(s), abundance, scan_mode, n, arr, lens, threads, outs, olens,
+                                   tim, C.byref(nl)), "sketch_buffers")
+    res = []
+    for i in range(n):
+        res.append(C.string_at(outs[i], olens[i]) if olens[i] else b"")
+        L.spsph_free(outs[i])
+    if info is not None:
+        info.update(pack_s=tim[0], scan_s=tim[1], post_s=tim[2], launches=int(nl.value))
+    return res
+
+
+def compare_buffers(sketches: Sequence[bytes], query_size: Optional[int] = None, n_gpus: int = 1,
+                    info: Optional[dict] = None):
+    """GPU: sketch bytes -> (inter[rows, n] uint32, sizes[n] uint64, full_rows)."""
+    L = host_lib()
+    n = len(sketches)
+    q = n if query_size is None else query_size
+    arr = (C.c_char_p * n)(*sketches)
+    lens = (C.c_size_t * n)(*[len(x) for x in sketches])
+    rows = n if q >= n else q
+    inter = np.zeros((rows, n), np.uint32)
+    sizes = np.zeros(n, np.uint64)
+    full, ms, nl = C.c_int(), C.c_float(), C.c_uint64()
+    _hcheck(L.spsph_compare_buffers(n_gpus, n, q, arr, lens, inter.ctypes.data, sizes.ctypes.data, C.byref(full),
+                                    C.byref(ms), C.byref(nl)), "compare_buffers")
+    if info is not None:
+        info.update(kernel_ms=float(ms.value), launches=int(nl.value))
+    return inter, sizes, bool(full.value)
+
+
+def _run_main(fn, argv: Sequence[str]) -> int:
+    args = [a.encode() for a in argv]
+    arr = (C.c_char_p * (len(args) + 1))(*args, None)
+    return int(fn(len(args), arr))
+
+
+def run_sub_sampler(args: Sequence[str]) -> int:
+    """In-process `sub_sampler <args>` (writes into the CWD like the reference)."""
+    return _run_main(host_lib().spsph_sub_sampler_main, ["sub_sampler", *args])
+
+
+def run_comparator(args: Sequence[str]) -> int:
+    return _run_main(host_lib().spsph_comparator_main, ["comparator", *args])
+
+
+class DeviceContext:
+    """Thin RAII wrapper of spsp_ctx for tests / bench (device C ABI, raw pointers)."""
+
+    def __init__(self, k: int, m: int, thr: int, device: int = 0, n_slots: int = 1):
+        self.L = device_lib()
+        self.h = C.c_void_p()
+        _dcheck(self.L.spsp_create(device, k, m, thr, n_slots, C.byref(self.h)), "spsp_create")
+        self.k, self.m, self.thr = k, m, thr
+
+    def close(self):
+        if self.h:
+            self.L.spsp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def config(self, mode: int):
+        _dcheck(self.L.spsp_scan_config(self.h, mode), "spsp_scan_config")
+
+    def scan(self, words: np.ndarray, n_bases: int, slot: int = 0) -> np.ndarray:
+        """Host buffer in, hits out (submit + collect)."""
+        words = np.ascontiguousarray(words, np.uint32)
+        assert words.size >= packed_words(n_bases)
+        _dcheck(self.L.spsp_scan_submit(self.h, slot, words.ctypes.data, n_bases), "spsp_scan_submit")
+        cap = 1 << 16
+        n = C.c_uint64()
+        hits = np.zeros(cap, HIT_DTYPE)
+        rc = self.L.spsp_scan_collect(self.h, slot, hits.ctypes.data, cap, C.byref(n))
+        if rc == -2:
+            hits = np.zeros(n.value, HIT_DTYPE)
+            rc = self.L.spsp_scan_collect(self.h, slot, hits.ctypes.data, n.value, C.byref(n))
+        _dcheck(rc, "spsp_scan_collect")
+        return hits[: n.value].copy()
+
+    def scan_device(self, d_packed: int, n_bases: int, d_hits: int, cap: int, d_count: int, slot: int = 0):
+        _dcheck(self.L.spsp_scan_device(self.h, slot, d_packed, n_bases, d_hits, cap, d_count), "spsp_scan_device")
+
+    def sync(self, slot: int = 0):
+        _dcheck(self.L.spsp_sync(self.h, slot), "spsp_sync")
+
+    def scan_kernel_ms(self, slot: int = 0) -> float:
+        ms = C.c_float()
+        _dcheck(self.L.spsp_scan_last_kernel_ms(self.h, slot, C.byref(ms)), "spsp_scan_last_kernel_ms")
+        return float(ms.value)
+
+    def stream(self, slot: int = 0) -> int:
+        p = C.c_void_p()
+        _dcheck(self.L.spsp_stream(self.h, slot, C.byref(p)), "spsp_stream")
+        return int(p.value or 0)
+
+    def cmp_load(self, sk_off: np.ndarray, minim: np.ndarray, klo: np.ndarray, khi: Optional[np.ndarray] = None):
+        sk_off = np.ascontiguousarray(sk_off, np.uint64)
+        minim = np.ascontiguousarray(minim, np.uint32)
+        klo = np.ascontiguousarray(klo, np.uint64)
+        khi_p = None
+        if khi is not None:
+            khi = np.ascontiguousarray(khi, np.uint64)
+            khi_p = khi.ctypes.data
+        _dcheck(self.L.spsp_cmp_load(self.h, sk_off.size - 1, sk_off.ctypes.data, minim.ctypes.data, klo.ctypes.data,
+                                     khi_p), "spsp_cmp_load")
+
+    def cmp_load_device(self, sk_off: np.ndarray, d_minim: int, d_klo: int, d_khi: Optional[int] = None):
+        sk_off = np.ascontiguousarray(sk_off, np.uint64)
+        _dcheck(self.L.spsp_cmp_load_device(self.h, sk_off.size - 1, sk_off.ctypes.data, d_minim, d_klo, d_khi),
+                "spsp_cmp_load_device")
+
+    def cmp_run(self, rows: Tuple[int, int], cols: Tuple[int, int], symmetric: bool, rank: int = 0, ranks: int = 1) -> np.ndarray:
+        out = np.zeros((rows[1] - rows[0], cols[1] - cols[0]), np.uint32)
+        _dcheck(self.L.spsp_cmp_run(self.h, rows[0], rows[1], cols[0], cols[1], int(symmetric), rank, ranks,
+                                    out.ctypes.data, out.shape[1]), "spsp_cmp_run")
+        return out
+
+    def cmp_run_device(self, rows, cols, symmetric: bool, rank: int, ranks: int, d_out: int, ld: int):
+        _dcheck(self.L.spsp_cmp_run_device(self.h, rows[0], rows[1], cols[0], cols[1], int(symmetric), rank, ranks,
+                                           d_out, ld), "spsp_cmp_run_device")
+
+    def cmp_kernel_ms(self) -> float:
+        ms = C.c_float()
+        _dcheck(self.L.spsp_cmp_last_kernel_ms(self.h, C.byref(ms)), "spsp_cmp_last_kernel_ms")
+        return float(ms.value)
+
+    def launches(self) -> int:
+        n = C.c_uint64()
+        _dcheck(self.L.spsp_launch_count(self.h, C.byref(n)), "spsp_launch_count")
+        return int(n.value)

@@ -1,0 +1,478 @@
+// C ABI of the device layer (include/spsp.h): contexts, slots (streams),
+// buffers and kernel launches.  No algorithmic work happens on the host here
+// and there is no CPU fallback: every entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/spsp.h"
+#include "compare.cuh"
+#include "scan.cuh"
+
+using namespace spsp;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(-1, std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint32_t *d_packed = nullptr;
+    uint64_t d_packed_words = 0;
+    spsp_hit *d_hits = nullptr;
+    uint64_t hits_cap = 0;
+    unsigned long long *d_count = nullptr;
+    unsigned long long *h_count = nullptr;     // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t n_bases = 0;
+    bool pending = false;
+    bool timed = false;
+};
+
+struct spsp_ctx {
+    int device = 0, k = 0, m = 0;
+    uint64_t thr = 0;
+    int mode = SPSP_SCAN_AUTO;
+    std::vector<Slot> slots;
+    // q-gram filter
+    bool filter_ready = false;
+    bool filter_profitable = false;
+    FilterParams fp{};
+    uint32_t *d_table = nullptr;
+    uint64_t n_selected = 0;
+    // compare
+    uint32_t n_sketches = 0, n_chunks = 0;
+    uint64_t n_elems = 0;
+    bool has_hi = false, owns_cmp = false;
+    CmpData cmp{};
+    uint32_t *own_minim = nullptr;
+    uint64_t *own_klo = nullptr, *own_khi = nullptr, *d_sk_off = nullptr, *d_chunk_off = nullptr;
+    cudaEvent_t cev0 = nullptr, cev1 = nullptr;
+    bool cmp_timed = false;
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+extern "C" int spsp_abi_version(void) { return SPSP_ABI_VERSION; }
+extern "C" const char *spsp_last_error(void) { return g_err.c_str(); }
+
+extern "C" int spsp_device_count(int *n)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return fail(-1, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *n = c;
+    return 0;
+}
+
+extern "C" uint64_t spsp_packed_words(uint64_t n_bases) { return 4 * ((n_bases + 4 + 63) / 64) + 8; }
+
+extern "C" int spsp_host_alloc(void **p, size_t bytes)
+{
+    CK(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int spsp_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+// Expected instruction cost per base of the filter kernel for stride g (see
+// DESIGN.md "scan kernel"): probe + queue push under divergence + verify.
+static double filter_cost(int m, int g, double n_sel, FilterParams *fp)
+{
+    int q = m - g + 1;
+    if (q < 3) return 1e9;
+    int bits = 2 * q;
+    int hashed = 0;
+    if (bits > FILTER_MAX_BITS) { bits = FILTER_MAX_BITS; hashed = 1; }
+    if (bits < 10) bits = 10;
+    double load = g * n_sel / std::ldexp(1.0, bits);
+    double delta = hashed ? 1.0 - std::exp(-load) : std::min(1.0, load);
+    double any = 1.0 - std::pow(1.0 - delta, 32.0);
+    fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed;
+    return 7.0 / g + any * 12.0 / g + delta * 50.0;
+}
+
+static int build_filter(spsp_ctx *c)
+{
+    double p = (double)c->thr / 18446744073709551616.0;
+    double n_sel = std::ldexp(1.0, 2 * c->m) * p;
+    double best = 1e9;
+    FilterParams bfp{};
+    for (int g : {4, 2, 1}) {
+        FilterParams fp{};
+        double cost = filter_cost(c->m, g, n_sel, &fp);
+        if (cost < best) { best = cost; bfp = fp; }
+    }
+    c->filter_profitable = best < 0.6 * 40.0;
+    if (best >= 1e9) { c->filter_ready = false; return 0; }
+    c->fp = bfp;
+    CK(cudaMalloc(&c->d_table, (size_t)1 << (bfp.bits - 3)));
+    unsigned long long *d_n = nullptr;
+    CK(cudaMalloc(&d_n, sizeof(unsigned long long)));
+    CK(launch_filter_build(c->m, c->thr, bfp, c->d_table, d_n, c->slots[0].stream));
+    c->launches++;
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, c->slots[0].stream));
+    CK(cudaStreamSynchronize(c->slots[0].stream));
+    CK(cudaFree(d_n));
+    c->n_selected = n;
+    c->filter_ready = true;
+    return 0;
+}
+
+extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_slots, spsp_ctx **out)
+{
+    if (!out) return fail(-3, "spsp_create: null out");
+    *out = nullptr;
+    if (k < 3 || k > 63 || m < 3 || m > 15 || m >= k || !(k & 1) || !(m & 1))
+        return fail(-3, "spsp_create: need odd 3<=m<=15, odd m<k<=63");
+    if (n_slots < 1 || n_slots > 64) return fail(-3, "spsp_create: n_slots out of range");
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+        return fail(-1, "spsp_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= cnt) return fail(-3, "spsp_create: bad device index");
+    CK(cudaSetDevice(device));
+    spsp_ctx *c = new spsp_ctx();
+    c->device = device; c->k = k; c->m = m; c->thr = threshold;
+    c->slots.resize(n_slots);
+    for (auto &s : c->slots) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaMalloc(&s.d_count, sizeof(unsigned long long)));
+        CK(cudaHostAlloc(&s.h_count, sizeof(unsigned long long), cudaHostAllocDefault));
+        CK(cudaEventCreate(&s.ev0));
+        CK(cudaEventCreate(&s.ev1));
+    }
+    CK(cudaEventCreate(&c->cev0));
+    CK(cudaEventCreate(&c->cev1));
+    int rc = build_filter(c);
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return 0;
+}
+
+static void free_cmp(spsp_ctx *c)
+{
+    if (c->owns_cmp) {
+        cudaFree(c->own_minim); cudaFree(c->own_klo); cudaFree(c->own_khi);
+    }
+    cudaFree(c->d_sk_off); cudaFree(c->d_chunk_off);
+    c->own_minim = nullptr; c->own_klo = c->own_khi = nullptr;
+    c->d_sk_off = c->d_chunk_off = nullptr;
+    c->owns_cmp = false;
+    c->n_sketches = 0;
+}
+
+extern "C" int spsp_destroy(spsp_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    for (auto &s : c->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_packed); cudaFree(s.d_hits); cudaFree(s.d_count);
+        cudaFreeHost(s.h_count);
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    free_cmp(c);
+    cudaFree(c->d_table);
+    if (c->cev0) cudaEventDestroy(c->cev0);
+    if (c->cev1) cudaEventDestroy(c->cev1);
+    delete c;
+    return 0;
+}
+
+extern "C" int spsp_scan_config(spsp_ctx *c, int mode)
+{
+    if (!c) return fail(-3, "null ctx");
+    if (mode < SPSP_SCAN_AUTO || mode > SPSP_SCAN_FILTER) return fail(-3, "spsp_scan_config: bad mode");
+    if (mode == SPSP_SCAN_FILTER && !c->filter_ready) return fail(-3, "spsp_scan_config: filter unavailable for this m");
+    c->mode = mode;
+    return 0;
+}
+
+static int launch_scan(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n_bases, ScanOut out)
+{
+    bool use_filter = c->mode == SPSP_SCAN_FILTER || (c->mode == SPSP_SCAN_AUTO && c->filter_ready && c->filter_profitable);
+    CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned long long), s.stream));
+    CK(cudaEventRecord(s.ev0, s.stream));
+    if (use_filter)
+        CK(launch_scan_filter(d_packed, n_bases, c->m, c->thr, c->fp, c->d_table, out, s.stream));
+    else
+        CK(launch_scan_dense(d_packed, n_bases, c->m, c->thr, out, s.stream));
+    CK(cudaEventRecord(s.ev1, s.stream));
+    s.timed = true;
+    if (n_bases >= (uint64_t)c->m) {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->launches++;
+    }
+    return 0;
+}
+
+static int ensure_hits(Slot &s, uint64_t want)
+{
+    if (want <= s.hits_cap) return 0;
+    if (s.d_hits) CK(cudaFree(s.d_hits));
+    s.d_hits = nullptr; s.hits_cap = 0;
+    CK(cudaMalloc(&s.d_hits, want * sizeof(spsp_hit)));
+    s.hits_cap = want;
+    return 0;
+}
+
+extern "C" int spsp_scan_submit(spsp_ctx *c, int slot, const uint32_t *packed, uint64_t n_bases)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_scan_submit: bad ctx/slot");
+    if (!packed && n_bases) return fail(-3, "spsp_scan_submit: null input");
+    Slot &s = c->slots[slot];
+    if (s.pending) return fail(-3, "spsp_scan_submit: slot busy (collect first)");
+    CK(cudaSetDevice(c->device));
+    uint64_t words = spsp_packed_words(n_bases);
+    if (words > s.d_packed_words) {
+        if (s.d_packed) CK(cudaFree(s.d_packed));
+        s.d_packed = nullptr; s.d_packed_words = 0;
+        uint64_t cap = words + words / 4;
+        CK(cudaMalloc(&s.d_packed, cap * sizeof(uint32_t)));
+        s.d_packed_words = cap;
+    }
+    CK(cudaMemcpyAsync(s.d_packed, packed, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    double p = (double)c->thr / 18446744073709551616.0;
+    uint64_t guess = (uint64_t)((double)n_bases * p * 1.5) + 4096;
+    if (guess > n_bases + 1) guess = n_bases + 1;
+    int rc = ensure_hits(s, guess);
+    if (rc) return rc;
+    s.n_bases = n_bases;
+    ScanOut out{s.d_hits, s.d_count, s.hits_cap};
+    rc = launch_scan(c, s, s.d_packed, n_bases, out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    s.pending = true;
+    return 0;
+}
+
+extern "C" int spsp_scan_collect(spsp_ctx *c, int slot, spsp_hit *hits_out, uint64_t cap, uint64_t *n_hits)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_scan_collect: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (!s.pending) return fail(-3, "spsp_scan_collect: nothing submitted");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(s.stream));
+    uint64_t n = *s.h_count;
+    if (n > s.hits_cap) {
+        // the estimate was too small: grow and rescan (exact, just slower)
+        int rc = ensure_hits(s, n + n / 8 + 1024);
+        if (rc) return rc;
+        ScanOut out{s.d_hits, s.d_count, s.hits_cap};
+        rc = launch_scan(c, s, s.d_packed, s.n_bases, out);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        n = *s.h_count;
+    }
+    if (n_hits) *n_hits = n;
+    if (n > cap) return fail(-2, "spsp_scan_collect: output buffer too small");
+    if (n) {
+        CK(cudaMemcpyAsync(hits_out, s.d_hits, n * sizeof(spsp_hit), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    s.pending = false;
+    return 0;
+}
+
+extern "C" int spsp_scan_device(spsp_ctx *c, int slot, const uint32_t *d_packed, uint64_t n_bases, spsp_hit *d_hits,
+                                uint64_t cap, uint64_t *d_count)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_scan_device: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    CK(cudaSetDevice(c->device));
+    ScanOut out{d_hits, reinterpret_cast<unsigned long long *>(d_count), cap};
+    return launch_scan(c, s, d_packed, n_bases, out);
+}
+
+extern "C" int spsp_sync(spsp_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_sync: bad ctx/slot");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->slots[slot].stream));
+    return 0;
+}
+
+extern "C" int spsp_scan_last_kernel_ms(spsp_ctx *c, int slot, float *ms)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !ms) return fail(-3, "spsp_scan_last_kernel_ms: bad args");
+    Slot &s = c->slots[slot];
+    if (!s.timed) return fail(-3, "no scan launched on this slot");
+    CK(cudaEventSynchronize(s.ev1));
+    CK(cudaEventElapsedTime(ms, s.ev0, s.ev1));
+    return 0;
+}
+
+extern "C" int spsp_stream(spsp_ctx *c, int slot, void **stream)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !stream) return fail(-3, "spsp_stream: bad args");
+    *stream = (void *)c->slots[slot].stream;
+    return 0;
+}
+
+// ----------------------------------------------------------------- compare
+
+static int finish_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *sketch_off)
+{
+    cudaStream_t st = c->slots[0].stream;
+    c->n_sketches = n_sketches;
+    c->n_elems = sketch_off[n_sketches];
+    for (uint32_t i = 0; i < n_sketches; i++)
+        if (sketch_off[i] > sketch_off[i + 1]) return fail(-3, "spsp_cmp_load: sketch_off not monotone");
+    CK(cudaMalloc(&c->d_sk_off, (size_t)(n_sketches + 1) * sizeof(uint64_t)));
+    CK(cudaMemcpyAsync(c->d_sk_off, sketch_off, (size_t)(n_sketches + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    double avg = n_sketches ? (double)c->n_elems / n_sketches : 0.0;
+    uint64_t chunks = (uint64_t)std::ceil(32.0 * avg / (0.7 * CMP_CAP));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 8192) chunks = 8192;
+    c->n_chunks = (uint32_t)chunks;
+    CK(cudaMalloc(&c->d_chunk_off, (size_t)n_sketches * (chunks + 1) * sizeof(uint64_t)));
+    c->cmp.sk_off = c->d_sk_off;
+    c->cmp.chunk_off = c->d_chunk_off;
+    CK(launch_chunk_offsets(c->cmp, n_sketches, c->n_chunks, c->m, st));
+    c->launches++;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int spsp_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *sketch_off, const uint32_t *minimizer,
+                             const uint64_t *kmer_lo, const uint64_t *kmer_hi)
+{
+    if (!c || !sketch_off) return fail(-3, "spsp_cmp_load: bad args");
+    if ((c->k > 32) != (kmer_hi != nullptr)) return fail(-3, "spsp_cmp_load: kmer_hi must be given iff k > 32");
+    CK(cudaSetDevice(c->device));
+    free_cmp(c);
+    cudaStream_t st = c->slots[0].stream;
+    uint64_t E = sketch_off[n_sketches];
+    size_t e1 = E ? E : 1;
+    CK(cudaMalloc(&c->own_minim, e1 * sizeof(uint32_t)));
+    CK(cudaMalloc(&c->own_klo, e1 * sizeof(uint64_t)));
+    c->owns_cmp = true;
+    if (kmer_hi) CK(cudaMalloc(&c->own_khi, e1 * sizeof(uint64_t)));
+    if (E) {
+        CK(cudaMemcpyAsync(c->own_minim, minimizer, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->own_klo, kmer_lo, E * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (kmer_hi) CK(cudaMemcpyAsync(c->own_khi, kmer_hi, E * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    }
+    c->has_hi = kmer_hi != nullptr;
+    c->cmp.minim = c->own_minim; c->cmp.klo = c->own_klo; c->cmp.khi = c->own_khi;
+    return finish_cmp_load(c, n_sketches, sketch_off);
+}
+
+extern "C" int spsp_cmp_load_device(spsp_ctx *c, uint32_t n_sketches, const uint64_t *sketch_off_host,
+                                    const uint32_t *d_minimizer, const uint64_t *d_kmer_lo, const uint64_t *d_kmer_hi)
+{
+    if (!c || !sketch_off_host) return fail(-3, "spsp_cmp_load_device: bad args");
+    if ((c->k > 32) != (d_kmer_hi != nullptr)) return fail(-3, "spsp_cmp_load_device: kmer_hi must be given iff k > 32");
+    CK(cudaSetDevice(c->device));
+    free_cmp(c);
+    c->has_hi = d_kmer_hi != nullptr;
+    c->cmp.minim = d_minimizer; c->cmp.klo = d_kmer_lo; c->cmp.khi = d_kmer_hi;
+    return finish_cmp_load(c, n_sketches, sketch_off_host);
+}
+
+static int cmp_run_impl(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint32_t col_end,
+                        int symmetric, uint32_t tile_rank, uint32_t tile_ranks, uint32_t *d_out, uint64_t ld)
+{
+    if (row_end > c->n_sketches || col_end > c->n_sketches || row_begin > row_end || col_begin > col_end)
+        return fail(-3, "spsp_cmp_run: range outside the loaded sketches");
+    if (ld < (uint64_t)(col_end - col_begin)) return fail(-3, "spsp_cmp_run: ld too small");
+    if (tile_ranks == 0 || tile_rank >= tile_ranks) return fail(-3, "spsp_cmp_run: bad tile rank");
+    if (symmetric && (row_begin != col_begin || row_end != col_end))
+        return fail(-3, "spsp_cmp_run: symmetric needs identical row and column ranges");
+    cudaStream_t st = c->slots[0].stream;
+    uint32_t nI = (row_end - row_begin + 31) / 32, nJ = (col_end - col_begin + 31) / 32;
+    std::vector<uint2> tiles;
+    uint64_t t = 0;
+    for (uint32_t ib = 0; ib < nI; ib++)
+        for (uint32_t jb = symmetric ? ib : 0; jb < nJ; jb++, t++)
+            if (t % tile_ranks == tile_rank) tiles.push_back(make_uint2(ib, jb));
+    CK(cudaEventRecord(c->cev0, st));
+    if (!tiles.empty()) {
+        uint2 *d_tiles = nullptr;
+        CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(uint2)));
+        CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->cev0, st));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        uint64_t groups = (4ull * sms + tiles.size() - 1) / tiles.size();
+        if (groups < 1) groups = 1;
+        if (groups > c->n_chunks) groups = c->n_chunks;
+        CK(launch_hashjoin(c->cmp, c->has_hi, d_tiles, (uint32_t)tiles.size(), c->n_chunks, (uint32_t)groups, row_begin,
+                           row_end, col_begin, col_end, d_out, ld, st));
+        c->launches++;
+        CK(cudaEventRecord(c->cev1, st));
+        CK(cudaStreamSynchronize(st));      // d_tiles and the host vector must outlive the launch
+        CK(cudaFree(d_tiles));
+    } else {
+        CK(cudaEventRecord(c->cev1, st));
+    }
+    c->cmp_timed = true;
+    return 0;
+}
+
+extern "C" int spsp_cmp_run_device(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t col_begin,
+                                   uint32_t col_end, int symmetric, uint32_t tile_rank, uint32_t tile_ranks,
+                                   uint32_t *d_out, uint64_t ld)
+{
+    if (!c || !d_out) return fail(-3, "spsp_cmp_run_device: bad args");
+    CK(cudaSetDevice(c->device));
+    return cmp_run_impl(c, row_begin, row_end, col_begin, col_end, symmetric, tile_rank, tile_ranks, d_out, ld);
+}
+
+extern "C" int spsp_cmp_run(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint32_t col_end,
+                            int symmetric, uint32_t tile_rank, uint32_t tile_ranks, uint32_t *out, uint64_t ld)
+{
+    if (!c || !out) return fail(-3, "spsp_cmp_run: bad args");
+    CK(cudaSetDevice(c->device));
+    uint64_t rows = row_end - row_begin, cols = col_end - col_begin;
+    if (!rows || !cols) return 0;
+    cudaStream_t st = c->slots[0].stream;
+    uint32_t *d_out = nullptr;
+    CK(cudaMalloc(&d_out, rows * cols * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(d_out, 0, rows * cols * sizeof(uint32_t), st));
+    int rc = cmp_run_impl(c, row_begin, row_end, col_begin, col_end, symmetric, tile_rank, tile_ranks, d_out, cols);
+    if (rc) { cudaFree(d_out); return rc; }
+    std::vector<uint32_t> tmp(rows * cols);
+    CK(cudaMemcpyAsync(tmp.data(), d_out, rows * cols * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_out));
+    for (uint64_t r = 0; r < rows; r++)
+        for (uint64_t q = 0; q < cols; q++) out[r * ld + q] += tmp[r * cols + q];
+    return 0;
+}
+
+extern "C" int spsp_cmp_last_kernel_ms(spsp_ctx *c, float *ms)
+{
+    if (!c || !ms) return fail(-3, "spsp_cmp_last_kernel_ms: bad args");
+    if (!c->cmp_timed) return fail(-3, "no compare launched");
+    CK(cudaEventSynchronize(c->cev1));
+    CK(cudaEventElapsedTime(ms, c->cev0, c->cev1));
+    return 0;
+}
+
+extern "C" int spsp_launch_count(spsp_ctx *c, uint64_t *n)
+{
+    if (!c || !n) return fail(-3, "spsp_launch_count: bad args");
+    *n = c->launches;
+    return 0;
+}

@@ -1,0 +1,161 @@
+#include "sketchfile.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace spsp_host {
+
+typedef unsigned __int128 u128;
+
+namespace {
+
+inline uint64_t rc_bits64(uint64_t x)
+{
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    return __builtin_bswap64(x) ^ 0xAAAAAAAAAAAAAAAAULL;
+}
+inline uint64_t canon(uint64_t x, int n)
+{
+    uint64_t r = rc_bits64(x) >> (64 - 2 * n);
+    return x < r ? x : r;
+}
+inline u128 canon(u128 x, int n)
+{
+    u128 r = (((u128)rc_bits64((uint64_t)x) << 64) | rc_bits64((uint64_t)(x >> 64))) >> (128 - 2 * n);
+    return x < r ? x : r;
+}
+
+inline void push_key(SketchElems &o, uint64_t v) { o.klo.push_back(v); }
+inline void push_key(SketchElems &o, u128 v) { o.klo.push_back((uint64_t)v); o.khi.push_back((uint64_t)(v >> 64)); }
+
+// All k-mers of a run of 2-bit codes (canonical) appended to keys.
+template <class Key>
+void kmers_of(const std::vector<uint8_t> &codes, int k, Key kmask, std::vector<Key> &keys)
+{
+    if ((int)codes.size() < k) return;
+    Key cur = 0;
+    for (int i = 0; i < k - 1; i++) cur = (cur << 2) | codes[i];
+    for (size_t i = (size_t)k - 1; i < codes.size(); i++) {
+        cur = ((cur << 2) | codes[i]) & kmask;
+        keys.push_back(canon(cur, k));
+    }
+}
+
+template <class Key>
+void decode_body(const uint8_t *p, size_t n, size_t pos, int k, int m, SketchElems &out)
+{
+    const int d = k - m;
+    const Key kmask = (((Key)1) << (2 * k)) - 1;
+    std::vector<uint8_t> sk, mcodes((size_t)m);
+    std::vector<Key> keys;
+    while (pos + (size_t)m <= n) {
+        uint32_t minimizer = 0;
+        for (int i = 0; i < m; i++) {
+            mcodes[i] = (p[pos + i] >> 1) & 3;           // str2num, utils.cpp:158-165
+            minimizer = (minimizer << 2) | mcodes[i];
+        }
+        pos += (size_t)m;
+        uint32_t sz = 0;
+        if (pos + 4 <= n) { memcpy(&sz, p + pos, 4); pos += 4; } else { pos = n; }
+        if ((size_t)sz > n - pos) sz = (uint32_t)(n - pos);
+        keys.clear();
+        // maximal super-k-mers: [mod byte][4 bases / byte]; every 2d bases are
+        // prefix(d) + suffix(d) around the minimizer (strDecompressor utils.cpp:71-111,
+        // inject_minimizer Comparator.cpp:78-92)
+        if (sz > 1) {
+            const uint8_t *q = p + pos;
+            unsigned mod = q[0];
+            size_t nbases = (mod == 0) ? ((size_t)sz - 1) * 4 : ((size_t)sz - 2) * 4 + mod;
+            const size_t full_bases = (mod == 0) ? nbases : ((size_t)sz - 2) * 4;
+            auto code_at = [&](size_t i) -> uint8_t {
+                if (i < full_bases) return (q[1 + (i >> 2)] >> (6 - 2 * (i & 3))) & 3;
+                return (q[sz - 1] >> (2 * (mod - (i - full_bases)))) & 3;   // trailing partial byte
+            };
+            for (size_t b = 0; b + 2 * (size_t)d <= nbases; b += 2 * (size_t)d) {
+                sk.clear();
+                for (int i = 0; i < d; i++) sk.push_back(code_at(b + i));
+                sk.insert(sk.end(), mcodes.begin(), mcodes.end());
+                for (int i = 0; i < d; i++) sk.push_back(code_at(b + d + i));
+                kmers_of<Key>(sk, k, kmask, keys);
+            }
+        }
+        pos += sz;
+        // non-maximal super-k-mers: "prefix\nsuffix\n" pairs until two empty lines
+        for (;;) {
+            size_t a0 = pos; while (pos < n && p[pos] != '\n') pos++;
+            size_t a1 = pos; if (pos < n) pos++;
+            size_t b0 = pos; while (pos < n && p[pos] != '\n') pos++;
+            size_t b1 = pos; if (pos < n) pos++;
+            if (a1 == a0 && b1 == b0) break;
+            sk.clear();
+            for (size_t i = a0; i < a1; i++) sk.push_back((p[i] >> 1) & 3);
+            sk.insert(sk.end(), mcodes.begin(), mcodes.end());
+            for (size_t i = b0; i < b1; i++) sk.push_back((p[i] >> 1) & 3);
+            kmers_of<Key>(sk, k, kmask, keys);
+            if (pos >= n) break;
+        }
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        for (const Key &x : keys) { out.minim.push_back(minimizer); push_key(out, x); }
+    }
+}
+
+}  // namespace
+
+bool decode_sketch(const uint8_t *p, size_t n, SketchElems &out, std::string *err)
+{
+    out = SketchElems();
+    size_t pos = 0;
+    while (pos < n && p[pos] != '\n') pos++;
+    if (pos >= n || pos > 120) { if (err) *err = "no header line"; return false; }
+    char hdr[128];
+    memcpy(hdr, p, pos);
+    hdr[pos] = 0;
+    int L = 0, m = 0;
+    if (sscanf(hdr, "%d %d", &L, &m) != 2 || m < 1 || m > 15 || L <= m) {
+        if (err) *err = "bad header";
+        return false;
+    }
+    int k = (L + m) / 2;                 // Comparator.cpp:34
+    if (k > 63 || k <= m) { if (err) *err = "unsupported k"; return false; }
+    out.k = k; out.m = m;
+    pos++;
+    if (k <= 32) decode_body<uint64_t>(p, n, pos, k, m, out);
+    else decode_body<u128>(p, n, pos, k, m, out);
+    return true;
+}
+
+void format_csv(const std::vector<std::string> &names, uint32_t query_size, const uint32_t *inter, uint64_t ld,
+                bool row_major_full, const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision,
+                double min_threshold, std::vector<uint8_t> &out)
+{
+    const uint32_t n = (uint32_t)names.size();
+    auto put = [&](const char *s, size_t l) { out.insert(out.end(), s, s + l); };
+    for (uint32_t i = 0; i < n; i++) {
+        put(names[i].data(), names[i].size());
+        out.push_back(i + 1 == n ? '\n' : ',');
+    }
+    if (!jaccard) out.push_back('\n');                    // Comparator.cpp:373
+    char tmp[64];
+    for (uint32_t i = 0; i < n && i < query_size; i++)
+        for (uint32_t j = 0; j < n; j++) {
+            if (i == j) out.push_back('1');
+            else {
+                // all-vs-all results hold the pair at (min,max); query results hold row i fully
+                uint32_t c = row_major_full ? inter[(uint64_t)i * ld + j]
+                                            : (i < j ? inter[(uint64_t)i * ld + j] : inter[(uint64_t)j * ld + i]);
+                if (!c) out.push_back('0');
+                else {
+                    double sc = jaccard ? (double)c / (double)(sizes[i] + sizes[j] - c) : (double)c / (double)sizes[i];
+                    if (sc < min_threshold) out.push_back('0');
+                    else put(tmp, (size_t)snprintf(tmp, sizeof tmp, "%.*g", (int)precision, sc));
+                }
+            }
+            out.push_back(j + 1 == n ? '\n' : ',');
+        }
+}
+
+}  // namespace spsp_host

@@ -1,0 +1,236 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every call goes through
+the C ABI (include/spsp.h via ctypes, or the host layer that calls it) and is
+compared bit-exactly with the oracle / the reference goldens."""
+import gzip
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import supersampler_b200 as S
+from supersampler_b200 import capi, synth
+from tests.golden_inputs import COMPARE_CASES, SKETCH_CASES, build_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    S.build()
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def unpack(words, n):
+    w = np.asarray(words, np.uint32)
+    codes = ((w[:, None] >> (30 - 2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).reshape(-1)[:n]
+    return np.frombuffer(b"ACTG", np.uint8)[codes]
+
+
+def sorted_hits(h):
+    return np.sort(h, order="pos")
+
+
+@pytest.mark.parametrize("inp,k,m,s", [
+    ("c1", 31, 11, 1000), ("c1", 31, 11, 100), ("c1", 31, 13, 200), ("nasty", 31, 11, 10), ("nasty", 21, 9, 5),
+    ("nasty", 15, 5, 3), ("nasty", 63, 15, 10), ("reads", 31, 11, 50), ("multi", 31, 15, 20), ("tiny", 31, 11, 1000),
+    ("nasty", 31, 11, 1), ("multi", 17, 7, 2),
+])
+def test_scan_kernels_match_closed_form(inp, k, m, s, oracle):
+    """Dense and q-gram-filter kernels both emit exactly the closed-form hit set."""
+    words, nb, _ = S.pack_fasta(build_input(inp), k)
+    thr = S.threshold(k, m, s)
+    seq = unpack(words, nb)
+    pos, cn, rv, _ = oracle.hits(seq, m, thr)
+    ctx = S.DeviceContext(k, m, thr)
+    for mode in (capi.SCAN_DENSE, capi.SCAN_FILTER, capi.SCAN_AUTO):
+        ctx.config(mode)
+        h = sorted_hits(ctx.scan(words, nb))
+        assert h.size == pos.size, (mode, h.size, pos.size)
+        assert np.array_equal(h["pos"], pos)
+        assert np.array_equal(h["canon"], cn)
+        assert np.array_equal(h["rev"], rv.astype(np.uint32))
+    ctx.close()
+
+
+def test_scan_random_lengths(oracle):
+    """Ragged sizes around the 64-base thread chunk / tile boundaries."""
+    rng = np.random.default_rng(3)
+    for k, m, s in ((31, 11, 20), (21, 9, 3), (31, 15, 50)):
+        thr = S.threshold(k, m, s)
+        ctx = S.DeviceContext(k, m, thr)
+        for n in [0, 1, m - 1, m, m + 1, 63, 64, 65, 64 + m - 1, 127, 128, 4095, 4096, 4097, 16384 + 7, 65536 + 63,
+                  int(rng.integers(100000, 300000))]:
+            seq = synth.random_genome(n, int(rng.integers(1 << 30)))
+            fa = b">r\n" + seq.tobytes() + b"\n"
+            words, nb, _ = S.pack_fasta(fa, 1)
+            assert nb == n
+            pos, cn, rv, _ = oracle.hits(seq, m, thr)
+            for mode in (capi.SCAN_DENSE, capi.SCAN_FILTER):
+                ctx.config(mode)
+                h = sorted_hits(ctx.scan(words, nb))
+                assert np.array_equal(h["pos"], pos), (n, mode)
+                assert np.array_equal(h["canon"], cn)
+        ctx.close()
+
+
+@pytest.mark.parametrize("name", sorted(SKETCH_CASES))
+def test_sketch_bytes_match_reference(name, golden):
+    inp, k, m, s, a = SKETCH_CASES[name]
+    sk = S.sketch_buffers([build_input(inp)], k, m, s, a, threads=1)[0]
+    g = golden["sketch"][name]
+    assert len(sk) == g["len"]
+    assert sha(sk) == g["sha256"]
+
+
+def test_sketch_many_inputs_threads(golden):
+    """File-parallel workers on separate streams give the same bytes."""
+    names = [n for n in sorted(SKETCH_CASES) if SKETCH_CASES[n][1:] == (31, 11, 100, 1) or n.endswith("k31_m11_s100")]
+    names = [n for n in names if SKETCH_CASES[n][1:4] == (31, 11, 100)]
+    fas = [build_input(SKETCH_CASES[n][0]) for n in names] * 4
+    out = S.sketch_buffers(fas, 31, 11, 100, 1, threads=6)
+    for i, sk in enumerate(out):
+        assert sha(sk) == golden["sketch"][names[i % len(names)]]["sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(COMPARE_CASES))
+def test_compare_matches_reference(name, golden, oracle):
+    inputs, k, m, s, nq, prec, thr = COMPARE_CASES[name]
+    sks = S.sketch_buffers([build_input(i) for i in inputs], k, m, s, threads=4)
+    g = golden["compare"][name]
+    assert [sha(x) for x in sks] == g["sketch_sha256"]
+    q = nq if nq else len(inputs)
+    inter, sizes, full = S.compare_buffers(sks, q)
+    o_inter, o_sizes, _, _ = oracle.compare(sks, q)
+    assert np.array_equal(sizes, o_sizes)
+    if full:
+        want = (o_inter + o_inter.T)[:q]
+        got = inter.copy()
+        np.fill_diagonal(got[:, :q], 0)
+        assert np.array_equal(got, want)
+    else:
+        assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    names = [i + ".gz" for i in inputs]
+    cont = S.format_csv(names, q, inter, full, sizes, False, prec, thr)
+    jac = S.format_csv(names, q, inter, full, sizes, True, prec, thr)
+    assert sha(cont) == g["containment_sha256"]
+    assert sha(jac) == g["jaccard_sha256"]
+
+
+def test_compare_k63_and_multi_tile(oracle):
+    """k > 32 (128-bit keys) and more than one 32x32 tile, ragged last tile."""
+    fas = [synth.fasta_bytes([(nm, g)]) for nm, g in synth.genome_family(70, 40_000, seed=9)]
+    for k, m, s in ((63, 15, 6), (31, 11, 8)):
+        sks = S.sketch_buffers(fas, k, m, s, threads=8)
+        for i in (0, 17, 69):
+            assert sks[i] == oracle.sketch(fas[i], k, m, s)[0]
+        inter, sizes, full = S.compare_buffers(sks)
+        o_inter, o_sizes, _, _ = oracle.compare(sks)
+        assert not full
+        assert np.array_equal(sizes, o_sizes)
+        assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+        # query mode: 5 queries against all
+        inter, sizes, full = S.compare_buffers(sks, 5)
+        assert full
+        want = (o_inter + o_inter.T)[:5]
+        got = inter.copy()
+        np.fill_diagonal(got[:, :5], 0)
+        assert np.array_equal(got, want)
+
+
+def test_compare_tile_ranks_partition(oracle):
+    """Tiles dealt to R ranks sum to the single-rank result (multi-GPU sharding logic)."""
+    fas = [synth.fasta_bytes([(nm, g)]) for nm, g in synth.genome_family(40, 30_000, seed=4)]
+    k, m, s = 31, 11, 10
+    sks = S.sketch_buffers(fas, k, m, s, threads=8)
+    el = [S.decode_sketch(x) for x in sks]
+    off = np.concatenate([[0], np.cumsum([e[2].size for e in el])]).astype(np.uint64)
+    mn = np.concatenate([e[2] for e in el]); lo = np.concatenate([e[3] for e in el])
+    ctx = S.DeviceContext(k, m, 0)
+    ctx.cmp_load(off, mn, lo)
+    n = len(sks)
+    whole = ctx.cmp_run((0, n), (0, n), True)
+    acc = np.zeros_like(whole)
+    for r in range(3):
+        acc += ctx.cmp_run((0, n), (0, n), True, r, 3)
+    assert np.array_equal(acc, whole)
+    o_inter, _, _, _ = oracle.compare(sks)
+    assert np.array_equal(np.triu(whole, 1), np.triu(o_inter, 1))
+    # a rectangular block
+    blk = ctx.cmp_run((3, 9), (10, 40), False)
+    assert np.array_equal(blk, (o_inter + o_inter.T)[3:9, 10:40])
+    ctx.close()
+
+
+def test_cli_end_to_end(tmp_path, golden):
+    """The drop-in executables: same flags, files in the CWD, gz outputs."""
+    exe_s = os.path.join(capi.BIN_DIR, "sub_sampler")
+    exe_c = os.path.join(capi.BIN_DIR, "comparator")
+    name = "fam12_s100"
+    inputs, k, m, s, nq, prec, thr = COMPARE_CASES[name]
+    paths = []
+    for i, inp in enumerate(inputs):
+        p = tmp_path / (inp + (".fa.gz" if i % 2 else ".fa"))
+        data = build_input(inp)
+        if i % 2:
+            with gzip.open(p, "wb", compresslevel=1) as f:
+                f.write(data)
+        else:
+            p.write_bytes(data)
+        paths.append(str(p))
+    fof = tmp_path / "genomes.txt"
+    fof.write_text("\n".join(paths) + "\n")
+    r = subprocess.run([exe_s, "-f", str(fof), "-k", str(k), "-m", str(m), "-s", str(s), "-t", "4", "-v", "0"],
+                       cwd=tmp_path, stdin=subprocess.DEVNULL, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out_fof = tmp_path / "subsampled_genomes.txt"
+    listed = out_fof.read_text().split()
+    assert listed == ["subsampled_" + inp + ".gz" for inp in inputs]
+    g = golden["compare"][name]
+    for inp, want in zip(inputs, g["sketch_sha256"]):
+        with gzip.open(tmp_path / ("subsampled_" + inp + ".gz"), "rb") as f:
+            assert sha(f.read()) == want
+    # comparator reads names relative to the CWD; rename to the golden's names
+    for inp in inputs:
+        os.rename(tmp_path / ("subsampled_" + inp + ".gz"), tmp_path / (inp + ".gz"))
+    sk_fof = tmp_path / "sk.txt"
+    sk_fof.write_text("\n".join(inp + ".gz" for inp in inputs) + "\n")
+    r = subprocess.run([exe_c, "-f", "sk.txt", "-o", "res"], cwd=tmp_path, stdin=subprocess.DEVNULL,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with gzip.open(tmp_path / "res_containment.csv.gz", "rb") as f:
+        assert sha(f.read()) == g["containment_sha256"]
+    with gzip.open(tmp_path / "res_jaccard.csv.gz", "rb") as f:
+        assert sha(f.read()) == g["jaccard_sha256"]
+    # single-input mode + in-process entry point
+    os.chdir(tmp_path)
+    assert S.run_sub_sampler(["-i", paths[0], "-k", str(k), "-m", str(m), "-s", str(s), "-p", "one_", "-v", "0"]) == 0
+    with gzip.open(tmp_path / ("one_" + inputs[0] + ".gz"), "rb") as f:
+        assert sha(f.read()) == g["sketch_sha256"][0]
+
+
+def test_full_size_properties(oracle):
+    """BASELINE config 2 shape (64 x 5 Mbp is bench territory; here 16 x 5 Mbp):
+    size-independent properties + spot checks against the oracle."""
+    fas = [synth.fasta_bytes([(nm, g)]) for nm, g in synth.genome_family(16, 5_000_000, seed=42)]
+    k, m, s = 31, 11, 1000
+    sks = S.sketch_buffers(fas, k, m, s, threads=8)
+    again = S.sketch_buffers(fas[::-1], k, m, s, threads=3)[::-1]
+    assert sks == again                                   # deterministic, order independent
+    for i in (0, 7, 15):
+        assert sks[i] == oracle.sketch(fas[i], k, m, s)[0]
+    inter, sizes, _ = S.compare_buffers(sks)
+    o_inter, o_sizes, _, _ = oracle.compare(sks)
+    assert np.array_equal(sizes, o_sizes)
+    assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    # self-comparison: a sketch against itself shares everything
+    inter2, sizes2, _ = S.compare_buffers([sks[0], sks[0], sks[1]])
+    assert inter2[0, 1] == sizes2[0] == sizes2[1]
+    assert inter2[0, 2] == inter2[1, 2] == inter[0, 1]
+    # intersections never exceed the smaller set
+    iu = np.triu_indices(len(sks), 1)
+    assert (inter[iu] <= np.minimum(sizes[iu[0]], sizes[iu[1]])).all()

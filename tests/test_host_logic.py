@@ -1,0 +1,139 @@
+"""CPU tests of the product's host layer (libspsp_host.so): FASTA cleaner/packer,
+the exact post-pass (sparse replay -> sketch bytes), the sketch decoder and the
+CSV writer.  The GPU's job -- the hit list -- is supplied here by the oracle's
+closed form (checker input only), so the bytes can be compared with the
+reference goldens without a GPU."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import supersampler_b200 as S
+from tests.conftest import GOLDEN_DIR
+from tests.golden_inputs import COMPARE_CASES, SKETCH_CASES, build_input
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    S.build()
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def unpack(words, n):
+    w = np.asarray(words, np.uint32)
+    codes = ((w[:, None] >> (30 - 2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).reshape(-1)[:n]
+    return np.frombuffer(b"ACTG", np.uint8)[codes]
+
+
+def oracle_hits(oracle, words, n_bases, m, thr):
+    """Closed-form hits over the whole packed buffer (records ignored, like the kernel)."""
+    seq = unpack(words, n_bases)
+    pos, cn, rv, _ = oracle.hits(seq, m, thr)
+    h = np.zeros(pos.size, S.HIT_DTYPE)
+    h["pos"], h["canon"], h["rev"] = pos, cn, rv
+    return h
+
+
+@pytest.mark.parametrize("inp", ["nasty", "multi", "noheader", "empty", "tiny", "reads", "wrap257"])
+def test_packer_matches_clean_dna(inp, oracle):
+    fa = build_input(inp)
+    for k in (1, 21, 31):
+        words, nb, offs = S.pack_fasta(fa, k)
+        bases, o = oracle.clean(fa)
+        keep = [(int(o[i]), int(o[i + 1])) for i in range(len(o) - 1) if int(o[i + 1]) - int(o[i]) >= k]
+        want = np.concatenate([bases[a:b] for a, b in keep]) if keep else np.zeros(0, np.uint8)
+        assert nb == want.size
+        assert np.array_equal(unpack(words, nb), want)
+        assert list(np.diff(offs.astype(np.int64))) == [b - a for a, b in keep]
+        assert words.size == S.packed_words(nb)
+        # zero padding behind the last base
+        tail = unpack(words, words.size * 16)[nb:]
+        assert (tail == ord("A")).all()
+
+
+def test_packer_streaming_chunks(oracle):
+    """Same result whatever the chunking (state machine across buffer boundaries)."""
+    fa = build_input("nasty")
+    ref = S.pack_fasta(fa, 31)
+    crlf = fa.replace(b"\n", b"\r\n")
+    w2, nb2, o2 = S.pack_fasta(crlf, 31)
+    assert nb2 == ref[1] and np.array_equal(w2, ref[0]) and np.array_equal(o2, ref[2])
+
+
+@pytest.mark.parametrize("name", sorted(SKETCH_CASES))
+def test_postpass_reproduces_reference_sketch(name, golden, oracle):
+    inp, k, m, s, a = SKETCH_CASES[name]
+    fa = build_input(inp)
+    words, nb, offs = S.pack_fasta(fa, k)
+    thr = S.threshold(k, m, s)
+    assert thr == oracle.threshold(k, m, s)
+    hits = oracle_hits(oracle, words, nb, m, thr)
+    rng = np.random.default_rng(0)
+    rng.shuffle(hits)                       # the kernel's output is unordered
+    sk, nsel = S.postpass(words, offs, hits, k, m, s, a)
+    g = golden["sketch"][name]
+    assert len(sk) == g["len"]
+    assert sk.split(b"\n", 1)[0].decode() == g["header"]
+    assert sha(sk) == g["sha256"]
+
+
+def _decode_all(sks):
+    el = [S.decode_sketch(x) for x in sks]
+    return el
+
+
+def _intersections(el):
+    n = len(el)
+    inter = np.zeros((n, n), np.uint32)
+    keys = []
+    for k, m, mn, lo, hi in el:
+        rec = np.zeros(mn.size, dtype=[("m", "<u4"), ("h", "<u8"), ("l", "<u8")])
+        rec["m"], rec["l"] = mn, lo
+        if hi is not None:
+            rec["h"] = hi
+        assert np.unique(rec).size == rec.size          # elements are distinct
+        assert (np.diff(mn.astype(np.int64)) >= 0).all()  # buckets ascending
+        keys.append(rec)
+    for i in range(n):
+        for j in range(i + 1, n):
+            inter[i, j] = np.intersect1d(keys[i], keys[j]).size
+    return inter, np.array([x.size for x in keys], np.uint64)
+
+
+@pytest.mark.parametrize("name", sorted(COMPARE_CASES))
+def test_decode_and_csv_match_reference(name, golden, oracle):
+    inputs, k, m, s, nq, prec, thr = COMPARE_CASES[name]
+    sks = [oracle.sketch(build_input(i), k, m, s)[0] for i in inputs]
+    el = _decode_all(sks)
+    assert all(e[0] == k and e[1] == m for e in el)
+    inter, sizes = _intersections(el)
+    o_inter, o_sizes, _, _ = oracle.compare(sks, None)
+    assert np.array_equal(sizes, o_sizes)
+    assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    q = nq if nq else len(inputs)
+    names = [i + ".gz" for i in inputs]
+    g = golden["compare"][name]
+    if q == len(inputs):
+        cont = S.format_csv(names, q, inter, False, sizes, False, prec, thr)
+        jac = S.format_csv(names, q, inter, False, sizes, True, prec, thr)
+    else:
+        full = (inter + inter.T)[:q]
+        cont = S.format_csv(names, q, full, True, sizes, False, prec, thr)
+        jac = S.format_csv(names, q, full, True, sizes, True, prec, thr)
+    assert sha(cont) == g["containment_sha256"]
+    assert sha(jac) == g["jaccard_sha256"]
+
+
+def test_k63_elements_have_high_words(oracle):
+    sk = oracle.sketch(build_input("nasty"), 63, 15, 10)[0]
+    k, m, mn, lo, hi = S.decode_sketch(sk)
+    assert (k, m) == (63, 15) and hi is not None and hi.size == lo.size and hi.max() > 0
+
+
+def test_out_name_and_threshold():
+    assert S.threshold(31, 11, 1) == 2 ** 64 - 1
+    assert S.threshold(31, 11, 0.5) == 2 ** 64 - 1
