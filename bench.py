@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- sketch Gbp/s (+ all-vs-all compare pairs/s) of the SuperSampler
+hot path on B200, next to the reference's CPU path.
+
+One *step* = one pass of the hot path over one batch: sketch G synthetic
+genomes (default: BASELINE config 2, 64 x 5 Mbp, k31 m11 s1000) and compare
+the G sketches all-vs-all.
+
+  value : inputs (2-bit packed genomes) resident in HBM; per step: one scan
+          launch over the batch, hits D2H, exact host post-pass to sketch
+          bytes, sketch decode + upload + compare kernel + matrix D2H.
+  e2e   : the same work through the host API with HOST buffers: FASTA text in
+          host memory -> clean/pack into pinned memory -> H2D -> scan -> D2H ->
+          post-pass -> compare; copies inside the timed region.
+  --impl reference : the unmodified reference binaries (oracle/_ref, built from
+          /root/reference in the build container) on this box's host cores,
+          same files / parameters; C restatement if the binaries are absent.
+
+Launch:  python bench.py --gpus N --steps K --warmup W        (N=1)
+         python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+Rank 0 prints ONE JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "sketch_gbp_per_s"
+UNIT = "Gbp/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ data
+
+def make_fastas(n_genomes: int, n_bases: int, first: int, seed: int = 42):
+    from supersampler_b200 import synth
+    fam = synth.Family(n_bases, seed)
+    return [fam.fasta(first + i) for i in range(n_genomes)], [f"g{first + i:05d}" for i in range(n_genomes)]
+
+
+def write_files(fastas, names, d):
+    paths = []
+    for fa, nm in zip(fastas, names):
+        p = os.path.join(d, nm + ".fa")
+        with open(p, "wb") as f:
+            f.write(fa)
+        paths.append(p)
+    return paths
+
+
+def scratch_dir():
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    return tempfile.mkdtemp(prefix="spsp_bench_", dir=base)
+
+
+# ------------------------------------------------------- reference CPU path
+
+def run_reference_step(paths, args, wd, cores):
+    """One pass of the reference's own path: sub_sampler -f ... -t cores, then comparator.
+    Returns (sketch_seconds, compare_seconds_total, 'Comparisons lasted' seconds, kind)."""
+    from oracle import oracle as O
+    for f in os.listdir(wd):
+        if f.startswith("subsampled_") or f.startswith("res_"):
+            os.remove(os.path.join(wd, f))
+    if O.have_ref():
+        fof = os.path.join(wd, "in.txt")
+        with open(fof, "w") as f:
+            f.write("\n".join(paths) + "\n")
+        t0 = time.perf_counter()
+        subprocess.run([os.path.join(O.REF_DIR, "sub_sampler"), "-f", fof, "-k", str(args.k), "-m", str(args.m),
+                        "-s", str(args.s), "-t", str(cores), "-v", "0"], cwd=wd, stdin=subprocess.DEVNULL,
+                       stdout=subprocess.DEVNULL, check=True)
+        t1 = time.perf_counter()
+        sk = [os.path.join(wd, "subsampled_" + os.path.basename(p).split(".")[0] + ".gz") for p in paths]
+        skf = os.path.join(wd, "sk.txt")
+        with open(skf, "w") as f:
+            f.write("\n".join(sk) + "\n")
+        r = subprocess.run([os.path.join(O.REF_DIR, "comparator"), "-f", skf, "-o", os.path.join(wd, "res")], cwd=wd,
+                           stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, text=True, check=True)
+        t2 = time.perf_counter()
+        lasted = None
+        for ln in r.stdout.splitlines():
+            if ln.startswith("Comparisons lasted"):
+                lasted = float(ln.split()[2])
+        return t1 - t0, t2 - t1, lasted, "reference"
+    # C restatement (single-threaded per call; ctypes drops the GIL so threads scale)
+    from concurrent.futures import ThreadPoolExecutor
+    datas = [open(p, "rb").read() for p in paths]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        sks = list(ex.map(lambda d: O.sketch(d, args.k, args.m, args.s)[0], datas))
+    t1 = time.perf_counter()
+    O.compare(sks)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, t2 - t1, "port"
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build(with_ref=os.path.isdir(O.REFERENCE_SRC))
+    cores = os.cpu_count() or 1
+    fastas, names = make_fastas(args.genomes, args.bases, 0)
+    total_bases = args.genomes * args.bases
+    wd = scratch_dir()
+    try:
+        paths = write_files(fastas, names, wd)
+        del fastas
+        for _ in range(args.warmup):
+            run_reference_step(paths, args, wd, cores)
+        ts, tc, tl, kind = [], [], [], "reference"
+        t_all0 = time.perf_counter()
+        for _ in range(args.steps):
+            a, b, c, kind = run_reference_step(paths, args, wd, cores)
+            ts.append(a); tc.append(b); tl.append(c if c is not None else b)
+        t_all = time.perf_counter() - t_all0
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    step = t_all / args.steps
+    pairs = args.genomes * (args.genomes - 1) // 2
+    value = total_bases / step / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "sketch_only_gbp_per_s": total_bases / statistics.mean(ts) / 1e9,
+        "compare": {"pairs": pairs, "pairs_per_s": pairs / statistics.mean(tl), "seconds": statistics.mean(tl),
+                    "note": "reference comparator is single-threaded; time = its own 'Comparisons lasted' line"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"full workload: {args.genomes} x {args.bases} bp, sub_sampler -f -t {cores} + comparator, files on tmpfs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"C2: file-of-files of {args.genomes} synthetic {args.bases} bp genomes per GPU "
+                        f"(one ancestor, substitution rate 10^U(-3,-1)), sketch + all-vs-all",
+            "k": args.k, "m": args.m, "s": args.s, "genomes_per_gpu": args.genomes, "bases_per_genome": args.bases,
+            "ranks": world,
+            "l2": "device-resident inputs rotate over replicas totalling > 126 MB (L2) between timed iterations"}
+
+
+# ------------------------------------------------------------- B200 arm
+
+def b200_arm(args, rank, world, local_rank):
+    import torch
+    import supersampler_b200 as S
+    from supersampler_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    cores = os.cpu_count() or 1
+    threads = max(1, min(32, cores // world))
+    k, m, s = args.k, args.m, args.s
+    fastas, names = make_fastas(args.genomes, args.bases, rank * args.genomes)
+    total_bases_rank = sum(args.bases for _ in fastas)
+
+    sketcher = S.Sketcher(k, m, s, device=local_rank, threads=threads)
+    comparer = S.Comparer(1, threads)
+    dctx = sketcher.device_context()
+
+    # ---- device-resident inputs: all genomes packed back to back, R replicas
+    ws, base_off, nbs, ro, off = [], [], [], [], 0
+    for fa in fastas:
+        w, nb, offs = S.pack_fasta(fa, k)
+        ws.append(w); base_off.append(off); nbs.append(nb); ro.append(offs)
+        off += w.size * 16
+    packed = np.concatenate(ws + [np.zeros(64, np.uint32)])     # tail padding the kernels may read
+    del ws
+    n_total = (packed.size - 64) * 16            # one scan launch covers every genome (and the gaps between them)
+    rec_off = np.concatenate(ro)
+    rec_first = np.array([0] + list(np.cumsum([r.size for r in ro])), np.uint64)
+    base_off = np.array(base_off, np.uint64); nbs = np.array(nbs, np.uint64)
+    packed_bytes = packed.size * 4
+    replicas = max(2, int(np.ceil(160e6 / packed_bytes)) + 1)
+    h_packed = torch.from_numpy(packed.view(np.int32))
+    d_packed = [h_packed.cuda() for _ in range(replicas)]
+    thr = S.threshold(k, m, s)
+    exp_hits = int(n_total * (thr / 2.0 ** 64) * 2) + 65536
+    d_hits = torch.empty(exp_hits * 16, dtype=torch.uint8, device="cuda")
+    d_count = torch.zeros(1, dtype=torch.int64, device="cuda")
+    h_hits = torch.empty(exp_hits * 16, dtype=torch.uint8).pin_memory()
+    h_count = torch.zeros(1, dtype=torch.int64).pin_memory()
+    ext = torch.cuda.ExternalStream(dctx.stream(0))
+
+    stats = {"scan_ms": [], "cmp_ms": [], "hits": 0, "launches": 0, "sketch_s": [], "compare_s": []}
+
+    def resident_step(i, record):
+        t0 = time.perf_counter()
+        with torch.cuda.stream(ext):
+            dctx.scan_device(d_packed[i % replicas].data_ptr(), n_total, d_hits.data_ptr(), exp_hits, d_count.data_ptr(), 0)
+            h_count.copy_(d_count, non_blocking=True)
+            ext.synchronize()
+            n = int(h_count[0])
+            assert n <= exp_hits, "hit buffer too small"
+            h_hits[: n * 16].copy_(d_hits[: n * 16], non_blocking=True)
+            ext.synchronize()
+        hits = np.frombuffer(h_hits.numpy()[: n * 16].tobytes(), capi.HIT_DTYPE)
+        sks = S.postpass_batch(packed, base_off, nbs, rec_off, rec_first, hits, k, m, s, threads=threads)
+        t1 = time.perf_counter()
+        cinfo = {}
+        res = compare_step(sks, cinfo)
+        t2 = time.perf_counter()
+        if record:
+            stats["scan_ms"].append(dctx.scan_kernel_ms(0))
+            stats["cmp_ms"].append(cinfo.get("kernel_ms", 0.0))
+            stats["hits"] = n
+            stats["launches"] += 1 + cinfo.get("launches", 0)
+            stats["sketch_s"].append(t1 - t0); stats["compare_s"].append(t2 - t1)
+        return sks, res
+
+    def compare_step(sks, cinfo):
+        if dist is None:
+            return comparer.run(sks, info=cinfo)
+        from supersampler_b200 import distributed as D
+        return D.allgather_compare(sks, k, m, rank, world, dctx, cinfo)
+
+    def e2e_step(record):
+        info, cinfo = {}, {}
+        sks = sketcher.run(fastas, info=info)
+        res = compare_step(sks, cinfo)
+        if record:
+            stats.setdefault("e2e_launches", 0)
+            stats["e2e_launches"] += info.get("launches", 0) + cinfo.get("launches", 0)
+            stats["e2e_pack_s"] = info.get("pack_s"); stats["e2e_scan_s"] = info.get("scan_s")
+            stats["e2e_post_s"] = info.get("post_s")
+        return sks, res
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i, False)
+        barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(ext):
+            ev0.record()
+        out = None
+        for i in range(steps):
+            out = fn(warmup + i, True)
+        with torch.cuda.stream(ext):
+            ev1.record()
+        torch.cuda.synchronize(); barrier()
+        wall = time.perf_counter() - t0
+        dev = ev0.elapsed_time(ev1) / 1e3
+        t = torch.tensor([max(wall, dev)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_res, (sks_res, cmp_res) = timed(resident_step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    t_e2e, (sks_e2e, cmp_e2e) = timed(lambda i, rec: e2e_step(rec), args.steps, max(1, args.warmup - 2))
+
+    # both paths must produce the same bytes / counts
+    assert sks_res == sks_e2e, "device-resident and host-buffer paths disagree"
+    assert np.array_equal(cmp_res[0], cmp_e2e[0])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    n_gen_total = args.genomes * world
+    total_bases = total_bases_rank * world
+    pairs = n_gen_total * (n_gen_total - 1) // 2
+    step_s = t_res / args.steps
+    scan_ms = statistics.mean(stats["scan_ms"])
+    algo_bytes = n_total / 4 + 16 * stats["hits"]
+    achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
+    sizes = cmp_res[1]
+    elem_bytes = int(sizes.sum()) * 12
+    h2d = packed_bytes + elem_bytes
+    d2h = stats["hits"] * 16 + cmp_res[0].size * 4
+    line = {
+        "metric": METRIC, "value": total_bases / step_s / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": total_bases / (t_e2e / args.steps) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3, "host_threads": threads,
+                "pack_thread_s": stats.get("e2e_pack_s"), "scan_thread_s": stats.get("e2e_scan_s"),
+                "post_thread_s": stats.get("e2e_post_s")},
+        "gpu_launches": stats["launches"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "scan (q-gram filter or dense, see DESIGN.md)",
+                     "kernel_ms": scan_ms, "bases_per_launch": int(n_total), "hits_per_launch": int(stats["hits"]),
+                     "kernel_tbp_per_s": n_total / (scan_ms * 1e-3) / 1e12},
+        "phases_ms": {"sketch": statistics.mean(stats["sketch_s"]) * 1e3,
+                      "compare": statistics.mean(stats["compare_s"]) * 1e3,
+                      "scan_kernel": scan_ms, "compare_kernel": statistics.mean(stats["cmp_ms"])},
+        "compare": {"pairs": pairs, "pairs_per_s": pairs / statistics.mean(stats["compare_s"]),
+                    "kernel_pairs_per_s": pairs / max(1e-9, statistics.mean(stats["cmp_ms"]) * 1e-3),
+                    "elements": int(sizes.sum())},
+    }
+    # CPU baseline on this box's host cores (rank 0, N=1 only): the reference binaries on the same workload
+    if world == 1 and not args.no_cpu_baseline:
+        wd = scratch_dir()
+        try:
+            paths = write_files(fastas, names, wd)
+            a, b, c, kind = run_reference_step(paths, args, wd, cores)
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        line["cpu_baseline"] = {"value": total_bases / (a + b) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"full workload once: {args.genomes} x {args.bases} bp, sub_sampler -f -t {cores} "
+                                          f"({a:.2f} s) + comparator ({b:.2f} s, single-threaded by construction)",
+                                "sketch_gbp_per_s": total_bases / a / 1e9,
+                                "compare_pairs_per_s": pairs / (c if c else b)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genomes", type=int, default=64)
+    ap.add_argument("--bases", type=int, default=5_000_000)
+    ap.add_argument("-k", type=int, default=31)
+    ap.add_argument("-m", type=int, default=11)
+    ap.add_argument("-s", type=float, default=1000.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    import supersampler_b200 as S
+    if rank == 0:
+        S.build()
+    b200_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

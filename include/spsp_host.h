@@ -61,10 +61,41 @@ int spsph_sketch_buffers(int device, int k, int m, double s, unsigned abundance,
                          const uint8_t *const *fasta, const size_t *len, int threads, uint8_t **out, size_t *out_len,
                          double *timings, uint64_t *launches);
 
+/* Persistent sketcher: one device context + `threads` workers (one stream
+ * each), reused across calls -- what a long-running caller keeps around. */
+typedef struct spsph_sketcher spsph_sketcher;
+int spsph_sketcher_create(int device, int k, int m, double s, unsigned abundance, int scan_mode, int threads,
+                          spsph_sketcher **out);
+int spsph_sketcher_destroy(spsph_sketcher *sk);
+/* Same contract as spsph_sketch_buffers. */
+int spsph_sketcher_run(spsph_sketcher *sk, uint32_t n, const uint8_t *const *fasta, const size_t *len, uint8_t **out,
+                       size_t *out_len, double *timings, uint64_t *launches);
+/* The sketcher's device context (for device-resident scans through spsp.h). */
+spsp_ctx *spsph_sketcher_ctx(spsph_sketcher *sk);
+
+/* [cpu] Post-pass of a batch: `packed` holds n_inputs inputs back to back,
+ * input i starting at base offset base_off[i] (a multiple of 64) with
+ * rec_off[rec_first[i] .. rec_first[i+1]) as its n_rec_i + 1 record offsets
+ * (relative to base_off[i]; rec_first has n_inputs + 1 entries); hits are positions in the whole buffer (any order, e.g. one
+ * scan launch over everything).  Hits in the padding between inputs are
+ * ignored.  `threads` host workers; out[i]/out_len[i] as above. */
+int spsph_postpass_batch(const uint32_t *packed, uint32_t n_inputs, const uint64_t *base_off, const uint64_t *n_bases,
+                         const uint64_t *rec_off, const uint64_t *rec_first, const spsp_hit *hits, uint64_t n_hits,
+                         int k, int m, double s, unsigned abundance, int threads, uint8_t **out, size_t *out_len);
+
 /* GPU: all-vs-all (query_size == n) or query-vs-all compare of n sketches held
  * in memory.  inter: rows x n uint32 (rows = n or query_size), sizes: n. */
 int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size, const uint8_t *const *sketch, const size_t *len,
                           uint32_t *inter, uint64_t *sizes, int *full_rows, float *kernel_ms, uint64_t *launches);
+
+/* Persistent comparer: keeps its device context(s) between calls. */
+typedef struct spsph_comparer spsph_comparer;
+int spsph_comparer_create(int n_gpus, int threads, spsph_comparer **out);
+int spsph_comparer_destroy(spsph_comparer *c);
+/* Same contract as spsph_compare_buffers; timings (may be NULL): [0] = decode s, [1] = device s. */
+int spsph_comparer_run(spsph_comparer *c, uint32_t n, uint32_t query_size, const uint8_t *const *sketch,
+                       const size_t *len, uint32_t *inter, uint64_t *sizes, int *full_rows, float *kernel_ms,
+                       uint64_t *launches, double *timings);
 
 #ifdef __cplusplus
 }

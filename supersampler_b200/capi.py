@@ -95,6 +95,22 @@ def host_lib():
                                            C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_double),
                                            C.POINTER(C.c_uint64)]
+        L.spsph_sketcher_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int,
+                                            C.POINTER(C.c_void_p)]
+        L.spsph_sketcher_destroy.argtypes = [C.c_void_p]
+        L.spsph_sketcher_ctx.restype = C.c_void_p
+        L.spsph_sketcher_ctx.argtypes = [C.c_void_p]
+        L.spsph_sketcher_run.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_uint64)]
+        L.spsph_postpass_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.spsph_comparer_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.spsph_comparer_destroy.argtypes = [C.c_void_p]
+        L.spsph_comparer_run.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p),
+                                         C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                         C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.spsph_compare_buffers.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p),
                                             C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                             C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
@@ -203,6 +219,74 @@ def sketch_buffers(fastas: Sequence[bytes], k: int = 31, m: int = 11, s: float =
     return res
 
 
+class Sketcher:
+    """Persistent Subsampler workers on one device context (one stream per worker)."""
+
+    def __init__(self, k: int = 31, m: int = 11, s: float = 1000.0, abundance: int = 1, device: int = 0,
+                 threads: int = 8, scan_mode: int = SCAN_AUTO):
+        self.L = host_lib()
+        self.h = C.c_void_p()
+        self.k, self.m, self.s = k, m, s
+        _hcheck(self.L.spsph_sketcher_create(device, k, m, _f32(s), abundance, scan_mode, threads, C.byref(self.h)),
+                "sketcher_create")
+
+    def close(self):
+        if self.h:
+            self.L.spsph_sketcher_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, fastas: Sequence[bytes], info: Optional[dict] = None) -> List[bytes]:
+        n = len(fastas)
+        arr = (C.c_char_p * n)(*fastas)
+        lens = (C.c_size_t * n)(*[len(f) for f in fastas])
+        outs = (C.c_void_p * n)()
+        olens = (C.c_size_t * n)()
+        tim = (C.c_double * 3)()
+        nl = C.c_uint64()
+        _hcheck(self.L.spsph_sketcher_run(self.h, n, arr, lens, outs, olens, tim, C.byref(nl)), "sketcher_run")
+        res = []
+        for i in range(n):
+            res.append(C.string_at(outs[i], olens[i]) if olens[i] else b"")
+            self.L.spsph_free(outs[i])
+        if info is not None:
+            info.update(pack_s=tim[0], scan_s=tim[1], post_s=tim[2], launches=int(nl.value))
+        return res
+
+    def device_context(self) -> "DeviceContext":
+        """Borrowed view of the sketcher's spsp_ctx (not destroyed by the view)."""
+        return DeviceContext._borrow(self.L.spsph_sketcher_ctx(self.h), self.k, self.m)
+
+
+def postpass_batch(packed: np.ndarray, base_off: np.ndarray, n_bases: np.ndarray, rec_off: np.ndarray,
+                   rec_first: np.ndarray, hits: np.ndarray, k: int, m: int, s: float, abundance: int = 1,
+                   threads: int = 8) -> List[bytes]:
+    """[cpu] hits of one scan over several inputs packed back to back -> one sketch per input."""
+    L = host_lib()
+    n = int(np.asarray(base_off).size)
+    packed = np.ascontiguousarray(packed, np.uint32)
+    base_off = np.ascontiguousarray(base_off, np.uint64)
+    n_bases = np.ascontiguousarray(n_bases, np.uint64)
+    rec_off = np.ascontiguousarray(rec_off, np.uint64)
+    rec_first = np.ascontiguousarray(rec_first, np.uint64)
+    hits = np.ascontiguousarray(hits, HIT_DTYPE)
+    outs = (C.c_void_p * n)()
+    olens = (C.c_size_t * n)()
+    _hcheck(L.spsph_postpass_batch(packed.ctypes.data, n, base_off.ctypes.data, n_bases.ctypes.data,
+                                   rec_off.ctypes.data, rec_first.ctypes.data, hits.ctypes.data, hits.size, k, m,
+                                   _f32(s), abundance, threads, outs, olens), "postpass_batch")
+    res = []
+    for i in range(n):
+        res.append(C.string_at(outs[i], olens[i]) if olens[i] else b"")
+        L.spsph_free(outs[i])
+    return res
+
+
 def compare_buffers(sketches: Sequence[bytes], query_size: Optional[int] = None, n_gpus: int = 1,
                     info: Optional[dict] = None):
     """GPU: sketch bytes -> (inter[rows, n] uint32, sizes[n] uint64, full_rows)."""
@@ -220,6 +304,42 @@ def compare_buffers(sketches: Sequence[bytes], query_size: Optional[int] = None,
     if info is not None:
         info.update(kernel_ms=float(ms.value), launches=int(nl.value))
     return inter, sizes, bool(full.value)
+
+
+class Comparer:
+    """Persistent Comparator (keeps its device contexts between calls)."""
+
+    def __init__(self, n_gpus: int = 1, threads: int = 0):
+        self.L = host_lib()
+        self.h = C.c_void_p()
+        _hcheck(self.L.spsph_comparer_create(n_gpus, threads, C.byref(self.h)), "comparer_create")
+
+    def close(self):
+        if self.h:
+            self.L.spsph_comparer_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, sketches: Sequence[bytes], query_size: Optional[int] = None, info: Optional[dict] = None):
+        n = len(sketches)
+        q = n if query_size is None else query_size
+        arr = (C.c_char_p * n)(*sketches)
+        lens = (C.c_size_t * n)(*[len(x) for x in sketches])
+        rows = n if q >= n else q
+        inter = np.zeros((rows, n), np.uint32)
+        sizes = np.zeros(n, np.uint64)
+        full, ms, nl = C.c_int(), C.c_float(), C.c_uint64()
+        tim = (C.c_double * 2)()
+        _hcheck(self.L.spsph_comparer_run(self.h, n, q, arr, lens, inter.ctypes.data, sizes.ctypes.data,
+                                          C.byref(full), C.byref(ms), C.byref(nl), tim), "comparer_run")
+        if info is not None:
+            info.update(kernel_ms=float(ms.value), launches=int(nl.value), decode_s=tim[0], device_s=tim[1])
+        return inter, sizes, bool(full.value)
 
 
 def _run_main(fn, argv: Sequence[str]) -> int:
@@ -246,10 +366,19 @@ class DeviceContext:
         _dcheck(self.L.spsp_create(device, k, m, thr, n_slots, C.byref(self.h)), "spsp_create")
         self.k, self.m, self.thr = k, m, thr
 
+    @classmethod
+    def _borrow(cls, handle: int, k: int, m: int) -> "DeviceContext":
+        o = cls.__new__(cls)
+        o.L = device_lib()
+        o.h = C.c_void_p(handle)
+        o.k, o.m, o.thr = k, m, None
+        o._borrowed = True
+        return o
+
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.L.spsp_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -48,6 +48,7 @@ struct spsp_ctx {
     std::vector<Slot> slots;
     // q-gram filter
     bool filter_ready = false;
+    bool filter_tried = false;
     bool filter_profitable = false;
     FilterParams fp{};
     uint32_t *d_table = nullptr;
@@ -135,6 +136,14 @@ static int build_filter(spsp_ctx *c)
     return 0;
 }
 
+static int ensure_filter(spsp_ctx *c)
+{
+    std::lock_guard<std::mutex> g(c->mu);
+    if (c->filter_tried) return 0;
+    c->filter_tried = true;
+    return build_filter(c);
+}
+
 extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_slots, spsp_ctx **out)
 {
     if (!out) return fail(-3, "spsp_create: null out");
@@ -160,9 +169,7 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
     }
     CK(cudaEventCreate(&c->cev0));
     CK(cudaEventCreate(&c->cev1));
-    int rc = build_filter(c);
-    if (rc) { delete c; return rc; }
-    *out = c;
+    *out = c;                        // the q-gram filter table is built on first scan
     return 0;
 }
 
@@ -202,13 +209,22 @@ extern "C" int spsp_scan_config(spsp_ctx *c, int mode)
 {
     if (!c) return fail(-3, "null ctx");
     if (mode < SPSP_SCAN_AUTO || mode > SPSP_SCAN_FILTER) return fail(-3, "spsp_scan_config: bad mode");
-    if (mode == SPSP_SCAN_FILTER && !c->filter_ready) return fail(-3, "spsp_scan_config: filter unavailable for this m");
+    if (mode == SPSP_SCAN_FILTER) {
+        CK(cudaSetDevice(c->device));
+        int rc = ensure_filter(c);
+        if (rc) return rc;
+        if (!c->filter_ready) return fail(-3, "spsp_scan_config: filter unavailable for this m");
+    }
     c->mode = mode;
     return 0;
 }
 
 static int launch_scan(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n_bases, ScanOut out)
 {
+    if (c->mode != SPSP_SCAN_DENSE) {
+        int rc = ensure_filter(c);
+        if (rc) return rc;
+    }
     bool use_filter = c->mode == SPSP_SCAN_FILTER || (c->mode == SPSP_SCAN_AUTO && c->filter_ready && c->filter_profitable);
     CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned long long), s.stream));
     CK(cudaEventRecord(s.ev0, s.stream));

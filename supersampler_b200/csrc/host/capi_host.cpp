@@ -97,35 +97,67 @@ extern "C" int spsph_format_csv(const char *const *names, uint32_t n, uint32_t q
     } catch (const std::exception &e) { return hfail(e.what()); }
 }
 
-extern "C" int spsph_sketch_buffers(int device, int k, int m, double s, unsigned abundance, int scan_mode, uint32_t n,
-                                    const uint8_t *const *fasta, const size_t *len, int threads, uint8_t **out,
-                                    size_t *out_len, double *timings, uint64_t *launches)
+struct spsph_sketcher {
+    std::shared_ptr<DeviceSession> session;
+    std::vector<std::unique_ptr<Subsampler>> workers;
+    int k, m;
+    double s;
+};
+
+extern "C" int spsph_sketcher_create(int device, int k, int m, double s, unsigned abundance, int scan_mode, int threads,
+                                     spsph_sketcher **out)
 {
     try {
         if (threads < 1) threads = 1;
-        if ((uint32_t)threads > n) threads = (int)(n ? n : 1);
-        auto session = std::make_shared<DeviceSession>(device, k, m, compute_threshold(k, m, s), threads);
-        if (scan_mode != SPSP_SCAN_AUTO && spsp_scan_config(session->ctx(), scan_mode) != 0)
+        if (threads > 64) threads = 64;
+        auto sk = std::make_unique<spsph_sketcher>();
+        sk->k = k; sk->m = m; sk->s = s;
+        sk->session = std::make_shared<DeviceSession>(device, k, m, compute_threshold(k, m, s), threads);
+        if (scan_mode != SPSP_SCAN_AUTO && spsp_scan_config(sk->session->ctx(), scan_mode) != 0)
             return hfail(std::string("spsp_scan_config: ") + spsp_last_error());
+        for (int w = 0; w < threads; w++)
+            sk->workers.emplace_back(new Subsampler((uint64_t)k, (uint64_t)m, s, (uint64_t)threads, 3, abundance,
+                                                    sk->session, w));
+        *out = sk.release();
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_sketcher_destroy(spsph_sketcher *sk)
+{
+    delete sk;
+    return 0;
+}
+
+extern "C" spsp_ctx *spsph_sketcher_ctx(spsph_sketcher *sk) { return sk ? sk->session->ctx() : nullptr; }
+
+extern "C" int spsph_sketcher_run(spsph_sketcher *sk, uint32_t n, const uint8_t *const *fasta, const size_t *len,
+                                  uint8_t **out, size_t *out_len, double *timings, uint64_t *launches)
+{
+    try {
+        if (!sk) return hfail("null sketcher");
+        const int threads = (int)std::min<size_t>(sk->workers.size(), n ? n : 1);
+        uint64_t l0 = sk->session->launches();
         std::atomic<uint32_t> next{0};
         std::vector<std::string> errors((size_t)threads);
         std::vector<double> tp((size_t)threads, 0), ts((size_t)threads, 0), tq((size_t)threads, 0);
         std::vector<std::thread> pool;
-        for (int w = 0; w < threads; w++)
-            pool.emplace_back([&, w]() {
-                try {
-                    Subsampler ss((uint64_t)k, (uint64_t)m, s, (uint64_t)threads, 3, abundance, session, w);
-                    std::vector<uint8_t> sk;
-                    for (;;) {
-                        uint32_t i = next.fetch_add(1);
-                        if (i >= n) break;
-                        ss.sketch_buffer(fasta[i], len[i], sk);
-                        out[i] = dup_vec(sk.data(), sk.size());
-                        out_len[i] = sk.size();
-                        tp[(size_t)w] += ss.t_pack; ts[(size_t)w] += ss.t_scan; tq[(size_t)w] += ss.t_post;
-                    }
-                } catch (const std::exception &e) { errors[(size_t)w] = e.what(); }
-            });
+        auto work = [&](int w) {
+            try {
+                Subsampler &ss = *sk->workers[(size_t)w];
+                std::vector<uint8_t> o;
+                for (;;) {
+                    uint32_t i = next.fetch_add(1);
+                    if (i >= n) break;
+                    ss.sketch_buffer(fasta[i], len[i], o);
+                    out[i] = dup_vec(o.data(), o.size());
+                    out_len[i] = o.size();
+                    tp[(size_t)w] += ss.t_pack; ts[(size_t)w] += ss.t_scan; tq[(size_t)w] += ss.t_post;
+                }
+            } catch (const std::exception &e) { errors[(size_t)w] = e.what(); }
+        };
+        for (int w = 1; w < threads; w++) pool.emplace_back(work, w);
+        work(0);
         for (auto &t : pool) t.join();
         for (const auto &e : errors)
             if (!e.empty()) return hfail(e);
@@ -133,18 +165,101 @@ extern "C" int spsph_sketch_buffers(int device, int k, int m, double s, unsigned
             timings[0] = timings[1] = timings[2] = 0;
             for (int w = 0; w < threads; w++) { timings[0] += tp[(size_t)w]; timings[1] += ts[(size_t)w]; timings[2] += tq[(size_t)w]; }
         }
-        if (launches) *launches = session->launches();
+        if (launches) *launches = sk->session->launches() - l0;
         return 0;
     } catch (const std::exception &e) { return hfail(e.what()); }
 }
 
-extern "C" int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size, const uint8_t *const *sketch,
-                                     const size_t *len, uint32_t *inter, uint64_t *sizes, int *full_rows,
-                                     float *kernel_ms, uint64_t *launches)
+extern "C" int spsph_sketch_buffers(int device, int k, int m, double s, unsigned abundance, int scan_mode, uint32_t n,
+                                    const uint8_t *const *fasta, const size_t *len, int threads, uint8_t **out,
+                                    size_t *out_len, double *timings, uint64_t *launches)
+{
+    if (threads < 1) threads = 1;
+    if ((uint32_t)threads > n) threads = (int)(n ? n : 1);
+    spsph_sketcher *sk = nullptr;
+    int rc = spsph_sketcher_create(device, k, m, s, abundance, scan_mode, threads, &sk);
+    if (rc) return rc;
+    rc = spsph_sketcher_run(sk, n, fasta, len, out, out_len, timings, launches);
+    spsph_sketcher_destroy(sk);
+    return rc;
+}
+
+extern "C" int spsph_postpass_batch(const uint32_t *packed, uint32_t n_inputs, const uint64_t *base_off,
+                                    const uint64_t *n_bases, const uint64_t *rec_off, const uint64_t *rec_first,
+                                    const spsp_hit *hits, uint64_t n_hits, int k, int m, double s, unsigned abundance,
+                                    int threads, uint8_t **out, size_t *out_len)
 {
     try {
-        Comparator comp(6, 0.0);
-        comp.n_gpus = n_gpus;
+        // route every hit to its input (inputs are disjoint, ascending ranges)
+        std::vector<std::vector<spsp_hit>> per((size_t)n_inputs);
+        for (uint64_t h = 0; h < n_hits; h++) {
+            const uint64_t p = hits[h].pos;
+            uint32_t lo = 0, hi = n_inputs;          // last input with base_off <= p
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (base_off[mid] <= p) lo = mid; else hi = mid; }
+            if (n_inputs == 0 || p < base_off[lo] || p + (uint64_t)m > base_off[lo] + n_bases[lo]) continue;
+            spsp_hit x = hits[h];
+            x.pos -= base_off[lo];
+            per[lo].push_back(x);
+        }
+        SketchParams prm;
+        prm.k = k; prm.m = m; prm.s = s; prm.abundance = abundance; prm.threshold = compute_threshold(k, m, s);
+        if (threads < 1) threads = 1;
+        if ((uint32_t)threads > n_inputs) threads = (int)(n_inputs ? n_inputs : 1);
+        std::atomic<uint32_t> next{0};
+        std::vector<std::string> errors((size_t)threads);
+        auto work = [&](int w) {
+            try {
+                std::vector<uint8_t> o;
+                std::vector<uint64_t> ro;
+                for (;;) {
+                    uint32_t i = next.fetch_add(1);
+                    if (i >= n_inputs) break;
+                    ro.assign(rec_off + rec_first[i], rec_off + rec_first[i + 1]);
+                    o.clear();
+                    build_sketch(packed + base_off[i] / 16, ro, per[i], prm, o, nullptr);
+                    out[i] = dup_vec(o.data(), o.size());
+                    out_len[i] = o.size();
+                }
+            } catch (const std::exception &e) { errors[(size_t)w] = e.what(); }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < threads; w++) pool.emplace_back(work, w);
+        work(0);
+        for (auto &t : pool) t.join();
+        for (const auto &e : errors)
+            if (!e.empty()) return hfail(e);
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+struct spsph_comparer {
+    Comparator comp{6, 0.0};
+};
+
+extern "C" int spsph_comparer_create(int n_gpus, int threads, spsph_comparer **out)
+{
+    try {
+        auto c = std::make_unique<spsph_comparer>();
+        c->comp.n_gpus = n_gpus < 1 ? 1 : n_gpus;
+        c->comp.n_threads = threads;
+        *out = c.release();
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_comparer_destroy(spsph_comparer *c)
+{
+    delete c;
+    return 0;
+}
+
+extern "C" int spsph_comparer_run(spsph_comparer *c, uint32_t n, uint32_t query_size, const uint8_t *const *sketch,
+                                  const size_t *len, uint32_t *inter, uint64_t *sizes, int *full_rows,
+                                  float *kernel_ms, uint64_t *launches, double *timings)
+{
+    try {
+        if (!c) return hfail("null comparer");
+        Comparator &comp = c->comp;
         std::vector<std::string> names(n);
         std::vector<const uint8_t *> data(sketch, sketch + n);
         std::vector<size_t> ln(len, len + n);
@@ -154,6 +269,19 @@ extern "C" int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size
         if (full_rows) *full_rows = comp.full_rows ? 1 : 0;
         if (kernel_ms) *kernel_ms = comp.kernel_ms;
         if (launches) *launches = comp.launches;
+        if (timings) { timings[0] = comp.t_load; timings[1] = comp.t_compare; }
         return 0;
     } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size, const uint8_t *const *sketch,
+                                     const size_t *len, uint32_t *inter, uint64_t *sizes, int *full_rows,
+                                     float *kernel_ms, uint64_t *launches)
+{
+    spsph_comparer *c = nullptr;
+    int rc = spsph_comparer_create(n_gpus, 0, &c);
+    if (rc) return rc;
+    rc = spsph_comparer_run(c, n, query_size, sketch, len, inter, sizes, full_rows, kernel_ms, launches, nullptr);
+    spsph_comparer_destroy(c);
+    return rc;
 }

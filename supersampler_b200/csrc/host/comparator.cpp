@@ -85,6 +85,8 @@ void Comparator::compare_sketches(unsigned size_query)
     query_size = q;
     t_load = secs(t0, clk::now());
     run_device(kept);
+    std::cout << "kmers evaluated are of length: " << k << " minimizer size is " << m << std::endl;
+    std::cout << "Comparisons done" << std::endl;
 }
 
 void Comparator::compare_buffers(const std::vector<std::string> &names, const std::vector<const uint8_t *> &data,
@@ -93,11 +95,25 @@ void Comparator::compare_buffers(const std::vector<std::string> &names, const st
     auto t0 = clk::now();
     files_names = names;
     query_size = size_query;
-    std::vector<SketchElems> sk(names.size());
-    for (size_t i = 0; i < names.size(); i++) {
-        std::string err;
-        if (!decode_sketch(data[i], len[i], sk[i], &err)) throw std::runtime_error("sketch " + names[i] + ": " + err);
-    }
+    const size_t n = names.size();
+    std::vector<SketchElems> sk(n);
+    std::vector<std::string> errs(n);
+    std::atomic<size_t> next{0};
+    unsigned nw = worker_count(n_threads, n);
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            std::string err;
+            if (!decode_sketch(data[i], len[i], sk[i], &err)) errs[i] = err.empty() ? "undecodable" : err;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < nw; w++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (!errs[i].empty()) throw std::runtime_error("sketch " + names[i] + ": " + errs[i]);
     t_load = secs(t0, clk::now());
     run_device(sk);
 }
@@ -116,7 +132,6 @@ void Comparator::run_device(std::vector<SketchElems> &sk)
     for (uint32_t i = 0; i < n; i++)
         if ((uint64_t)sk[i].k != k || (uint64_t)sk[i].m != m)
             throw std::runtime_error("sketches were built with different k/m");
-    std::cout << "kmers evaluated are of length: " << k << " minimizer size is " << m << std::endl;
     std::vector<uint64_t> off(n + 1, 0);
     for (uint32_t i = 0; i < n; i++) {
         nb_kmer_seen_infile[i] = sk[i].size();
@@ -145,9 +160,16 @@ void Comparator::run_device(std::vector<SketchElems> &sk)
     std::vector<std::vector<uint32_t>> part((size_t)g);
     std::vector<float> kms((size_t)g, 0.f);
     std::vector<uint64_t> nl((size_t)g, 0);
+    if (sess_k_ != k || sess_m_ != m || (int)sessions_.size() != g) {
+        sessions_.clear();
+        for (int dev = 0; dev < g; dev++) sessions_.push_back(std::make_shared<DeviceSession>(dev, (int)k, (int)m, 0, 1));
+        sess_k_ = k; sess_m_ = m;
+    }
+    std::vector<uint64_t> l0((size_t)g, 0);
+    for (int dev = 0; dev < g; dev++) l0[(size_t)dev] = sessions_[(size_t)dev]->launches();
     auto work = [&](int dev) {
         try {
-            DeviceSession session(dev, (int)k, (int)m, 0, 1);
+            DeviceSession &session = *sessions_[(size_t)dev];
             if (spsp_cmp_load(session.ctx(), n, off.data(), minim.data(), klo.data(), hi ? khi.data() : nullptr) != 0)
                 throw_spsp("spsp_cmp_load");
             std::vector<uint32_t> &out = dev == 0 ? score : part[(size_t)dev];
@@ -155,7 +177,7 @@ void Comparator::run_device(std::vector<SketchElems> &sk)
             if (spsp_cmp_run(session.ctx(), 0, rows, 0, n, full_rows ? 0 : 1, (uint32_t)dev, (uint32_t)g, out.data(), n) != 0)
                 throw_spsp("spsp_cmp_run");
             spsp_cmp_last_kernel_ms(session.ctx(), &kms[(size_t)dev]);
-            nl[(size_t)dev] = session.launches();
+            nl[(size_t)dev] = session.launches() - l0[(size_t)dev];
         } catch (const std::exception &e) {
             errors[(size_t)dev] = e.what();
         }
@@ -172,7 +194,6 @@ void Comparator::run_device(std::vector<SketchElems> &sk)
     launches = 0;
     for (int dev = 0; dev < g; dev++) { kernel_ms = std::max(kernel_ms, kms[(size_t)dev]); launches += nl[(size_t)dev]; }
     t_compare = secs(t0, clk::now());
-    std::cout << "Comparisons done" << std::endl;
 }
 
 void Comparator::csv(bool jaccard, std::vector<uint8_t> &out) const

@@ -6,6 +6,9 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
+#include "session.h"
 #include "sketchfile.h"
 
 namespace spsp_host {
@@ -36,6 +39,8 @@ public:
 
 private:
     void run_device(std::vector<SketchElems> &sk);
+    std::vector<std::shared_ptr<DeviceSession>> sessions_;   // one per GPU, reused while (k, m) stay the same
+    uint64_t sess_k_ = 0, sess_m_ = 0;
 };
 
 int comparator_main(int argc, char **argv);          // Comparator.cpp:464-521

@@ -167,3 +167,20 @@ def raw_fasta_bytes(records: Sequence[Tuple[str, bytes]], width: int = 60) -> by
 def ensure_dir(path: str) -> str:
     os.makedirs(path, exist_ok=True)
     return path
+
+
+class Family:
+    """Random access to the members of a genome family (same recipe as
+    genome_family, but the mutation rates come from a fixed pool so that member
+    idx is the same genome whatever the number of ranks)."""
+
+    def __init__(self, n_bases: int, seed: int = 42, pool: int = 16384, lo_exp: float = -3.0, hi_exp: float = -1.0):
+        self.anc = random_genome(n_bases, seed)
+        self.rates = 10.0 ** np.random.default_rng(seed + 1).uniform(lo_exp, hi_exp, size=pool)
+        self.seed = seed
+
+    def member(self, idx: int) -> np.ndarray:
+        return mutate(self.anc, float(self.rates[idx % self.rates.size]), self.seed * 1000003 + idx)
+
+    def fasta(self, idx: int, width: int = 80) -> bytes:
+        return fasta_bytes([(f"g{idx:05d}", self.member(idx))], width)

@@ -137,3 +137,23 @@ def test_k63_elements_have_high_words(oracle):
 def test_out_name_and_threshold():
     assert S.threshold(31, 11, 1) == 2 ** 64 - 1
     assert S.threshold(31, 11, 0.5) == 2 ** 64 - 1
+
+
+def test_postpass_batch_one_scan_many_inputs(oracle):
+    """Several inputs packed back to back, one hit list over everything (what a
+    single kernel launch over a batch produces): per-input sketches are unchanged
+    and hits in the padding are ignored."""
+    k, m, s = 31, 11, 20
+    inputs = ["multi", "nasty", "tiny", "reads", "empty"]
+    ws, bo, nbs, ro, off = [], [], [], [], 0
+    for i in inputs:
+        w, nb, offs = S.pack_fasta(build_input(i), k)
+        ws.append(w); bo.append(off); nbs.append(nb); ro.append(offs)
+        off += w.size * 16
+    packed = np.concatenate(ws)
+    rec_first = np.array([0] + list(np.cumsum([r.size for r in ro])), np.uint64)
+    thr = S.threshold(k, m, s)
+    hits = oracle_hits(oracle, packed, packed.size * 16, m, thr)      # includes poly-A padding hits, if any
+    out = S.postpass_batch(packed, np.array(bo), np.array(nbs), np.concatenate(ro), rec_first, hits, k, m, s, threads=3)
+    for i, sk in zip(inputs, out):
+        assert sk == oracle.sketch(build_input(i), k, m, s)[0], i
