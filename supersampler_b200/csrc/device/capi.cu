@@ -3,6 +3,7 @@
 // and there is no CPU fallback: every entry point needs a CUDA device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,6 +27,39 @@ static int fail(int code, const std::string &msg)
         if (e_ != cudaSuccess)                                                                        \
             return fail(-1, std::string(#call) + ": " + cudaGetErrorString(e_));                      \
     } while (0)
+
+// Grow-only device / pinned buffers: steady-state calls never hit cudaMalloc / cudaFree
+// (both serialise against the whole device and against driver queries).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -51,15 +85,15 @@ struct spsp_ctx {
     bool filter_tried = false;
     bool filter_profitable = false;
     FilterParams fp{};
-    uint32_t *d_table = nullptr;
+    uint32_t *d_table = nullptr, *d_exact = nullptr;
     uint64_t n_selected = 0;
     // compare
     uint32_t n_sketches = 0, n_chunks = 0;
     uint64_t n_elems = 0;
     bool has_hi = false, owns_cmp = false;
     CmpData cmp{};
-    uint32_t *own_minim = nullptr;
-    uint64_t *own_klo = nullptr, *own_khi = nullptr, *d_sk_off = nullptr, *d_chunk_off = nullptr;
+    DevBuf b_minim, b_klo, b_khi, b_sk_off, b_chunk_off, b_tiles, b_out;
+    PinBuf p_stage, p_out;
     cudaEvent_t cev0 = nullptr, cev1 = nullptr;
     bool cmp_timed = false;
     uint64_t launches = 0;
@@ -100,12 +134,16 @@ static double filter_cost(int m, int g, double n_sel, FilterParams *fp)
     int bits = 2 * q;
     int hashed = 0;
     if (bits > FILTER_MAX_BITS) { bits = FILTER_MAX_BITS; hashed = 1; }
-    if (bits < 10) bits = 10;
     double load = g * n_sel / std::ldexp(1.0, bits);
-    double delta = hashed ? 1.0 - std::exp(-load) : std::min(1.0, load);
-    double any = 1.0 - std::pow(1.0 - delta, 32.0);
-    fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed;
-    return 7.0 / g + any * 12.0 / g + delta * 50.0;
+    double delta = hashed ? 1.0 - std::exp(-load) : std::min(1.0, load);   // P(probe positive)
+    double lam = delta * 64.0 / g;                                          // positives per 64-base thread chunk
+    double slow = 12.0 * (lam + 2.0 * std::sqrt(lam)) * (1.0 - std::exp(-32.0 * lam));
+    double verify = lam * g * 12.0;
+    // replicate the table (interleaved copies, lane % R) up to 64 KB to thin out bank conflicts
+    int rep = 0;
+    while (rep < 4 && (((size_t)1 << (bits - 3)) << (rep + 1)) <= ((size_t)64 << 10)) rep++;
+    fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed; fp->rep_log2 = rep;
+    return ((hashed ? 8.0 : 6.5) * 64.0 / g + slow + verify) / 64.0 + 0.4;
 }
 
 static int build_filter(spsp_ctx *c)
@@ -119,13 +157,24 @@ static int build_filter(spsp_ctx *c)
         double cost = filter_cost(c->m, g, n_sel, &fp);
         if (cost < best) { best = cost; bfp = fp; }
     }
+    // tuning overrides (experiments only): SPSP_FILTER_G = 1|2|4, SPSP_FILTER_REP = log2 copies
+    if (const char *eg = getenv("SPSP_FILTER_G")) {
+        FilterParams fp{};
+        double cost = filter_cost(c->m, atoi(eg), n_sel, &fp);
+        if (cost < 1e9) { best = cost; bfp = fp; }
+    }
+    if (const char *er = getenv("SPSP_FILTER_REP")) {
+        int rep = atoi(er);
+        if (rep >= 0 && rep <= 5 && ((((size_t)1 << (bfp.bits - 3)) << rep) <= FILTER_MAX_SMEM)) bfp.rep_log2 = rep;
+    }
     c->filter_profitable = best < 0.6 * 40.0;
     if (best >= 1e9) { c->filter_ready = false; return 0; }
     c->fp = bfp;
     CK(cudaMalloc(&c->d_table, (size_t)1 << (bfp.bits - 3)));
+    CK(cudaMalloc(&c->d_exact, ((size_t)1 << (2 * c->m)) / 8));
     unsigned long long *d_n = nullptr;
     CK(cudaMalloc(&d_n, sizeof(unsigned long long)));
-    CK(launch_filter_build(c->m, c->thr, bfp, c->d_table, d_n, c->slots[0].stream));
+    CK(launch_filter_build(c->m, c->thr, bfp, c->d_table, c->d_exact, d_n, c->slots[0].stream));
     c->launches++;
     unsigned long long n = 0;
     CK(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, c->slots[0].stream));
@@ -175,12 +224,9 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
 
 static void free_cmp(spsp_ctx *c)
 {
-    if (c->owns_cmp) {
-        cudaFree(c->own_minim); cudaFree(c->own_klo); cudaFree(c->own_khi);
-    }
-    cudaFree(c->d_sk_off); cudaFree(c->d_chunk_off);
-    c->own_minim = nullptr; c->own_klo = c->own_khi = nullptr;
-    c->d_sk_off = c->d_chunk_off = nullptr;
+    c->b_minim.release(); c->b_klo.release(); c->b_khi.release(); c->b_sk_off.release();
+    c->b_chunk_off.release(); c->b_tiles.release(); c->b_out.release();
+    c->p_stage.release(); c->p_out.release();
     c->owns_cmp = false;
     c->n_sketches = 0;
 }
@@ -199,6 +245,7 @@ extern "C" int spsp_destroy(spsp_ctx *c)
     }
     free_cmp(c);
     cudaFree(c->d_table);
+    cudaFree(c->d_exact);
     if (c->cev0) cudaEventDestroy(c->cev0);
     if (c->cev1) cudaEventDestroy(c->cev1);
     delete c;
@@ -229,7 +276,7 @@ static int launch_scan(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t 
     CK(cudaMemsetAsync(out.count, 0, sizeof(unsigned long long), s.stream));
     CK(cudaEventRecord(s.ev0, s.stream));
     if (use_filter)
-        CK(launch_scan_filter(d_packed, n_bases, c->m, c->thr, c->fp, c->d_table, out, s.stream));
+        CK(launch_scan_filter(d_packed, n_bases, c->m, c->thr, c->fp, c->d_table, c->d_exact, out, s.stream));
     else
         CK(launch_scan_dense(d_packed, n_bases, c->m, c->thr, out, s.stream));
     CK(cudaEventRecord(s.ev1, s.stream));
@@ -354,16 +401,16 @@ static int finish_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *ske
     c->n_elems = sketch_off[n_sketches];
     for (uint32_t i = 0; i < n_sketches; i++)
         if (sketch_off[i] > sketch_off[i + 1]) return fail(-3, "spsp_cmp_load: sketch_off not monotone");
-    CK(cudaMalloc(&c->d_sk_off, (size_t)(n_sketches + 1) * sizeof(uint64_t)));
-    CK(cudaMemcpyAsync(c->d_sk_off, sketch_off, (size_t)(n_sketches + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(c->b_sk_off.ensure((size_t)(n_sketches + 1) * sizeof(uint64_t)));
+    CK(cudaMemcpyAsync(c->b_sk_off.p, sketch_off, (size_t)(n_sketches + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     double avg = n_sketches ? (double)c->n_elems / n_sketches : 0.0;
     uint64_t chunks = (uint64_t)std::ceil(32.0 * avg / (0.7 * CMP_CAP));
     if (chunks < 1) chunks = 1;
     if (chunks > 8192) chunks = 8192;
     c->n_chunks = (uint32_t)chunks;
-    CK(cudaMalloc(&c->d_chunk_off, (size_t)n_sketches * (chunks + 1) * sizeof(uint64_t)));
-    c->cmp.sk_off = c->d_sk_off;
-    c->cmp.chunk_off = c->d_chunk_off;
+    CK(c->b_chunk_off.ensure((size_t)n_sketches * (chunks + 1) * sizeof(uint64_t)));
+    c->cmp.sk_off = static_cast<const uint64_t *>(c->b_sk_off.p);
+    c->cmp.chunk_off = static_cast<uint64_t *>(c->b_chunk_off.p);
     CK(launch_chunk_offsets(c->cmp, n_sketches, c->n_chunks, c->m, st));
     c->launches++;
     CK(cudaStreamSynchronize(st));
@@ -376,21 +423,34 @@ extern "C" int spsp_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *s
     if (!c || !sketch_off) return fail(-3, "spsp_cmp_load: bad args");
     if ((c->k > 32) != (kmer_hi != nullptr)) return fail(-3, "spsp_cmp_load: kmer_hi must be given iff k > 32");
     CK(cudaSetDevice(c->device));
-    free_cmp(c);
     cudaStream_t st = c->slots[0].stream;
+    CK(cudaStreamSynchronize(st));            // previous run may still read the buffers
     uint64_t E = sketch_off[n_sketches];
     size_t e1 = E ? E : 1;
-    CK(cudaMalloc(&c->own_minim, e1 * sizeof(uint32_t)));
-    CK(cudaMalloc(&c->own_klo, e1 * sizeof(uint64_t)));
+    CK(c->b_minim.ensure(e1 * sizeof(uint32_t)));
+    CK(c->b_klo.ensure(e1 * sizeof(uint64_t)));
+    if (kmer_hi) CK(c->b_khi.ensure(e1 * sizeof(uint64_t)));
     c->owns_cmp = true;
-    if (kmer_hi) CK(cudaMalloc(&c->own_khi, e1 * sizeof(uint64_t)));
     if (E) {
-        CK(cudaMemcpyAsync(c->own_minim, minimizer, E * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->own_klo, kmer_lo, E * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        if (kmer_hi) CK(cudaMemcpyAsync(c->own_khi, kmer_hi, E * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        // stage through pinned memory so the three copies are truly asynchronous
+        size_t bytes = E * (sizeof(uint32_t) + sizeof(uint64_t) * (kmer_hi ? 2 : 1));
+        CK(c->p_stage.ensure(bytes));
+        unsigned char *sp = static_cast<unsigned char *>(c->p_stage.p);
+        memcpy(sp, kmer_lo, E * 8);
+        CK(cudaMemcpyAsync(c->b_klo.p, sp, E * 8, cudaMemcpyHostToDevice, st));
+        sp += E * 8;
+        if (kmer_hi) {
+            memcpy(sp, kmer_hi, E * 8);
+            CK(cudaMemcpyAsync(c->b_khi.p, sp, E * 8, cudaMemcpyHostToDevice, st));
+            sp += E * 8;
+        }
+        memcpy(sp, minimizer, E * 4);
+        CK(cudaMemcpyAsync(c->b_minim.p, sp, E * 4, cudaMemcpyHostToDevice, st));
     }
     c->has_hi = kmer_hi != nullptr;
-    c->cmp.minim = c->own_minim; c->cmp.klo = c->own_klo; c->cmp.khi = c->own_khi;
+    c->cmp.minim = static_cast<const uint32_t *>(c->b_minim.p);
+    c->cmp.klo = static_cast<const uint64_t *>(c->b_klo.p);
+    c->cmp.khi = kmer_hi ? static_cast<const uint64_t *>(c->b_khi.p) : nullptr;
     return finish_cmp_load(c, n_sketches, sketch_off);
 }
 
@@ -400,7 +460,8 @@ extern "C" int spsp_cmp_load_device(spsp_ctx *c, uint32_t n_sketches, const uint
     if (!c || !sketch_off_host) return fail(-3, "spsp_cmp_load_device: bad args");
     if ((c->k > 32) != (d_kmer_hi != nullptr)) return fail(-3, "spsp_cmp_load_device: kmer_hi must be given iff k > 32");
     CK(cudaSetDevice(c->device));
-    free_cmp(c);
+    CK(cudaStreamSynchronize(c->slots[0].stream));
+    c->owns_cmp = false;
     c->has_hi = d_kmer_hi != nullptr;
     c->cmp.minim = d_minimizer; c->cmp.klo = d_kmer_lo; c->cmp.khi = d_kmer_hi;
     return finish_cmp_load(c, n_sketches, sketch_off_host);
@@ -424,8 +485,8 @@ static int cmp_run_impl(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint3
             if (t % tile_ranks == tile_rank) tiles.push_back(make_uint2(ib, jb));
     CK(cudaEventRecord(c->cev0, st));
     if (!tiles.empty()) {
-        uint2 *d_tiles = nullptr;
-        CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(uint2)));
+        CK(c->b_tiles.ensure(tiles.size() * sizeof(uint2)));
+        uint2 *d_tiles = static_cast<uint2 *>(c->b_tiles.p);
         CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(c->cev0, st));
         int sms = 148;
@@ -437,8 +498,7 @@ static int cmp_run_impl(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint3
                            row_end, col_begin, col_end, d_out, ld, st));
         c->launches++;
         CK(cudaEventRecord(c->cev1, st));
-        CK(cudaStreamSynchronize(st));      // d_tiles and the host vector must outlive the launch
-        CK(cudaFree(d_tiles));
+        CK(cudaStreamSynchronize(st));      // the host tile vector must outlive the copy
     } else {
         CK(cudaEventRecord(c->cev1, st));
     }
@@ -463,15 +523,15 @@ extern "C" int spsp_cmp_run(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, u
     uint64_t rows = row_end - row_begin, cols = col_end - col_begin;
     if (!rows || !cols) return 0;
     cudaStream_t st = c->slots[0].stream;
-    uint32_t *d_out = nullptr;
-    CK(cudaMalloc(&d_out, rows * cols * sizeof(uint32_t)));
+    CK(c->b_out.ensure(rows * cols * sizeof(uint32_t)));
+    CK(c->p_out.ensure(rows * cols * sizeof(uint32_t)));
+    uint32_t *d_out = static_cast<uint32_t *>(c->b_out.p);
     CK(cudaMemsetAsync(d_out, 0, rows * cols * sizeof(uint32_t), st));
     int rc = cmp_run_impl(c, row_begin, row_end, col_begin, col_end, symmetric, tile_rank, tile_ranks, d_out, cols);
-    if (rc) { cudaFree(d_out); return rc; }
-    std::vector<uint32_t> tmp(rows * cols);
-    CK(cudaMemcpyAsync(tmp.data(), d_out, rows * cols * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (rc) return rc;
+    const uint32_t *tmp = static_cast<const uint32_t *>(c->p_out.p);
+    CK(cudaMemcpyAsync(c->p_out.p, d_out, rows * cols * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaFree(d_out));
     for (uint64_t r = 0; r < rows; r++)
         for (uint64_t q = 0; q < cols; q++) out[r * ld + q] += tmp[r * cols + q];
     return 0;

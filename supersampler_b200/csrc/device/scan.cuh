@@ -13,25 +13,24 @@ struct ScanOut {
 };
 
 // Aligned q-gram filter: probe every g-th position with the q-gram that
-// starts there; bits = log2(table bits); hashed != 0 when 2q > bits.
+// starts there; bits = log2(table bits); hashed != 0 when 2q > bits;
+// rep_log2 = log2 of the number of interleaved table copies in shared memory
+// (copy = lane % R, so lanes of different copies never share a bank).
 struct FilterParams {
-    int g, q, bits, hashed;
+    int g, q, bits, hashed, rep_log2;
 };
 
 constexpr int FILTER_MAX_BITS = 20;          // 128 KB of shared memory
+constexpr size_t FILTER_MAX_SMEM = (size_t)1 << (FILTER_MAX_BITS - 3);   // table incl. replication
 constexpr int FILTER_THREADS = 1024;         // upper bound (launch bounds)
 constexpr int FILTER_QUEUE = 4096;           // candidate queue entries per CTA
 
-__host__ __device__ __forceinline__ uint32_t filter_index(uint32_t key, const FilterParams &fp)
-{
-    return fp.hashed ? (key * 0x9E3779B1u) >> (32 - fp.bits) : key;
-}
-
 cudaError_t launch_scan_dense(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, ScanOut out,
                               cudaStream_t st);
-cudaError_t launch_filter_build(int m, uint64_t thr, FilterParams fp, uint32_t *d_table,
+// d_exact: bitmap over the 4^m forward m-mers (bit x set iff m-mer x is selected).
+cudaError_t launch_filter_build(int m, uint64_t thr, FilterParams fp, uint32_t *d_table, uint32_t *d_exact,
                                 unsigned long long *d_nsel, cudaStream_t st);
 cudaError_t launch_scan_filter(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, FilterParams fp,
-                               const uint32_t *d_table, ScanOut out, cudaStream_t st);
+                               const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st);
 
 }  // namespace spsp
