@@ -139,9 +139,7 @@ static double filter_cost(int m, int g, double n_sel, FilterParams *fp)
     double lam = delta * 64.0 / g;                                          // positives per 64-base thread chunk
     double slow = 12.0 * (lam + 2.0 * std::sqrt(lam)) * (1.0 - std::exp(-32.0 * lam));
     double verify = lam * g * 12.0;
-    // replicate the table (interleaved copies, lane % R) up to 64 KB to thin out bank conflicts
-    int rep = 0;
-    while (rep < 4 && (((size_t)1 << (bits - 3)) << (rep + 1)) <= ((size_t)64 << 10)) rep++;
+    int rep = 0;      // interleaved table copies did not pay off on B200 (profiles/): shared-memory wavefronts are not the limiter
     fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed; fp->rep_log2 = rep;
     return ((hashed ? 8.0 : 6.5) * 64.0 / g + slow + verify) / 64.0 + 0.4;
 }

@@ -154,89 +154,122 @@ __device__ __forceinline__ void verify_exact(const uint32_t *__restrict__ packed
     }
 }
 
+// One warp owns 32 consecutive 64-base chunks (2048 bases, one coalesced 512 B
+// read) per iteration and never synchronises with the rest of the CTA: probe
+// results are packed into per-lane bit masks, compacted into the warp's own
+// shared-memory queue with a shuffle scan, and verified by the whole warp
+// against the exact bitmap.  The next iteration's words are prefetched into
+// registers before the probes of the current one.
 template <int G, bool HASHED>
-__global__ void __launch_bounds__(FILTER_THREADS) scan_filter_kernel(const uint32_t *__restrict__ packed,
-                                                                       uint64_t n_bases, int m, FilterParams fp,
-                                                                       const uint32_t *__restrict__ table_g,
-                                                                       const uint32_t *__restrict__ exact,
-                                                                       ScanOut out)
+__global__ void __launch_bounds__(FILTER_THREADS, FILTER_CTAS_PER_SM)
+scan_filter_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m, FilterParams fp,
+                   const uint32_t *__restrict__ table_g, const uint32_t *__restrict__ exact, ScanOut out)
 {
     extern __shared__ uint32_t smem[];
     const uint32_t tbl_words = 1u << (fp.bits - 5);
-    const uint32_t R = 1u << fp.rep_log2;
-    uint32_t *tbl = smem;                                   // tbl_words * R words, copy r of word i at i*R + r
-    uint32_t *queue = smem + tbl_words * R;                 // FILTER_QUEUE entries
-    __shared__ unsigned int q_count;
+    uint32_t *tbl = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wq = smem + tbl_words + warp * FILTER_WQ;     // this warp's candidate queue
 
-    for (uint32_t i = threadIdx.x; i < tbl_words * R; i += blockDim.x) tbl[i] = __ldg(table_g + (i >> fp.rep_log2));
-    if (threadIdx.x == 0) q_count = 0;
+    for (uint32_t i = threadIdx.x; i < tbl_words; i += blockDim.x) tbl[i] = __ldg(table_g + i);
     __syncthreads();
     if (n_bases < (uint64_t)m) return;
 
     const uint64_t n_pos = n_bases - m + 1;
     const uint64_t n_chunks = (n_pos + G - 1 + 63) >> 6;    // aligned probes reach G-1 past the last m-mer start
-    const uint64_t n_tiles = (n_chunks + blockDim.x - 1) / blockDim.x;
+    const uint64_t n_groups = (n_chunks + 31) >> 5;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     const int ksh = 32 - 2 * fp.q;                          // window -> clean key (hashed mode)
     const int wsh = 32 - (fp.bits - 5);                     // index -> word number
     const int bsh = 32 - fp.bits;                           // index -> bit number (low 5 bits used)
-    const char *tbl_lane = reinterpret_cast<const char *>(tbl + (threadIdx.x & (R - 1)));
-    const uint32_t stride = 4u << fp.rep_log2;              // bytes between consecutive table words
     constexpr int NPROBE = 64 / G;
+    constexpr int NB0 = NPROBE > 32 ? 32 : NPROBE;          // probes recorded in acc0
 
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t c = tile * blockDim.x + threadIdx.x;
+    uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    uint4 nv = make_uint4(0, 0, 0, 0);
+    uint32_t nw4 = 0;
+    if (g < n_groups) {
+        const uint64_t c = (g << 5) + lane;
         if (c < n_chunks) {
-            uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(packed) + c);
-            uint32_t W[5];
-            W[0] = v.x; W[1] = v.y; W[2] = v.z; W[3] = v.w;
-            W[4] = __ldg(packed + 4 * c + 4);
-            // one result bit per probe: probe i ends up at bit NPROBE-1-i of acc (two words for G == 1)
-            uint32_t acc0 = 0, acc1 = 0;
+            nv = __ldg(reinterpret_cast<const uint4 *>(packed) + c);
+            nw4 = __ldg(packed + 4 * c + 4);
+        }
+    }
+    for (; g < n_groups; g += n_warps) {
+        uint32_t W[5];
+        W[0] = nv.x; W[1] = nv.y; W[2] = nv.z; W[3] = nv.w; W[4] = nw4;
+        {
+            const uint64_t gn = g + n_warps, cn = (gn << 5) + lane;
+            if (gn < n_groups && cn < n_chunks) {
+                nv = __ldg(reinterpret_cast<const uint4 *>(packed) + cn);
+                nw4 = __ldg(packed + 4 * cn + 4);
+            }
+        }
+        const bool live = ((g << 5) + lane) < n_chunks;
+        // one result bit per probe: probe i ends up at bit NB0-1-i of acc0 (i < 32) or bit NPROBE-1-i of acc1
+        uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int i = 0; i < NPROBE; i++) {
-                const int a = i * G, j = a >> 4, o = a & 15;
-                uint32_t x = window16(W[j], W[j + 1], o);
-                if (HASHED) x = (x >> ksh) * 0x9E3779B1u;
-                const uint32_t word = *reinterpret_cast<const uint32_t *>(tbl_lane + (x >> wsh) * stride);
-                const uint32_t t = __funnelshift_l(0u, word, x >> bsh);      // wanted bit -> bit 31
-                if (i < 32) acc0 = __funnelshift_l(t, acc0, 1);
-                else acc1 = __funnelshift_l(t, acc1, 1);
+        for (int i = 0; i < NPROBE; i++) {
+            const int a = i * G, j = a >> 4, o = a & 15;
+            uint32_t x = window16(W[j], W[j + 1], o);
+            if (HASHED) x = (x >> ksh) * 0x9E3779B1u;
+            const uint32_t word = tbl[x >> wsh];
+            const uint32_t t = __funnelshift_l(0u, word, x >> bsh);          // wanted bit -> bit 31
+            if (i < 32) acc0 = __funnelshift_l(t, acc0, 1);
+            else acc1 = __funnelshift_l(t, acc1, 1);
+        }
+        if (!live) { acc0 = 0; acc1 = 0; }
+        // warp-level compaction of the positives
+        const uint32_t cnt = __popc(acc0) + __popc(acc1);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        const uint64_t gbase = g << 11;                      // first base of this warp's block
+        if (total <= FILTER_WQ) {
+            uint32_t off = incl - cnt;
+            const uint32_t rel = (uint32_t)lane << 6;
+            while (acc0) {
+                const int bit = 31 - __clz(acc0);
+                acc0 &= ~(1u << bit);
+                wq[off++] = rel + (uint32_t)((NB0 - 1 - bit) * G);
             }
-            if (acc0 | acc1) {
-                const uint32_t rel = threadIdx.x << 6;       // chunk start relative to the tile
+            while (acc1) {
+                const int bit = 31 - __clz(acc1);
+                acc1 &= ~(1u << bit);
+                wq[off++] = rel + (uint32_t)((NPROBE - 1 - bit) * G);
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < total * G; i += 32) {
+                const uint64_t a = gbase + wq[i / G];
+                const uint32_t r = i % G;
+                if (a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
+            }
+            __syncwarp();
+        } else {
+            // more positives than the queue holds (dense tables): every lane verifies its own
+            const uint64_t cb = gbase + ((uint64_t)lane << 6);
+            while (acc0) {
+                const int bit = 31 - __clz(acc0);
+                acc0 &= ~(1u << bit);
+                const uint64_t a = cb + (uint64_t)((NB0 - 1 - bit) * G);
 #pragma unroll 1
-                for (int half = 0; half < (NPROBE > 32 ? 2 : 1); half++) {
-                    uint32_t acc = half ? acc1 : acc0;
-                    const int nbit = NPROBE > 32 ? 32 : NPROBE;
-                    while (acc) {
-                        int bit = 31 - __clz(acc);
-                        acc &= ~(1u << bit);
-                        uint32_t a = (uint32_t)((half * 32 + (nbit - 1 - bit)) * G);
-                        unsigned int slot = atomicAdd(&q_count, 1u);
-                        if (slot < FILTER_QUEUE) {
-                            queue[slot] = rel + a;
-                        } else {
-                            // queue full: verify inline (exact, just slower)
-                            uint64_t pa = (c << 6) + a;
+                for (int r = 0; r < G; r++)
+                    if (a >= (uint64_t)r) verify_exact(packed, exact, a - r, n_bases, m, out);
+            }
+            while (acc1) {
+                const int bit = 31 - __clz(acc1);
+                acc1 &= ~(1u << bit);
+                const uint64_t a = cb + (uint64_t)((NPROBE - 1 - bit) * G);
 #pragma unroll 1
-                            for (int r = 0; r < G; r++)
-                                if (pa >= (uint64_t)r) verify_exact(packed, exact, pa - r, n_bases, m, out);
-                        }
-                    }
-                }
+                for (int r = 0; r < G; r++)
+                    if (a >= (uint64_t)r) verify_exact(packed, exact, a - r, n_bases, m, out);
             }
         }
-        __syncthreads();
-        const unsigned int nq = min(q_count, (unsigned int)FILTER_QUEUE);
-        const uint64_t tile_base = tile * ((uint64_t)blockDim.x << 6);
-        for (unsigned int i = threadIdx.x; i < nq * G; i += blockDim.x) {
-            uint64_t a = tile_base + queue[i / G];
-            unsigned int r = i % G;
-            if (a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) q_count = 0;
-        __syncthreads();
     }
 }
 
@@ -285,24 +318,23 @@ template <int G, bool HASHED>
 static cudaError_t launch_filter_g(const uint32_t *d_packed, uint64_t n_bases, int m, FilterParams fp,
                                    const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
 {
-    size_t smem = (((size_t)1 << (fp.bits - 3)) << fp.rep_log2) + FILTER_QUEUE * sizeof(uint32_t);
+    const int threads = FILTER_THREADS;
+    size_t smem = ((size_t)1 << (fp.bits - 3)) + (size_t)(threads / 32) * FILTER_WQ * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(scan_filter_kernel<G, HASHED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(FILTER_MAX_SMEM + FILTER_QUEUE * sizeof(uint32_t)));
+                                             (int)(FILTER_MAX_SMEM + (FILTER_THREADS / 32) * FILTER_WQ * sizeof(uint32_t)));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     uint64_t n_chunks = ((n_bases - m + 1) + G - 1 + 63) >> 6;
-    // small inputs use smaller CTAs so that every SM gets a tile
-    int threads = FILTER_THREADS;
-    while (threads > 256 && (n_chunks + threads - 1) / threads < 2ull * sm_count()) threads >>= 1;
-    uint64_t n_tiles = (n_chunks + threads - 1) / threads;
+    uint64_t n_groups = (n_chunks + 31) >> 5;
+    uint64_t want = (n_groups + (threads / 32) - 1) / (threads / 32);     // CTAs if every warp took one group
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_filter_kernel<G, HASHED>, threads, smem);
     if (per_sm < 1) per_sm = 1;
     uint64_t blocks = (uint64_t)sm_count() * per_sm;
-    if (blocks > n_tiles) blocks = n_tiles;
+    if (blocks > want) blocks = want;
     if (blocks < 1) blocks = 1;
     scan_filter_kernel<G, HASHED><<<(unsigned)blocks, threads, smem, st>>>(d_packed, n_bases, m, fp, d_table, d_exact, out);
     return cudaGetLastError();

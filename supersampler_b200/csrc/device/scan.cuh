@@ -22,8 +22,9 @@ struct FilterParams {
 
 constexpr int FILTER_MAX_BITS = 20;          // 128 KB of shared memory
 constexpr size_t FILTER_MAX_SMEM = (size_t)1 << (FILTER_MAX_BITS - 3);   // table incl. replication
-constexpr int FILTER_THREADS = 1024;         // upper bound (launch bounds)
-constexpr int FILTER_QUEUE = 4096;           // candidate queue entries per CTA
+constexpr int FILTER_THREADS = 512;          // 16 warps per CTA
+constexpr int FILTER_CTAS_PER_SM = 3;        // register budget: 65536 / (512 * 3) = 42 per thread
+constexpr int FILTER_WQ = 128;               // candidate queue entries per warp
 
 cudaError_t launch_scan_dense(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, ScanOut out,
                               cudaStream_t st);
