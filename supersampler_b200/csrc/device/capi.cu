@@ -140,7 +140,7 @@ static double filter_cost(int m, int g, double n_sel, FilterParams *fp)
     double slow = 12.0 * (lam + 2.0 * std::sqrt(lam)) * (1.0 - std::exp(-32.0 * lam));
     double verify = lam * g * 12.0;
     int rep = 0;      // interleaved table copies did not pay off on B200 (profiles/): shared-memory wavefronts are not the limiter
-    fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed; fp->rep_log2 = rep;
+    fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed; fp->rep_log2 = rep; fp->kind = 0;
     return ((hashed ? 8.0 : 6.5) * 64.0 / g + slow + verify) / 64.0 + 0.4;
 }
 
@@ -155,8 +155,21 @@ static int build_filter(spsp_ctx *c)
         double cost = filter_cost(c->m, g, n_sel, &fp);
         if (cost < best) { best = cost; bfp = fp; }
     }
+    // byte table of phase masks (g = 4, keys of at most 16 bits): about half the instructions per probe
+    if (c->m - 3 >= 3 && 2 * (c->m - 3) <= 16) {
+        int q = c->m - 3;
+        double delta = std::min(1.0, 4.0 * n_sel / std::ldexp(1.0, 2 * q));
+        double lam = delta * 16.0;                        // positives per 64-base chunk
+        double cost = (3.3 * 16.0 + 30.0 + lam * 10.0 + lam * 1.3 * 41.0 / 32.0 * 4.0 + 10.0) / 64.0;
+        const char *ek = getenv("SPSP_FILTER_KIND");
+        bool allow = !(ek && atoi(ek) == 0);
+        if (allow && (cost < best || (ek && atoi(ek) == 1))) {
+            best = cost;
+            bfp.g = 4; bfp.q = q; bfp.bits = 2 * q + 3; bfp.hashed = 0; bfp.rep_log2 = 0; bfp.kind = 1;
+        }
+    }
     // tuning overrides (experiments only): SPSP_FILTER_G = 1|2|4, SPSP_FILTER_REP = log2 copies
-    if (const char *eg = getenv("SPSP_FILTER_G")) {
+    if (const char *eg = getenv("SPSP_FILTER_G"); eg && bfp.kind == 0) {
         FilterParams fp{};
         double cost = filter_cost(c->m, atoi(eg), n_sel, &fp);
         if (cost < 1e9) { best = cost; bfp = fp; }
@@ -168,7 +181,7 @@ static int build_filter(spsp_ctx *c)
     c->filter_profitable = best < 0.6 * 40.0;
     if (best >= 1e9) { c->filter_ready = false; return 0; }
     c->fp = bfp;
-    CK(cudaMalloc(&c->d_table, (size_t)1 << (bfp.bits - 3)));
+    CK(cudaMalloc(&c->d_table, filter_table_bytes(bfp)));
     CK(cudaMalloc(&c->d_exact, ((size_t)1 << (2 * c->m)) / 8));
     unsigned long long *d_n = nullptr;
     CK(cudaMalloc(&d_n, sizeof(unsigned long long)));

@@ -129,8 +129,13 @@ __global__ void filter_build_kernel(int m, uint64_t thr, FilterParams fp, uint32
             for (int r = 0; r < fp.g; r++) {
                 // q-gram that starts r bases into the m-mer
                 uint32_t key = (fw >> (2 * (m - fp.q - r))) & ((1u << (2 * fp.q)) - 1u);
-                uint32_t idx = table_index(key, fp);
-                atomicOr(table + (idx >> 5), 0x80000000u >> (idx & 31));
+                if (fp.kind == 1) {
+                    // byte table: bit r of byte `key` (little-endian bytes inside the u32 words)
+                    atomicOr(table + (key >> 2), (1u << r) << (8 * (key & 3)));
+                } else {
+                    uint32_t idx = table_index(key, fp);
+                    atomicOr(table + (idx >> 5), 0x80000000u >> (idx & 31));
+                }
             }
         }
         exact[w] = bitsw;
@@ -273,6 +278,137 @@ scan_filter_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m,
     }
 }
 
+// ------------------------------------------------- byte-table filter (2q <= 16)
+
+// Same idea with a denser encoding for short keys: the table has one BYTE per
+// q-gram and the byte is the mask of phases r (0..G-1) at which some selected
+// m-mer carries that q-gram.  A probe is then a byte extract (PRMT when the key
+// is the 16 bits of two whole bytes), an 8-bit shared load whose address is the
+// key itself, and one multiply-add that appends the 4-bit mask to a per-lane
+// accumulator (8 probes per 32-bit register).  Only the phases named by the
+// mask are verified.  Each lane handles FILTER8_CH chunks per iteration before
+// the warp verifies its queue, which amortises the compaction and the verify
+// pass over 8192 bases.
+template <bool Q8>
+__global__ void __launch_bounds__(FILTER8_THREADS, FILTER8_CTAS_PER_SM)
+scan_filter8_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m, FilterParams fp,
+                    const uint32_t *__restrict__ table_g, const uint32_t *__restrict__ exact, ScanOut out)
+{
+    constexpr int G = 4, NPROBE = 16, CH = FILTER8_CH;
+    extern __shared__ uint32_t smem[];
+    const uint32_t tbl_bytes = 1u << (2 * fp.q);
+    const uint8_t *tbl = reinterpret_cast<const uint8_t *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wq = smem + (tbl_bytes >> 2) + warp * (FILTER_WQ + 1);   // [0] = count, then entries
+    uint32_t *wcnt = wq;
+    wq += 1;
+
+    for (uint32_t i = threadIdx.x; i < (tbl_bytes >> 2); i += blockDim.x) smem[i] = __ldg(table_g + i);
+    if (lane == 0) *wcnt = 0;
+    __syncthreads();
+    if (n_bases < (uint64_t)m) return;
+
+    const uint64_t n_pos = n_bases - m + 1;
+    const uint64_t n_chunks = (n_pos + G - 1 + 63) >> 6;
+    const uint64_t n_groups = (n_chunks + 32 * CH - 1) / (32 * CH);   // one group = CH x 32 chunks
+    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const int ksh = 32 - 2 * fp.q;
+
+    uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    uint4 nv = make_uint4(0, 0, 0, 0);
+    uint32_t nw4 = 0;
+    if (g < n_groups) {
+        const uint64_t c = g * (32 * CH) + lane;
+        if (c < n_chunks) {
+            nv = __ldg(reinterpret_cast<const uint4 *>(packed) + c);
+            nw4 = __ldg(packed + 4 * c + 4);
+        }
+    }
+    for (; g < n_groups; g += n_warps) {
+        const uint64_t gchunk = g * (32 * CH);               // first chunk of the group
+#pragma unroll 1
+        for (int kk = 0; kk < CH; kk++) {
+            uint32_t W[5];
+            W[0] = nv.x; W[1] = nv.y; W[2] = nv.z; W[3] = nv.w; W[4] = nw4;
+            {
+                // next chunk of this lane: same group (kk+1) or the first of the warp's next group
+                const uint64_t cn = (kk + 1 < CH) ? gchunk + (uint64_t)(kk + 1) * 32 + lane
+                                                 : (g + n_warps) * (32 * CH) + lane;
+                if (cn < n_chunks) {
+                    nv = __ldg(reinterpret_cast<const uint4 *>(packed) + cn);
+                    nw4 = __ldg(packed + 4 * cn + 4);
+                }
+            }
+            const bool live = (gchunk + (uint64_t)kk * 32 + lane) < n_chunks;
+            // probe i leaves its 4-bit phase mask in nibble (7 - i%8) of acc[i/8]
+            uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+            for (int i = 0; i < NPROBE; i++) {
+                const int j = i >> 2, ob = i & 3;            // word, byte offset of the probe (4 bases per byte)
+                uint32_t key;
+                if (Q8) {
+                    if (ob == 0) key = __byte_perm(W[j], 0u, 0x4432);
+                    else if (ob == 1) key = __byte_perm(W[j], 0u, 0x4421);
+                    else if (ob == 2) key = __byte_perm(W[j], 0u, 0x4410);
+                    else key = __funnelshift_l(W[j + 1], W[j], 24) >> 16;
+                } else {
+                    key = window16(W[j], W[j + 1], ob * 4) >> ksh;
+                }
+                const uint32_t val = tbl[key];
+                if (i < 8) acc0 = acc0 * 16u + val;
+                else acc1 = acc1 * 16u + val;
+            }
+            if (!live) { acc0 = 0; acc1 = 0; }
+            if (acc0 | acc1) {
+                // nonzero nibbles -> one flag bit each, then claim queue slots
+                uint32_t f0 = (acc0 | (acc0 >> 1) | (acc0 >> 2) | (acc0 >> 3)) & 0x11111111u;
+                uint32_t f1 = (acc1 | (acc1 >> 1) | (acc1 >> 2) | (acc1 >> 3)) & 0x11111111u;
+                const uint32_t cnt = __popc(f0) + __popc(f1);
+                uint32_t off = atomicAdd(wcnt, cnt);
+                const uint32_t rel = ((uint32_t)kk * 32 + lane) << 6;    // chunk start relative to the group
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    uint32_t f = half ? f1 : f0;
+                    const uint32_t acc = half ? acc1 : acc0;
+                    while (f) {
+                        const int bit = 31 - __clz(f);       // multiple of 4: nibble index = bit / 4
+                        f &= ~(1u << bit);
+                        const uint32_t mask = (acc >> bit) & 15u;
+                        const uint32_t a = rel + (uint32_t)((half * 8 + (7 - (bit >> 2))) * G);
+                        const uint32_t ent = (a << 4) | mask;
+                        if (off < FILTER_WQ) {
+                            wq[off] = ent;
+                        } else {
+                            // queue full: verify inline
+                            const uint64_t pa = (gchunk << 6) + a;
+#pragma unroll 1
+                            for (int r = 0; r < G; r++)
+                                if (((mask >> r) & 1u) && pa >= (uint64_t)r)
+                                    verify_exact(packed, exact, pa - r, n_bases, m, out);
+                        }
+                        off++;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t total = min(*wcnt, (uint32_t)FILTER_WQ);
+        if (total) {
+            const uint64_t gbase = gchunk << 6;
+            // 4 (phase) lanes per entry
+            for (uint32_t i = lane; i < total * G; i += 32) {
+                const uint32_t ent = wq[i >> 2];
+                const uint32_t r = i & 3;
+                const uint64_t a = gbase + (ent >> 4);
+                if (((ent >> r) & 1u) && a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
+            }
+            __syncwarp();
+            if (lane == 0) *wcnt = 0;
+            __syncwarp();
+        }
+    }
+}
+
 // ------------------------------------------------------------- launchers
 
 static int g_sm_count = 0;
@@ -302,7 +438,7 @@ cudaError_t launch_scan_dense(const uint32_t *d_packed, uint64_t n_bases, int m,
 cudaError_t launch_filter_build(int m, uint64_t thr, FilterParams fp, uint32_t *d_table, uint32_t *d_exact,
                                 unsigned long long *d_nsel, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(d_table, 0, (size_t)1 << (fp.bits - 3), st);
+    cudaError_t e = cudaMemsetAsync(d_table, 0, filter_table_bytes(fp), st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(d_nsel, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
@@ -340,11 +476,42 @@ static cudaError_t launch_filter_g(const uint32_t *d_packed, uint64_t n_bases, i
     return cudaGetLastError();
 }
 
+template <bool Q8>
+static cudaError_t launch_filter8(const uint32_t *d_packed, uint64_t n_bases, int m, FilterParams fp,
+                                  const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
+{
+    const int threads = FILTER8_THREADS;
+    size_t smem = filter_table_bytes(fp) + (size_t)(threads / 32) * (FILTER_WQ + 1) * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(scan_filter8_kernel<Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(((size_t)64 << 10) + (FILTER8_THREADS / 32) * (FILTER_WQ + 1) * sizeof(uint32_t)));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    uint64_t n_chunks = ((n_bases - m + 1) + 4 - 1 + 63) >> 6;
+    uint64_t n_groups = (n_chunks + 32 * FILTER8_CH - 1) / (32 * FILTER8_CH);
+    uint64_t want = (n_groups + (threads / 32) - 1) / (threads / 32);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_filter8_kernel<Q8>, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t blocks = (uint64_t)sm_count() * per_sm;
+    if (blocks > want) blocks = want;
+    if (blocks < 1) blocks = 1;
+    scan_filter8_kernel<Q8><<<(unsigned)blocks, threads, smem, st>>>(d_packed, n_bases, m, fp, d_table, d_exact, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan_filter(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, FilterParams fp,
                                const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
 {
     (void)thr;
     if (n_bases < (uint64_t)m) return cudaSuccess;
+    if (fp.kind == 1) {
+        if (fp.g != 4 || 2 * fp.q > 16) return cudaErrorInvalidValue;
+        return fp.q == 8 ? launch_filter8<true>(d_packed, n_bases, m, fp, d_table, d_exact, out, st)
+                         : launch_filter8<false>(d_packed, n_bases, m, fp, d_table, d_exact, out, st);
+    }
 #define SPSP_F(G_, H_) return launch_filter_g<G_, H_>(d_packed, n_bases, m, fp, d_table, d_exact, out, st)
     switch (fp.g * 2 + (fp.hashed ? 1 : 0)) {
     case 2: SPSP_F(1, false);

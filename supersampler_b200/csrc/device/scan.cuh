@@ -16,8 +16,10 @@ struct ScanOut {
 // starts there; bits = log2(table bits); hashed != 0 when 2q > bits;
 // rep_log2 = log2 of the number of interleaved table copies in shared memory
 // (copy = lane % R, so lanes of different copies never share a bank).
+// kind 0: bit table (any key width, direct or hashed); kind 1: byte table of
+// phase masks (g == 4, 2q <= 16, one byte per q-gram).
 struct FilterParams {
-    int g, q, bits, hashed, rep_log2;
+    int g, q, bits, hashed, rep_log2, kind;
 };
 
 constexpr int FILTER_MAX_BITS = 20;          // 128 KB of shared memory
@@ -25,6 +27,14 @@ constexpr size_t FILTER_MAX_SMEM = (size_t)1 << (FILTER_MAX_BITS - 3);   // tabl
 constexpr int FILTER_THREADS = 512;          // 16 warps per CTA
 constexpr int FILTER_CTAS_PER_SM = 3;        // register budget: 65536 / (512 * 3) = 42 per thread
 constexpr int FILTER_WQ = 128;               // candidate queue entries per warp
+constexpr int FILTER8_THREADS = 768;         // byte-table kernel: 2 CTAs x 24 warps per SM (64 KB table each)
+constexpr int FILTER8_CTAS_PER_SM = 2;
+constexpr int FILTER8_CH = 4;                // 64-base chunks per lane per iteration
+
+__host__ __device__ __forceinline__ size_t filter_table_bytes(const FilterParams &fp)
+{
+    return fp.kind == 1 ? ((size_t)1 << (2 * fp.q)) : ((size_t)1 << (fp.bits - 3));
+}
 
 cudaError_t launch_scan_dense(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, ScanOut out,
                               cudaStream_t st);
