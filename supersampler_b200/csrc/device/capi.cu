@@ -125,61 +125,49 @@ extern "C" int spsp_host_free(void *p)
     return 0;
 }
 
-// Expected instruction cost per base of the filter kernel for stride g (see
-// DESIGN.md "scan kernel"): probe + queue push under divergence + verify.
-static double filter_cost(int m, int g, double n_sel, FilterParams *fp)
+// Cost model of the filter kernel, in instruction-equivalents per 64-base lane
+// chunk, fitted to B200 measurements (profiles/r01_scan_sweep.md): the kernel is
+// bound by shared-memory wavefronts, so a probe costs about the same whatever
+// its instruction count; positives cost a queue entry plus the exact checks.
+//   n_sel  expected number of selected forward m-mers (4^m * T / 2^64)
+static double filter_cost(int m, int kind, int g, double n_sel, FilterParams *fp)
 {
     int q = m - g + 1;
-    if (q < 3) return 1e9;
-    int bits = 2 * q;
-    int hashed = 0;
-    if (bits > FILTER_MAX_BITS) { bits = FILTER_MAX_BITS; hashed = 1; }
-    double load = g * n_sel / std::ldexp(1.0, bits);
-    double delta = hashed ? 1.0 - std::exp(-load) : std::min(1.0, load);   // P(probe positive)
-    double lam = delta * 64.0 / g;                                          // positives per 64-base thread chunk
-    double slow = 12.0 * (lam + 2.0 * std::sqrt(lam)) * (1.0 - std::exp(-32.0 * lam));
-    double verify = lam * g * 12.0;
-    int rep = 0;      // interleaved table copies did not pay off on B200 (profiles/): shared-memory wavefronts are not the limiter
-    fp->g = g; fp->q = q; fp->bits = bits; fp->hashed = hashed; fp->rep_log2 = rep; fp->kind = 0;
-    return ((hashed ? 8.0 : 6.5) * 64.0 / g + slow + verify) / 64.0 + 0.4;
+    if (q < 3) return 1e18;
+    int bits = 2 * q, hashed = 0;
+    if (kind == 1) {
+        if (g != 4 || bits > 16) return 1e18;
+    } else if (bits > FILTER_MAX_BITS) {
+        bits = FILTER_MAX_BITS; hashed = 1;
+    }
+    const double n_probe = 64.0 / g;
+    const double load = g * n_sel / std::ldexp(1.0, bits);
+    const double delta = hashed ? 1.0 - std::exp(-load) : std::min(1.0, load);   // P(probe positive)
+    const double lam = delta * n_probe;                                          // positives per lane chunk
+    const double p_lane = 1.0 - std::pow(1.0 - delta, n_probe);                  // P(lane queues an entry)
+    const double phases = kind == 1 ? 1.0 + 0.75 * delta : (double)g;            // exact checks per positive
+    fp->g = g; fp->q = q; fp->bits = kind == 1 ? 2 * q + 3 : bits; fp->hashed = hashed; fp->rep_log2 = 0; fp->kind = kind;
+    return n_probe * 5.5 + 30.0 + 20.0 * p_lane + lam * phases * 45.0;
 }
 
 static int build_filter(spsp_ctx *c)
 {
-    double p = (double)c->thr / 18446744073709551616.0;
-    double n_sel = std::ldexp(1.0, 2 * c->m) * p;
-    double best = 1e9;
+    const double p = (double)c->thr / 18446744073709551616.0;
+    const double n_sel = std::ldexp(1.0, 2 * c->m) * p;
+    double best = 1e18;
     FilterParams bfp{};
-    for (int g : {4, 2, 1}) {
-        FilterParams fp{};
-        double cost = filter_cost(c->m, g, n_sel, &fp);
-        if (cost < best) { best = cost; bfp = fp; }
-    }
-    // byte table of phase masks (g = 4, keys of at most 16 bits): about half the instructions per probe
-    if (c->m - 3 >= 3 && 2 * (c->m - 3) <= 16) {
-        int q = c->m - 3;
-        double delta = std::min(1.0, 4.0 * n_sel / std::ldexp(1.0, 2 * q));
-        double lam = delta * 16.0;                        // positives per 64-base chunk
-        double cost = (3.3 * 16.0 + 30.0 + lam * 10.0 + lam * 1.3 * 41.0 / 32.0 * 4.0 + 10.0) / 64.0;
-        const char *ek = getenv("SPSP_FILTER_KIND");
-        bool allow = !(ek && atoi(ek) == 0);
-        if (allow && (cost < best || (ek && atoi(ek) == 1))) {
-            best = cost;
-            bfp.g = 4; bfp.q = q; bfp.bits = 2 * q + 3; bfp.hashed = 0; bfp.rep_log2 = 0; bfp.kind = 1;
+    const char *ek = getenv("SPSP_FILTER_KIND"), *eg = getenv("SPSP_FILTER_G");   // tuning overrides (experiments)
+    for (int kind = 0; kind < 2; kind++)
+        for (int g : {4, 2, 1}) {
+            if (ek && atoi(ek) != kind) continue;
+            if (eg && atoi(eg) != g && kind == 0) continue;
+            FilterParams fp{};
+            double cost = filter_cost(c->m, kind, g, n_sel, &fp);
+            if (cost < best) { best = cost; bfp = fp; }
         }
-    }
-    // tuning overrides (experiments only): SPSP_FILTER_G = 1|2|4, SPSP_FILTER_REP = log2 copies
-    if (const char *eg = getenv("SPSP_FILTER_G"); eg && bfp.kind == 0) {
-        FilterParams fp{};
-        double cost = filter_cost(c->m, atoi(eg), n_sel, &fp);
-        if (cost < 1e9) { best = cost; bfp = fp; }
-    }
-    if (const char *er = getenv("SPSP_FILTER_REP")) {
-        int rep = atoi(er);
-        if (rep >= 0 && rep <= 5 && ((((size_t)1 << (bfp.bits - 3)) << rep) <= FILTER_MAX_SMEM)) bfp.rep_log2 = rep;
-    }
-    c->filter_profitable = best < 0.6 * 40.0;
-    if (best >= 1e9) { c->filter_ready = false; return 0; }
+    const double dense_cost = 64.0 * 30.0;                 // full hash at every position
+    c->filter_profitable = best < dense_cost;
+    if (best >= 1e18) { c->filter_ready = false; return 0; }
     c->fp = bfp;
     CK(cudaMalloc(&c->d_table, filter_table_bytes(bfp)));
     CK(cudaMalloc(&c->d_exact, ((size_t)1 << (2 * c->m)) / 8));

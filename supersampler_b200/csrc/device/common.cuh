@@ -65,4 +65,42 @@ __device__ __forceinline__ uint32_t window16(uint32_t w0, uint32_t w1, int o)
     return __funnelshift_l(w1, w0, 2 * o);
 }
 
+// ---- TMA bulk copy (global -> shared) signalled on an mbarrier ---------------
+// One thread arms the barrier with the byte count and issues cp.async.bulk
+// (SASS: UBLKCP); every thread then waits on the barrier's phase.  dst, src and
+// bytes must be multiples of 16.
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    const uint32_t piece = 16384;                 // keep single copies modest
+    for (uint32_t off = 0; off < bytes; off += piece) {
+        const uint32_t n = bytes - off < piece ? bytes - off : piece;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(static_cast<char *>(dst_smem) + off)),
+                       "l"(static_cast<const char *>(src_gmem) + off), "r"(n), "r"(b)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t b = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    }
+}
+
 }  // namespace spsp

@@ -143,8 +143,6 @@ __global__ void filter_build_kernel(int m, uint64_t thr, FilterParams fp, uint32
     if (local) atomicAdd(n_selected, local);
 }
 
-// ----------------------------------------------------------------- filter
-
 // Verify one candidate position against the exact m-mer bitmap.
 __device__ __forceinline__ void verify_exact(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ exact,
                                              uint64_t p, uint64_t n_bases, int m, const ScanOut &out)
@@ -159,160 +157,98 @@ __device__ __forceinline__ void verify_exact(const uint32_t *__restrict__ packed
     }
 }
 
-// One warp owns 32 consecutive 64-base chunks (2048 bases, one coalesced 512 B
-// read) per iteration and never synchronises with the rest of the CTA: probe
-// results are packed into per-lane bit masks, compacted into the warp's own
-// shared-memory queue with a shuffle scan, and verified by the whole warp
-// against the exact bitmap.  The next iteration's words are prefetched into
-// registers before the probes of the current one.
-template <int G, bool HASHED>
-__global__ void __launch_bounds__(FILTER_THREADS, FILTER_CTAS_PER_SM)
-scan_filter_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m, FilterParams fp,
-                   const uint32_t *__restrict__ table_g, const uint32_t *__restrict__ exact, ScanOut out)
+// ----------------------------------------------------------------- filter
+//
+// One warp owns FILTER_CH x 32 consecutive 64-base chunks per iteration (lane l
+// of pass kk reads chunk group*CH*32 + kk*32 + l: one coalesced 512 B read per
+// pass, the halo word comes from the neighbour lane by shuffle) and never
+// synchronises with the rest of the CTA.  Probe results are appended to two
+// per-lane accumulator words; lanes with a positive store {chunk, acc0, acc1}
+// into the warp's shared-memory queue at a ballot-ranked slot (no atomics, no
+// scan); when the queue could overflow or the group ends, every lane takes one
+// entry and verifies the positions it names against the exact bitmap.  The
+// next chunk's words are requested before the current chunk is probed, and the
+// table itself arrives by one TMA bulk copy.
+//
+//   MODE_BIT_DIRECT / MODE_BIT_HASHED: bit table, 64/G probes of one bit;
+//       a set bit means "some phase may match": all G phases are verified.
+//   MODE_BYTE_Q8 / MODE_BYTE: G = 4, one byte per q-gram holding the 4-bit
+//       phase mask; 16 probes of one nibble; only the named phases are verified.
+enum { MODE_BIT_DIRECT = 0, MODE_BIT_HASHED = 1, MODE_BYTE_Q8 = 2, MODE_BYTE = 3 };
+
+template <int G, int MODE>
+__device__ __forceinline__ void verify_entry(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ exact,
+                                             uint64_t cbase, uint32_t a0, uint32_t a1, uint64_t n_bases, int m,
+                                             const ScanOut &out)
 {
-    extern __shared__ uint32_t smem[];
-    const uint32_t tbl_words = 1u << (fp.bits - 5);
-    uint32_t *tbl = smem;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *wq = smem + tbl_words + warp * FILTER_WQ;     // this warp's candidate queue
-
-    for (uint32_t i = threadIdx.x; i < tbl_words; i += blockDim.x) tbl[i] = __ldg(table_g + i);
-    __syncthreads();
-    if (n_bases < (uint64_t)m) return;
-
-    const uint64_t n_pos = n_bases - m + 1;
-    const uint64_t n_chunks = (n_pos + G - 1 + 63) >> 6;    // aligned probes reach G-1 past the last m-mer start
-    const uint64_t n_groups = (n_chunks + 31) >> 5;
-    const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const int ksh = 32 - 2 * fp.q;                          // window -> clean key (hashed mode)
-    const int wsh = 32 - (fp.bits - 5);                     // index -> word number
-    const int bsh = 32 - fp.bits;                           // index -> bit number (low 5 bits used)
     constexpr int NPROBE = 64 / G;
-    constexpr int NB0 = NPROBE > 32 ? 32 : NPROBE;          // probes recorded in acc0
-
-    uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    uint4 nv = make_uint4(0, 0, 0, 0);
-    uint32_t nw4 = 0;
-    if (g < n_groups) {
-        const uint64_t c = (g << 5) + lane;
-        if (c < n_chunks) {
-            nv = __ldg(reinterpret_cast<const uint4 *>(packed) + c);
-            nw4 = __ldg(packed + 4 * c + 4);
-        }
-    }
-    for (; g < n_groups; g += n_warps) {
-        uint32_t W[5];
-        W[0] = nv.x; W[1] = nv.y; W[2] = nv.z; W[3] = nv.w; W[4] = nw4;
-        {
-            const uint64_t gn = g + n_warps, cn = (gn << 5) + lane;
-            if (gn < n_groups && cn < n_chunks) {
-                nv = __ldg(reinterpret_cast<const uint4 *>(packed) + cn);
-                nw4 = __ldg(packed + 4 * cn + 4);
-            }
-        }
-        const bool live = ((g << 5) + lane) < n_chunks;
-        // one result bit per probe: probe i ends up at bit NB0-1-i of acc0 (i < 32) or bit NPROBE-1-i of acc1
-        uint32_t acc0 = 0, acc1 = 0;
-#pragma unroll
-        for (int i = 0; i < NPROBE; i++) {
-            const int a = i * G, j = a >> 4, o = a & 15;
-            uint32_t x = window16(W[j], W[j + 1], o);
-            if (HASHED) x = (x >> ksh) * 0x9E3779B1u;
-            const uint32_t word = tbl[x >> wsh];
-            const uint32_t t = __funnelshift_l(0u, word, x >> bsh);          // wanted bit -> bit 31
-            if (i < 32) acc0 = __funnelshift_l(t, acc0, 1);
-            else acc1 = __funnelshift_l(t, acc1, 1);
-        }
-        if (!live) { acc0 = 0; acc1 = 0; }
-        // warp-level compaction of the positives
-        const uint32_t cnt = __popc(acc0) + __popc(acc1);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        const uint64_t gbase = g << 11;                      // first base of this warp's block
-        if (total <= FILTER_WQ) {
-            uint32_t off = incl - cnt;
-            const uint32_t rel = (uint32_t)lane << 6;
-            while (acc0) {
-                const int bit = 31 - __clz(acc0);
-                acc0 &= ~(1u << bit);
-                wq[off++] = rel + (uint32_t)((NB0 - 1 - bit) * G);
-            }
-            while (acc1) {
-                const int bit = 31 - __clz(acc1);
-                acc1 &= ~(1u << bit);
-                wq[off++] = rel + (uint32_t)((NPROBE - 1 - bit) * G);
-            }
-            __syncwarp();
-            for (uint32_t i = lane; i < total * G; i += 32) {
-                const uint64_t a = gbase + wq[i / G];
-                const uint32_t r = i % G;
-                if (a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
-            }
-            __syncwarp();
-        } else {
-            // more positives than the queue holds (dense tables): every lane verifies its own
-            const uint64_t cb = gbase + ((uint64_t)lane << 6);
-            while (acc0) {
-                const int bit = 31 - __clz(acc0);
-                acc0 &= ~(1u << bit);
-                const uint64_t a = cb + (uint64_t)((NB0 - 1 - bit) * G);
+    if (MODE >= MODE_BYTE_Q8) {
 #pragma unroll 1
-                for (int r = 0; r < G; r++)
-                    if (a >= (uint64_t)r) verify_exact(packed, exact, a - r, n_bases, m, out);
+        for (int half = 0; half < 2; half++) {
+            uint32_t acc = half ? a1 : a0;
+            while (acc) {
+                const int nib = (31 - __clz(acc)) >> 2;              // highest non-empty nibble
+                uint32_t mask = (acc >> (nib * 4)) & 15u;
+                acc &= ~(15u << (nib * 4));
+                const uint64_t a = cbase + (uint64_t)((half * 8 + (7 - nib)) * G);
+                while (mask) {
+                    const uint32_t r = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
+                }
             }
-            while (acc1) {
-                const int bit = 31 - __clz(acc1);
-                acc1 &= ~(1u << bit);
-                const uint64_t a = cb + (uint64_t)((NPROBE - 1 - bit) * G);
+        }
+    } else {
+        constexpr int NB0 = NPROBE > 32 ? 32 : NPROBE;               // probes recorded in a0
 #pragma unroll 1
-                for (int r = 0; r < G; r++)
-                    if (a >= (uint64_t)r) verify_exact(packed, exact, a - r, n_bases, m, out);
+        for (int half = 0; half < (NPROBE > 32 ? 2 : 1); half++) {
+            uint32_t acc = half ? a1 : a0;
+            while (acc) {
+                const int bit = 31 - __clz(acc);
+                acc &= ~(1u << bit);
+                const int probe = half ? (NPROBE - 1 - bit) : (NB0 - 1 - bit);
+                const uint64_t a = cbase + (uint64_t)(probe * G);
+#pragma unroll 1
+                for (uint32_t r = 0; r < (uint32_t)G; r++)
+                    if (a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
             }
         }
     }
 }
 
-// ------------------------------------------------- byte-table filter (2q <= 16)
-
-// Same idea with a denser encoding for short keys: the table has one BYTE per
-// q-gram and the byte is the mask of phases r (0..G-1) at which some selected
-// m-mer carries that q-gram.  A probe is then a byte extract (PRMT when the key
-// is the 16 bits of two whole bytes), an 8-bit shared load whose address is the
-// key itself, and one multiply-add that appends the 4-bit mask to a per-lane
-// accumulator (8 probes per 32-bit register).  Only the phases named by the
-// mask are verified.  Each lane handles FILTER8_CH chunks per iteration before
-// the warp verifies its queue, which amortises the compaction and the verify
-// pass over 8192 bases.
-template <bool Q8>
-__global__ void __launch_bounds__(FILTER8_THREADS, FILTER8_CTAS_PER_SM)
-scan_filter8_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m, FilterParams fp,
-                    const uint32_t *__restrict__ table_g, const uint32_t *__restrict__ exact, ScanOut out)
+template <int G, int MODE, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+scan_filter_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m, FilterParams fp,
+                   const uint32_t *__restrict__ table_g, const uint32_t *__restrict__ exact, ScanOut out)
 {
-    constexpr int G = 4, NPROBE = 16, CH = FILTER8_CH;
-    extern __shared__ uint32_t smem[];
-    const uint32_t tbl_bytes = 1u << (2 * fp.q);
-    const uint8_t *tbl = reinterpret_cast<const uint8_t *>(smem);
+    constexpr int NPROBE = 64 / G, CH = FILTER_CH;
+    static_assert(MODE < MODE_BYTE_Q8 || G == 4, "byte tables use G = 4");
+    extern __shared__ __align__(128) uint32_t smem[];
+    const uint32_t tbl_bytes = (uint32_t)filter_table_bytes(fp);
+    const uint8_t *tbl8 = reinterpret_cast<const uint8_t *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *wq = smem + (tbl_bytes >> 2) + warp * (FILTER_WQ + 1);   // [0] = count, then entries
-    uint32_t *wcnt = wq;
-    wq += 1;
+    uint32_t *wq = smem + (tbl_bytes >> 2) + warp * (FILTER_WQ * 3);  // entries {chunk id in group, acc0, acc1}
 
-    for (uint32_t i = threadIdx.x; i < (tbl_bytes >> 2); i += blockDim.x) smem[i] = __ldg(table_g + i);
-    if (lane == 0) *wcnt = 0;
-    __syncthreads();
-    if (n_bases < (uint64_t)m) return;
+    __shared__ __align__(8) uint64_t tbl_bar;
+    const bool use_tma = tbl_bytes >= 16;
+    if (use_tma) {
+        if (threadIdx.x == 0) mbar_init(&tbl_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(smem, table_g, tbl_bytes, &tbl_bar);
+    } else {
+        for (uint32_t i = threadIdx.x; i < (tbl_bytes >> 2); i += blockDim.x) smem[i] = __ldg(table_g + i);
+        __syncthreads();
+    }
+    if (n_bases < (uint64_t)m) { if (use_tma) mbar_wait(&tbl_bar, 0); return; }
 
     const uint64_t n_pos = n_bases - m + 1;
-    const uint64_t n_chunks = (n_pos + G - 1 + 63) >> 6;
-    const uint64_t n_groups = (n_chunks + 32 * CH - 1) / (32 * CH);   // one group = CH x 32 chunks
+    const uint64_t n_chunks = (n_pos + G - 1 + 63) >> 6;    // aligned probes reach G-1 past the last m-mer start
+    const uint64_t n_groups = (n_chunks + 32 * CH - 1) / (32 * CH);
     const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const int ksh = 32 - 2 * fp.q;
+    const int ksh = 32 - 2 * fp.q;                          // window -> clean key
+    const int wsh = 32 - (fp.bits - 5);                     // bit table: index -> word number
+    const int bsh = 32 - fp.bits;                           // bit table: index -> bit number (low 5 bits used)
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     uint4 nv = make_uint4(0, 0, 0, 0);
@@ -321,90 +257,81 @@ scan_filter8_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m
         const uint64_t c = g * (32 * CH) + lane;
         if (c < n_chunks) {
             nv = __ldg(reinterpret_cast<const uint4 *>(packed) + c);
-            nw4 = __ldg(packed + 4 * c + 4);
+            if (lane == 31) nw4 = __ldg(packed + 4 * c + 4);
         }
     }
+    if (use_tma) mbar_wait(&tbl_bar, 0);
     for (; g < n_groups; g += n_warps) {
         const uint64_t gchunk = g * (32 * CH);               // first chunk of the group
+        uint32_t qn = 0;                                     // queued entries (warp-uniform)
 #pragma unroll 1
         for (int kk = 0; kk < CH; kk++) {
             uint32_t W[5];
-            W[0] = nv.x; W[1] = nv.y; W[2] = nv.z; W[3] = nv.w; W[4] = nw4;
+            W[0] = nv.x; W[1] = nv.y; W[2] = nv.z; W[3] = nv.w;
+            W[4] = __shfl_down_sync(0xffffffffu, nv.x, 1);   // halo = neighbour lane's first word
+            if (lane == 31) W[4] = nw4;
             {
                 // next chunk of this lane: same group (kk+1) or the first of the warp's next group
                 const uint64_t cn = (kk + 1 < CH) ? gchunk + (uint64_t)(kk + 1) * 32 + lane
                                                  : (g + n_warps) * (32 * CH) + lane;
                 if (cn < n_chunks) {
                     nv = __ldg(reinterpret_cast<const uint4 *>(packed) + cn);
-                    nw4 = __ldg(packed + 4 * cn + 4);
+                    if (lane == 31) nw4 = __ldg(packed + 4 * cn + 4);
                 }
             }
             const bool live = (gchunk + (uint64_t)kk * 32 + lane) < n_chunks;
-            // probe i leaves its 4-bit phase mask in nibble (7 - i%8) of acc[i/8]
             uint32_t acc0 = 0, acc1 = 0;
+            if (MODE >= MODE_BYTE_Q8) {
+                // probe i leaves its 4-bit phase mask in nibble (7 - i%8) of acc[i/8]
 #pragma unroll
-            for (int i = 0; i < NPROBE; i++) {
-                const int j = i >> 2, ob = i & 3;            // word, byte offset of the probe (4 bases per byte)
-                uint32_t key;
-                if (Q8) {
-                    if (ob == 0) key = __byte_perm(W[j], 0u, 0x4432);
-                    else if (ob == 1) key = __byte_perm(W[j], 0u, 0x4421);
-                    else if (ob == 2) key = __byte_perm(W[j], 0u, 0x4410);
-                    else key = __funnelshift_l(W[j + 1], W[j], 24) >> 16;
-                } else {
-                    key = window16(W[j], W[j + 1], ob * 4) >> ksh;
-                }
-                const uint32_t val = tbl[key];
-                if (i < 8) acc0 = acc0 * 16u + val;
-                else acc1 = acc1 * 16u + val;
-            }
-            if (!live) { acc0 = 0; acc1 = 0; }
-            if (acc0 | acc1) {
-                // nonzero nibbles -> one flag bit each, then claim queue slots
-                uint32_t f0 = (acc0 | (acc0 >> 1) | (acc0 >> 2) | (acc0 >> 3)) & 0x11111111u;
-                uint32_t f1 = (acc1 | (acc1 >> 1) | (acc1 >> 2) | (acc1 >> 3)) & 0x11111111u;
-                const uint32_t cnt = __popc(f0) + __popc(f1);
-                uint32_t off = atomicAdd(wcnt, cnt);
-                const uint32_t rel = ((uint32_t)kk * 32 + lane) << 6;    // chunk start relative to the group
-#pragma unroll 1
-                for (int half = 0; half < 2; half++) {
-                    uint32_t f = half ? f1 : f0;
-                    const uint32_t acc = half ? acc1 : acc0;
-                    while (f) {
-                        const int bit = 31 - __clz(f);       // multiple of 4: nibble index = bit / 4
-                        f &= ~(1u << bit);
-                        const uint32_t mask = (acc >> bit) & 15u;
-                        const uint32_t a = rel + (uint32_t)((half * 8 + (7 - (bit >> 2))) * G);
-                        const uint32_t ent = (a << 4) | mask;
-                        if (off < FILTER_WQ) {
-                            wq[off] = ent;
-                        } else {
-                            // queue full: verify inline
-                            const uint64_t pa = (gchunk << 6) + a;
-#pragma unroll 1
-                            for (int r = 0; r < G; r++)
-                                if (((mask >> r) & 1u) && pa >= (uint64_t)r)
-                                    verify_exact(packed, exact, pa - r, n_bases, m, out);
-                        }
-                        off++;
+                for (int i = 0; i < 16; i++) {
+                    const int j = i >> 2, ob = i & 3;        // word, byte offset of the probe (4 bases per byte)
+                    uint32_t key;
+                    if (MODE == MODE_BYTE_Q8) {
+                        if (ob == 0) key = __byte_perm(W[j], 0u, 0x4432);
+                        else if (ob == 1) key = __byte_perm(W[j], 0u, 0x4421);
+                        else if (ob == 2) key = __byte_perm(W[j], 0u, 0x4410);
+                        else key = __funnelshift_l(W[j + 1], W[j], 24) >> 16;
+                    } else {
+                        key = window16(W[j], W[j + 1], ob * 4) >> ksh;
                     }
+                    const uint32_t val = tbl8[key];
+                    if (i < 8) acc0 = acc0 * 16u + val;
+                    else acc1 = acc1 * 16u + val;
+                }
+            } else {
+                // probe i ends up at bit NB0-1-i of acc0 (i < 32) or bit NPROBE-1-i of acc1
+#pragma unroll
+                for (int i = 0; i < NPROBE; i++) {
+                    const int a = i * G, j = a >> 4, o = a & 15;
+                    uint32_t x = window16(W[j], W[j + 1], o);
+                    if (MODE == MODE_BIT_HASHED) x = (x >> ksh) * 0x9E3779B1u;
+                    const uint32_t word = smem[x >> wsh];
+                    const uint32_t t = __funnelshift_l(0u, word, x >> bsh);  // wanted bit -> bit 31
+                    if (i < 32) acc0 = __funnelshift_l(t, acc0, 1);
+                    else acc1 = __funnelshift_l(t, acc1, 1);
                 }
             }
-        }
-        __syncwarp();
-        const uint32_t total = min(*wcnt, (uint32_t)FILTER_WQ);
-        if (total) {
-            const uint64_t gbase = gchunk << 6;
-            // 4 (phase) lanes per entry
-            for (uint32_t i = lane; i < total * G; i += 32) {
-                const uint32_t ent = wq[i >> 2];
-                const uint32_t r = i & 3;
-                const uint64_t a = gbase + (ent >> 4);
-                if (((ent >> r) & 1u) && a >= r) verify_exact(packed, exact, a - r, n_bases, m, out);
+            const bool pos = live && (acc0 | acc1) != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, pos);
+            if (pos) {
+                uint32_t *e = wq + (qn + __popc(bal & lt_mask)) * 3;
+                e[0] = (uint32_t)kk * 32 + lane;
+                e[1] = acc0;
+                e[2] = acc1;
             }
-            __syncwarp();
-            if (lane == 0) *wcnt = 0;
-            __syncwarp();
+            qn += __popc(bal);
+            // the queue always has room for one more chunk (32 entries); verify when it could overflow
+            if (qn > FILTER_WQ - 32 || kk == CH - 1) {
+                __syncwarp();
+                const uint64_t gbase = gchunk << 6;
+                for (uint32_t ei = lane; ei < qn; ei += 32) {
+                    const uint32_t *e = wq + ei * 3;
+                    verify_entry<G, MODE>(packed, exact, gbase + ((uint64_t)e[0] << 6), e[1], e[2], n_bases, m, out);
+                }
+                __syncwarp();
+                qn = 0;
+            }
         }
     }
 }
@@ -450,56 +377,40 @@ cudaError_t launch_filter_build(int m, uint64_t thr, FilterParams fp, uint32_t *
     return cudaGetLastError();
 }
 
-template <int G, bool HASHED>
-static cudaError_t launch_filter_g(const uint32_t *d_packed, uint64_t n_bases, int m, FilterParams fp,
+template <int G, int MODE, int THREADS, int CTAS>
+static cudaError_t launch_filter_t(const uint32_t *d_packed, uint64_t n_bases, int m, FilterParams fp,
                                    const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
 {
-    const int threads = FILTER_THREADS;
-    size_t smem = ((size_t)1 << (fp.bits - 3)) + (size_t)(threads / 32) * FILTER_WQ * sizeof(uint32_t);
+    auto kern = scan_filter_kernel<G, MODE, THREADS, CTAS>;
+    size_t smem = filter_table_bytes(fp) + (size_t)(THREADS / 32) * (FILTER_WQ * 3) * sizeof(uint32_t);
     static bool attr_set = false;
+    static int per_sm = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_filter_kernel<G, HASHED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(FILTER_MAX_SMEM + (FILTER_THREADS / 32) * FILTER_WQ * sizeof(uint32_t)));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(FILTER_MAX_SMEM + (THREADS / 32) * (FILTER_WQ * 3) * sizeof(uint32_t)));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    uint64_t n_chunks = ((n_bases - m + 1) + G - 1 + 63) >> 6;
-    uint64_t n_groups = (n_chunks + 31) >> 5;
-    uint64_t want = (n_groups + (threads / 32) - 1) / (threads / 32);     // CTAs if every warp took one group
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_filter_kernel<G, HASHED>, threads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (per_sm < 1) per_sm = 1;
+    uint64_t n_chunks = ((n_bases - m + 1) + G - 1 + 63) >> 6;
+    uint64_t n_groups = (n_chunks + 32 * FILTER_CH - 1) / (32 * FILTER_CH);
+    uint64_t want = (n_groups + (THREADS / 32) - 1) / (THREADS / 32);     // CTAs if every warp took one group
     uint64_t blocks = (uint64_t)sm_count() * per_sm;
     if (blocks > want) blocks = want;
     if (blocks < 1) blocks = 1;
-    scan_filter_kernel<G, HASHED><<<(unsigned)blocks, threads, smem, st>>>(d_packed, n_bases, m, fp, d_table, d_exact, out);
+    kern<<<(unsigned)blocks, THREADS, smem, st>>>(d_packed, n_bases, m, fp, d_table, d_exact, out);
     return cudaGetLastError();
 }
 
-template <bool Q8>
-static cudaError_t launch_filter8(const uint32_t *d_packed, uint64_t n_bases, int m, FilterParams fp,
-                                  const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
+// Tables of up to 64 KB run as 2 CTAs x 768 threads per SM; the 128 KB bit table as 1 CTA x 1024.
+template <int G, int MODE>
+static cudaError_t launch_filter_m(const uint32_t *d_packed, uint64_t n_bases, int m, FilterParams fp,
+                                   const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
 {
-    const int threads = FILTER8_THREADS;
-    size_t smem = filter_table_bytes(fp) + (size_t)(threads / 32) * (FILTER_WQ + 1) * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_filter8_kernel<Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(((size_t)64 << 10) + (FILTER8_THREADS / 32) * (FILTER_WQ + 1) * sizeof(uint32_t)));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    uint64_t n_chunks = ((n_bases - m + 1) + 4 - 1 + 63) >> 6;
-    uint64_t n_groups = (n_chunks + 32 * FILTER8_CH - 1) / (32 * FILTER8_CH);
-    uint64_t want = (n_groups + (threads / 32) - 1) / (threads / 32);
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_filter8_kernel<Q8>, threads, smem);
-    if (per_sm < 1) per_sm = 1;
-    uint64_t blocks = (uint64_t)sm_count() * per_sm;
-    if (blocks > want) blocks = want;
-    if (blocks < 1) blocks = 1;
-    scan_filter8_kernel<Q8><<<(unsigned)blocks, threads, smem, st>>>(d_packed, n_bases, m, fp, d_table, d_exact, out);
-    return cudaGetLastError();
+    if (filter_table_bytes(fp) <= ((size_t)64 << 10))
+        return launch_filter_t<G, MODE, 768, 2>(d_packed, n_bases, m, fp, d_table, d_exact, out, st);
+    return launch_filter_t<G, MODE, 1024, 1>(d_packed, n_bases, m, fp, d_table, d_exact, out, st);
 }
 
 cudaError_t launch_scan_filter(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, FilterParams fp,
@@ -507,19 +418,19 @@ cudaError_t launch_scan_filter(const uint32_t *d_packed, uint64_t n_bases, int m
 {
     (void)thr;
     if (n_bases < (uint64_t)m) return cudaSuccess;
+#define SPSP_F(G_, M_) return launch_filter_m<G_, M_>(d_packed, n_bases, m, fp, d_table, d_exact, out, st)
     if (fp.kind == 1) {
         if (fp.g != 4 || 2 * fp.q > 16) return cudaErrorInvalidValue;
-        return fp.q == 8 ? launch_filter8<true>(d_packed, n_bases, m, fp, d_table, d_exact, out, st)
-                         : launch_filter8<false>(d_packed, n_bases, m, fp, d_table, d_exact, out, st);
+        if (fp.q == 8) SPSP_F(4, MODE_BYTE_Q8);
+        SPSP_F(4, MODE_BYTE);
     }
-#define SPSP_F(G_, H_) return launch_filter_g<G_, H_>(d_packed, n_bases, m, fp, d_table, d_exact, out, st)
     switch (fp.g * 2 + (fp.hashed ? 1 : 0)) {
-    case 2: SPSP_F(1, false);
-    case 3: SPSP_F(1, true);
-    case 4: SPSP_F(2, false);
-    case 5: SPSP_F(2, true);
-    case 8: SPSP_F(4, false);
-    case 9: SPSP_F(4, true);
+    case 2: SPSP_F(1, MODE_BIT_DIRECT);
+    case 3: SPSP_F(1, MODE_BIT_HASHED);
+    case 4: SPSP_F(2, MODE_BIT_DIRECT);
+    case 5: SPSP_F(2, MODE_BIT_HASHED);
+    case 8: SPSP_F(4, MODE_BIT_DIRECT);
+    case 9: SPSP_F(4, MODE_BIT_HASHED);
     default: return cudaErrorInvalidValue;
     }
 #undef SPSP_F

@@ -24,12 +24,8 @@ struct FilterParams {
 
 constexpr int FILTER_MAX_BITS = 20;          // 128 KB of shared memory
 constexpr size_t FILTER_MAX_SMEM = (size_t)1 << (FILTER_MAX_BITS - 3);   // table incl. replication
-constexpr int FILTER_THREADS = 512;          // 16 warps per CTA
-constexpr int FILTER_CTAS_PER_SM = 3;        // register budget: 65536 / (512 * 3) = 42 per thread
-constexpr int FILTER_WQ = 128;               // candidate queue entries per warp
-constexpr int FILTER8_THREADS = 768;         // byte-table kernel: 2 CTAs x 24 warps per SM (64 KB table each)
-constexpr int FILTER8_CTAS_PER_SM = 2;
-constexpr int FILTER8_CH = 4;                // 64-base chunks per lane per iteration
+constexpr int FILTER_CH = 4;                 // 64-base chunks per lane per iteration (8192 bases per warp)
+constexpr int FILTER_WQ = 64;                // queue entries (3 words each) per warp
 
 __host__ __device__ __forceinline__ size_t filter_table_bytes(const FilterParams &fp)
 {

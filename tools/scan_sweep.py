@@ -32,10 +32,12 @@ def run(k, m, s, mode, n_bases=320_000_000, reps=20):
     print(json.dumps({"k": k, "m": m, "s": s, "mode": mode, "G": os.environ.get("SPSP_FILTER_G"),
                       "rep": os.environ.get("SPSP_FILTER_REP"), "ms": round(t, 4), "min_ms": round(min(ms), 4),
                       "tbp_s": round(n_bases / (t * 1e-3) / 1e12, 3), "gb_s": round(gbs, 1),
-                      "frac_hbm": round(gbs / 6534.8, 4), "hits": n}), flush=True)
+                      "frac_hbm": round(gbs / 6534.8, 4), "hits": n, "n_bases": n_bases,
+                      "kind": os.environ.get("SPSP_FILTER_KIND")}), flush=True)
     ctx.close()
 
 if __name__ == "__main__":
     k, m, s = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
     mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-    run(k, m, s, mode)
+    nb = int(float(sys.argv[5])) if len(sys.argv) > 5 else 320_000_000
+    run(k, m, s, mode, n_bases=nb)
