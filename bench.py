@@ -46,6 +46,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def measured_traffic(bases_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if abs(bases_per_launch - 320012288) < 1e6:
+            return t["traffic_bytes_per_launch"], t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -334,12 +347,14 @@ def b200_arm(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), out
 
+    # nvidia-smi needs ~0.2 s to start reporting: sample over both timed regions (device busy throughout)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
     t_res, (sks_res, cmp_res) = timed(resident_step, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
     t_e2e, (sks_e2e, cmp_e2e) = timed(lambda i, rec: e2e_step(rec), args.steps, max(1, args.warmup - 2))
+    clocks = sampler.stop() if rank == 0 else None
 
     # both paths must produce the same bytes / counts
     assert sks_res == sks_e2e, "device-resident and host-buffer paths disagree"
@@ -373,7 +388,8 @@ def b200_arm(args, rank, world, local_rank):
                 "post_thread_s": stats.get("e2e_post_s")},
         "gpu_launches": stats["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "scan (q-gram filter or dense, see DESIGN.md)",
+                     "traffic": measured_traffic(n_total)[0], "traffic_source": measured_traffic(n_total)[1],
+                     "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src, "kernel": "scan (q-gram filter or dense, see DESIGN.md)",
                      "kernel_ms": scan_ms, "bases_per_launch": int(n_total), "hits_per_launch": int(stats["hits"]),
                      "kernel_tbp_per_s": n_total / (scan_ms * 1e-3) / 1e12},
         "phases_ms": {"sketch": statistics.mean(stats["sketch_s"]) * 1e3,
