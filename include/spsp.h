@@ -137,6 +137,39 @@ int spsp_cmp_run_device(spsp_ctx *ctx, uint32_t row_begin, uint32_t row_end, uin
                         uint32_t *d_out, uint64_t ld);
 int spsp_cmp_last_kernel_ms(spsp_ctx *ctx, float *ms);
 
+/* ---- sketch stage, whole batch on the device ------------------------------
+ * One call = scan + exact post-pass of a batch of inputs (files) packed back
+ * to back, entirely on the GPU (csrc/device/postpass.cu; CUB does the generic
+ * radix sorts / prefix sums): replaces parse_fasta_test's loop AND
+ * handle_superkmer / the writer loop (SubSampler.cpp:243-302, :352-504) for
+ * every input at once, and leaves the comparator's decoded elements
+ * (Comparator.cpp:97-264) resident on the device for spsp_cmp_load_batch.
+ *
+ * Records are described by host arrays (n_rec entries, ascending, global base
+ * offsets into the packed buffer): [rec_begin, rec_end) and the input each
+ * record belongs to (0 <= rec_input < n_inputs, non-decreasing).
+ * Result pointers stay valid until the next batch call on the same slot. */
+typedef struct {
+    const uint8_t *body;         /* sketch bytes after the header line, inputs back to back   */
+    const uint64_t *body_off;    /* [n_inputs + 1] byte range of each input inside body       */
+    const uint64_t *selected;    /* [n_inputs] selected k-mer occurrences (header field 3)    */
+    const uint64_t *elem_off;    /* [n_inputs + 1] compare elements (distinct canonical k-mers per bucket) */
+    uint64_t n_hits, n_elems;
+    float scan_ms, post_ms;      /* CUDA events on the slot's stream */
+} spsp_batch_result;
+
+/* packed: HOST buffer (pinned recommended), copied by the call. */
+int spsp_sketch_batch(spsp_ctx *ctx, int slot, const uint32_t *packed, uint64_t n_bases, const uint64_t *rec_begin,
+                      const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                      unsigned abundance, spsp_batch_result *res);
+/* d_packed: caller-owned DEVICE buffer of spsp_packed_words(n_bases) words. */
+int spsp_sketch_batch_device(spsp_ctx *ctx, int slot, const uint32_t *d_packed, uint64_t n_bases,
+                             const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input,
+                             uint64_t n_rec, uint32_t n_inputs, unsigned abundance, spsp_batch_result *res);
+/* Load the compare stage with the elements the last batch on `slot` left on the
+ * device (one sketch per input): the sketch -> compare hand-off without files. */
+int spsp_cmp_load_batch(spsp_ctx *ctx, int slot);
+
 /* Number of kernels this library launched on the context since creation. */
 int spsp_launch_count(spsp_ctx *ctx, uint64_t *n);
 

@@ -22,6 +22,27 @@ class SpspError(RuntimeError):
     pass
 
 
+class BatchResult(C.Structure):
+    """spsp_batch_result (include/spsp.h)."""
+    _fields_ = [("body", C.c_void_p), ("body_off", C.POINTER(C.c_uint64)), ("selected", C.POINTER(C.c_uint64)),
+                ("elem_off", C.POINTER(C.c_uint64)), ("n_hits", C.c_uint64), ("n_elems", C.c_uint64),
+                ("scan_ms", C.c_float), ("post_ms", C.c_float)]
+
+
+def batch_layout(packed_list, rec_off_list):
+    """Concatenate per-input packed buffers (each spsp_packed_words long, so every
+    input starts on a 64-base boundary) -> (words, n_bases, rec_begin, rec_end, rec_input)."""
+    base, begins, ends, inputs, off = [], [], [], [], 0
+    for i, (w, ro) in enumerate(zip(packed_list, rec_off_list)):
+        ro = np.asarray(ro, np.uint64)
+        begins.append(ro[:-1] + np.uint64(off)); ends.append(ro[1:] + np.uint64(off))
+        inputs.append(np.full(ro.size - 1, i, np.uint32))
+        off += int(np.asarray(w).size) * 16
+    words = np.concatenate(list(packed_list) + [np.zeros(64, np.uint32)])
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return words, off, cat(begins, np.uint64), cat(ends, np.uint64), cat(inputs, np.uint32)
+
+
 def build(force: bool = False) -> None:
     """Compile the CUDA device layer (sm_100a), the host layer and the CLIs in-tree."""
     args = ["make", "-C", CSRC, "all", "-j4"]
@@ -66,6 +87,10 @@ def device_lib():
         L.spsp_cmp_run_device.argtypes = L.spsp_cmp_run.argtypes
         L.spsp_cmp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.spsp_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.spsp_sketch_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
+        L.spsp_sketch_batch_device.argtypes = L.spsp_sketch_batch.argtypes
+        L.spsp_cmp_load_batch.argtypes = [C.c_void_p, C.c_int]
         _dev = L
     return _dev
 
@@ -419,6 +444,40 @@ class DeviceContext:
         p = C.c_void_p()
         _dcheck(self.L.spsp_stream(self.h, slot, C.byref(p)), "spsp_stream")
         return int(p.value or 0)
+
+    def sketch_batch(self, words, n_bases: int, rec_begin, rec_end, rec_input, n_inputs: int, s: float,
+                     abundance: int = 1, slot: int = 0, device_ptr: Optional[int] = None, info: Optional[dict] = None):
+        """Scan + device post-pass of a whole batch.  `words` is a host array (copied) unless
+        device_ptr gives a device-resident packed buffer.  Returns the sketch bytes of every input."""
+        rec_begin = np.ascontiguousarray(rec_begin, np.uint64)
+        rec_end = np.ascontiguousarray(rec_end, np.uint64)
+        rec_input = np.ascontiguousarray(rec_input, np.uint32)
+        res = BatchResult()
+        if device_ptr is None:
+            words = np.ascontiguousarray(words, np.uint32)
+            assert words.size >= packed_words(n_bases)
+            rc = self.L.spsp_sketch_batch(self.h, slot, words.ctypes.data, n_bases, rec_begin.ctypes.data,
+                                          rec_end.ctypes.data, rec_input.ctypes.data, rec_begin.size, n_inputs,
+                                          abundance, C.byref(res))
+        else:
+            rc = self.L.spsp_sketch_batch_device(self.h, slot, device_ptr, n_bases, rec_begin.ctypes.data,
+                                                 rec_end.ctypes.data, rec_input.ctypes.data, rec_begin.size, n_inputs,
+                                                 abundance, C.byref(res))
+        _dcheck(rc, "spsp_sketch_batch")
+        total = int(res.body_off[n_inputs])
+        body = C.string_at(res.body, total) if total else b""
+        hdr = f"{2 * self.k - self.m} {self.m} "
+        tail = " %f\n" % _f32(s)
+        out = []
+        for i in range(n_inputs):
+            out.append((hdr + str(int(res.selected[i])) + tail).encode() + body[int(res.body_off[i]):int(res.body_off[i + 1])])
+        if info is not None:
+            info.update(n_hits=int(res.n_hits), n_elems=int(res.n_elems), scan_ms=float(res.scan_ms),
+                        post_ms=float(res.post_ms), elem_off=[int(res.elem_off[i]) for i in range(n_inputs + 1)])
+        return out
+
+    def cmp_load_batch(self, slot: int = 0):
+        _dcheck(self.L.spsp_cmp_load_batch(self.h, slot), "spsp_cmp_load_batch")
 
     def cmp_load(self, sk_off: np.ndarray, minim: np.ndarray, klo: np.ndarray, khi: Optional[np.ndarray] = None):
         sk_off = np.ascontiguousarray(sk_off, np.uint64)

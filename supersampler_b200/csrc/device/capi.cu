@@ -11,6 +11,7 @@
 
 #include "../../../include/spsp.h"
 #include "compare.cuh"
+#include "postpass.cuh"
 #include "scan.cuh"
 
 using namespace spsp;
@@ -69,10 +70,16 @@ struct Slot {
     uint64_t hits_cap = 0;
     unsigned long long *d_count = nullptr;
     unsigned long long *h_count = nullptr;     // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     uint64_t n_bases = 0;
     bool pending = false;
     bool timed = false;
+    // whole-batch path
+    PostpassBuffers *pp = nullptr;
+    DevBuf b_rec_begin, b_rec_end, b_rec_input;
+    PostpassOut last_batch{};
+    uint32_t last_batch_inputs = 0;
+    bool has_batch = false;
 };
 
 struct spsp_ctx {
@@ -214,6 +221,7 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
         CK(cudaHostAlloc(&s.h_count, sizeof(unsigned long long), cudaHostAllocDefault));
         CK(cudaEventCreate(&s.ev0));
         CK(cudaEventCreate(&s.ev1));
+        CK(cudaEventCreate(&s.ev2));
     }
     CK(cudaEventCreate(&c->cev0));
     CK(cudaEventCreate(&c->cev1));
@@ -240,6 +248,9 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         cudaFreeHost(s.h_count);
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.ev2) cudaEventDestroy(s.ev2);
+        if (s.pp) postpass_buffers_destroy(s.pp);
+        s.b_rec_begin.release(); s.b_rec_end.release(); s.b_rec_input.release();
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     free_cmp(c);
@@ -543,6 +554,115 @@ extern "C" int spsp_cmp_last_kernel_ms(spsp_ctx *c, float *ms)
     CK(cudaEventSynchronize(c->cev1));
     CK(cudaEventElapsedTime(ms, c->cev0, c->cev1));
     return 0;
+}
+
+// ------------------------------------------------------------ whole batch
+
+static int batch_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n_bases, const uint64_t *rec_begin,
+                      const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                      unsigned abundance, spsp_batch_result *res)
+{
+    if (!res) return fail(-3, "spsp_sketch_batch: null result");
+    if (n_rec && (!rec_begin || !rec_end || !rec_input)) return fail(-3, "spsp_sketch_batch: null record arrays");
+    for (uint64_t r = 0; r < n_rec; r++) {
+        if (rec_begin[r] > rec_end[r] || rec_end[r] > n_bases || rec_input[r] >= n_inputs ||
+            (r && (rec_begin[r] < rec_end[r - 1] || rec_input[r] < rec_input[r - 1])))
+            return fail(-3, "spsp_sketch_batch: records must be ascending, disjoint and inside the buffer");
+    }
+    cudaStream_t st = s.stream;
+    const size_t nr = n_rec ? n_rec : 1;
+    CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
+    if (n_rec) {
+        CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, st));
+    }
+    // scan (grow the hit buffer and rescan if the estimate was too small)
+    const double p = (double)c->thr / 18446744073709551616.0;
+    uint64_t guess = (uint64_t)((double)n_bases * p * 1.5) + 4096;
+    if (guess > n_bases + 1) guess = n_bases + 1;
+    int rc = ensure_hits(s, guess);
+    if (rc) return rc;
+    uint64_t n_hits = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        ScanOut so{s.d_hits, s.d_count, s.hits_cap};
+        rc = launch_scan(c, s, d_packed, n_bases, so);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_hits = *s.h_count;
+        if (n_hits <= s.hits_cap) break;
+        rc = ensure_hits(s, n_hits + n_hits / 8 + 1024);
+        if (rc) return rc;
+    }
+    float scan_ms = 0;
+    CK(cudaEventElapsedTime(&scan_ms, s.ev0, s.ev1));
+    if (!s.pp) s.pp = postpass_buffers_create();
+    PostpassIn in{};
+    in.d_packed = d_packed; in.n_bases = n_bases; in.d_hits = s.d_hits; in.n_hits = n_hits;
+    in.d_rec_begin = static_cast<const uint64_t *>(s.b_rec_begin.p);
+    in.d_rec_end = static_cast<const uint64_t *>(s.b_rec_end.p);
+    in.d_rec_input = static_cast<const uint32_t *>(s.b_rec_input.p);
+    in.n_rec = n_rec; in.n_inputs = n_inputs; in.k = c->k; in.m = c->m; in.abundance = abundance;
+    CK(cudaEventRecord(s.ev1, st));
+    cudaError_t e = postpass_run(s.pp, in, &s.last_batch, st);
+    if (e != cudaSuccess) {
+        s.has_batch = false;
+        return fail(e == cudaErrorInvalidValue ? -4 : -1, std::string("device post-pass: ") + cudaGetErrorString(e));
+    }
+    CK(cudaEventRecord(s.ev2, st));
+    CK(cudaEventSynchronize(s.ev2));
+    float post_ms = 0;
+    CK(cudaEventElapsedTime(&post_ms, s.ev1, s.ev2));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->launches += s.last_batch.kernels_launched;
+    }
+    s.has_batch = true;
+    s.last_batch_inputs = n_inputs;
+    res->body = s.last_batch.h_body; res->body_off = s.last_batch.h_body_off; res->selected = s.last_batch.h_selected;
+    res->elem_off = s.last_batch.h_elem_off; res->n_hits = n_hits; res->n_elems = s.last_batch.n_elems;
+    res->scan_ms = scan_ms; res->post_ms = post_ms;
+    return 0;
+}
+
+extern "C" int spsp_sketch_batch_device(spsp_ctx *c, int slot, const uint32_t *d_packed, uint64_t n_bases,
+                                        const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input,
+                                        uint64_t n_rec, uint32_t n_inputs, unsigned abundance, spsp_batch_result *res)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_sketch_batch_device: bad ctx/slot");
+    CK(cudaSetDevice(c->device));
+    return batch_impl(c, c->slots[slot], d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+}
+
+extern "C" int spsp_sketch_batch(spsp_ctx *c, int slot, const uint32_t *packed, uint64_t n_bases, const uint64_t *rec_begin,
+                                 const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                                 unsigned abundance, spsp_batch_result *res)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_sketch_batch: bad ctx/slot");
+    if (!packed && n_bases) return fail(-3, "spsp_sketch_batch: null input");
+    Slot &s = c->slots[slot];
+    if (s.pending) return fail(-3, "spsp_sketch_batch: slot busy (collect first)");
+    CK(cudaSetDevice(c->device));
+    uint64_t words = spsp_packed_words(n_bases);
+    if (words > s.d_packed_words) {
+        if (s.d_packed) CK(cudaFree(s.d_packed));
+        s.d_packed = nullptr; s.d_packed_words = 0;
+        uint64_t cap = words + words / 4;
+        CK(cudaMalloc(&s.d_packed, cap * sizeof(uint32_t)));
+        s.d_packed_words = cap;
+    }
+    CK(cudaMemcpyAsync(s.d_packed, packed, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+}
+
+extern "C" int spsp_cmp_load_batch(spsp_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_cmp_load_batch: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (!s.has_batch) return fail(-3, "spsp_cmp_load_batch: no batch on this slot");
+    return spsp_cmp_load_device(c, s.last_batch_inputs, s.last_batch.h_elem_off, s.last_batch.d_minim, s.last_batch.d_klo,
+                                s.last_batch.d_khi);
 }
 
 extern "C" int spsp_launch_count(spsp_ctx *c, uint64_t *n)

@@ -1,0 +1,895 @@
+// Device post-pass of the sketch stage (see postpass.cuh).  Pipeline, all on
+// one stream, no host round trip until the sizes of the results are known:
+//
+//   hits ──K1 classify──▶ CUB sort by position ──K2 clusters──▶ K3 replay (count, write)
+//        ──▶ pieces ──K4 k-mer entries──▶ CUB stable sorts (key, bucket) ──K5 runs──▶
+//        unique k-mers (count mod 256, first order, pos_min) ──▶ buckets
+//        ──K6 greedy reconstruction (size, write)──▶ sketch bytes
+//        ──K7 canonical elements──▶ compare stage (device resident)
+//
+// The generic steps (radix sort, prefix sum) are CUB library calls; everything
+// that carries reference semantics is a kernel in this file, each citing the
+// reference lines it restates (via csrc/host/postpass.cpp, which it mirrors).
+#include "postpass.cuh"
+
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace spsp {
+
+// ------------------------------------------------------------------ helpers
+
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 1024;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    ~DBuf() { if (p) cudaFree(p); }
+};
+struct HBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 1024;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    ~HBuf() { if (p) cudaFreeHost(p); }
+};
+
+// counters kept on the device between kernels
+struct Counters {
+    unsigned long long n_valid, n_clusters, n_pieces, n_entries, n_unique, n_buckets, n_elems, body_bytes;
+};
+
+struct PostpassBuffers {
+    DBuf cnt, hkey, hval, hkey2, hval2, hhash, hrec, cflag, cid, cl_first, cl_np, cl_nk, cl_poff, cl_eoff;
+    DBuf pc_first, pc_nk, pc_min, pc_meta, pc_eoff;
+    DBuf eA, eklo, ekhi, epm, idx0, idx1, idx2, skey, skey2, head, uid;
+    DBuf uA, uklo, ukhi, ufirst, upm, ucnt, uhead, bflag, bidm, bstart, ukey32, ukey32b, uidx0, uidx1, uidx2, ins, seen;
+    DBuf bbytes, bnmax, boff, body, in_bytes, in_sel, in_elems, eflag, eoff, el_min, el_klo, el_khi, cubtmp;
+    HBuf h_cnt, h_body, h_in, h_off;
+};
+
+PostpassBuffers *postpass_buffers_create() { return new PostpassBuffers(); }
+void postpass_buffers_destroy(PostpassBuffers *b) { delete b; }
+
+struct K128 {
+    uint64_t lo, hi;
+};
+__device__ __forceinline__ bool k_eq(const K128 &a, const K128 &b) { return a.lo == b.lo && a.hi == b.hi; }
+__device__ __forceinline__ bool k_lt(const K128 &a, const K128 &b) { return a.hi != b.hi ? a.hi < b.hi : a.lo < b.lo; }
+__device__ __forceinline__ K128 k_shr(K128 a, int s)
+{
+    if (s == 0) return a;
+    if (s >= 64) return K128{s >= 128 ? 0 : a.hi >> (s - 64), 0};
+    return K128{(a.lo >> s) | (a.hi << (64 - s)), a.hi >> s};
+}
+__device__ __forceinline__ K128 k_shl(K128 a, int s)
+{
+    if (s == 0) return a;
+    if (s >= 64) return K128{0, s >= 128 ? 0 : a.lo << (s - 64)};
+    return K128{a.lo << s, (a.hi << s) | (a.lo >> (64 - s))};
+}
+__device__ __forceinline__ uint64_t rc_bits64(uint64_t x)
+{
+    uint64_t r = __brevll(x);
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    return r ^ 0xAAAAAAAAAAAAAAAAULL;
+}
+// reverse complement of a k-mer held right-aligned in 128 bits (utils.cpp:397-438 rcb)
+__device__ __forceinline__ K128 k_rc(K128 a, int k)
+{
+    K128 r{rc_bits64(a.hi), rc_bits64(a.lo)};
+    return k_shr(r, 128 - 2 * k);
+}
+// k-mer starting at global base `pos`, right-aligned (first base most significant)
+__device__ __forceinline__ K128 kmer_at(const uint32_t *__restrict__ w, uint64_t pos, int k)
+{
+    const uint64_t i = pos >> 4;
+    const int o = (int)(pos & 15);
+    uint32_t W[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) W[j] = __ldg(w + i + j);
+    uint32_t T[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) T[j] = __funnelshift_l(W[j + 1], W[j], 2 * o);
+    K128 top{((uint64_t)T[2] << 32) | T[3], ((uint64_t)T[0] << 32) | T[1]};
+    return k_shr(top, 128 - 2 * k);
+}
+__device__ __forceinline__ uint32_t base_of(const uint32_t *__restrict__ w, uint64_t pos)
+{
+    return (__ldg(w + (pos >> 4)) >> (30 - 2 * (pos & 15))) & 3u;
+}
+
+// last record r with rec_begin[r] <= pos (n_rec >= 1, rec_begin[0] <= pos assumed checked by caller)
+__device__ __forceinline__ long long find_rec(const uint64_t *__restrict__ rec_begin, uint64_t n_rec, uint64_t pos)
+{
+    uint64_t lo = 0, hi = n_rec;           // first index with begin > pos
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (rec_begin[mid] <= pos) lo = mid + 1; else hi = mid;
+    }
+    return (long long)lo - 1;
+}
+
+// ------------------------------------------------------------- K1 classify
+
+// A hit counts only if its m-mer lies inside one record of at least k bases
+// (host: build_sketch_t drops hits that straddle a record / records < k).
+__global__ void pp_classify_kernel(const spsp_hit *__restrict__ hits, uint64_t n_hits, const uint64_t *__restrict__ rec_begin,
+                                   const uint64_t *__restrict__ rec_end, uint64_t n_rec, int k, int m,
+                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, Counters *cnt)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits) return;
+    const uint64_t pos = hits[i].pos;
+    bool valid = false;
+    if (n_rec) {
+        long long r = find_rec(rec_begin, n_rec, pos);
+        if (r >= 0) {
+            uint64_t b = rec_begin[r], e = rec_end[r];
+            valid = pos + (uint64_t)m <= e && e - b >= (uint64_t)k;
+        }
+    }
+    key[i] = valid ? pos : ~0ULL;
+    val[i] = (hits[i].canon << 1) | (hits[i].rev & 1u);
+    if (valid) atomicAdd(&cnt->n_valid, 1ULL);
+}
+
+// ------------------------------------------------------------- K2 clusters
+
+// Hits closer than d = k-m apart (same record) can share a k-mer window and
+// must be replayed together; everything else is independent.
+__global__ void pp_cluster_flag_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, uint64_t n_hits,
+                                       const uint64_t *__restrict__ rec_begin, uint64_t n_rec, int d,
+                                       uint32_t *__restrict__ hrec, uint64_t *__restrict__ hhash,
+                                       uint32_t *__restrict__ cflag, const Counters *cnt)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits) return;
+    if (i >= cnt->n_valid) { cflag[i] = 0; return; }
+    const uint64_t pos = key[i];
+    const uint32_t r = (uint32_t)find_rec(rec_begin, n_rec, pos);
+    hrec[i] = r;
+    hhash[i] = xxh64_8((uint64_t)(val[i] >> 1));
+    bool start = true;
+    if (i > 0) {
+        const uint64_t pp = key[i - 1];
+        // gap == d + 1 still couples two hits: the k-mer after the older hit's last window already sees the
+        // newer one, and the rescan that fetches it applies the reference's position quirks
+        start = pp < rec_begin[r] || pos - pp > (uint64_t)d + 1;
+    }
+    cflag[i] = start ? 1u : 0u;
+}
+
+__global__ void pp_cluster_first_kernel(const uint32_t *__restrict__ cflag, const uint32_t *__restrict__ cid, uint64_t n_hits,
+                                        uint32_t *__restrict__ cl_first, Counters *cnt)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_hits || i >= cnt->n_valid) return;
+    if (cflag[i]) cl_first[cid[i]] = (uint32_t)i;
+    if (i + 1 == cnt->n_valid) cnt->n_clusters = cid[i] + cflag[i];
+}
+
+// --------------------------------------------------------------- K3 replay
+
+struct Track {
+    bool valid;
+    uint32_t canon;
+    uint64_t hash, posmin;
+    bool rev;
+};
+
+// regular_minimizer_pos restricted to hits (SubSampler.cpp:81-169), window of
+// k-mer c = hits [lo, hi); keeps the reference's position quirks (:88-93, :149-164).
+__device__ Track pp_rescan(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val,
+                           const uint64_t *__restrict__ hash, uint64_t rb, uint32_t lo, uint32_t hi, uint64_t c, uint64_t d)
+{
+    Track t{false, 0, 0, 0, false};
+    uint64_t position = 0;
+    for (uint32_t i = hi; i-- > lo;) {
+        const uint64_t p = key[i] - rb, h = hash[i];
+        const uint32_t cn = val[i] >> 1;
+        const bool rv = val[i] & 1u;
+        const uint64_t j = c + d - p;
+        if (j == 0) {
+            t.valid = true; t.canon = cn; t.hash = h; t.rev = rv;
+            position = rv ? 0 : d;
+        } else if (!t.valid || t.hash > h) {
+            t.valid = true; t.canon = cn; t.hash = h; t.rev = rv;
+            position = d - j;
+        } else if (cn == t.canon && rv == t.rev) {
+            if (t.rev && position > j) position = j;
+            if (!t.rev && position > d - j) position = d - j;
+        }
+    }
+    t.posmin = c + position;
+    return t;
+}
+
+// Sparse replay of SubSampler.cpp:352-454 over one cluster of hits.
+// WRITE = false: count pieces and k-mers; WRITE = true: store the pieces.
+template <bool WRITE>
+__global__ void pp_replay_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val,
+                                 const uint64_t *__restrict__ hash, const uint32_t *__restrict__ hrec,
+                                 const uint32_t *__restrict__ cl_first, const uint64_t *__restrict__ rec_begin,
+                                 const uint64_t *__restrict__ rec_end, const uint32_t *__restrict__ rec_input, int k, int m,
+                                 uint32_t *__restrict__ cl_np, uint32_t *__restrict__ cl_nk,
+                                 const uint32_t *__restrict__ cl_poff, uint64_t *__restrict__ pc_first,
+                                 uint32_t *__restrict__ pc_nk, uint32_t *__restrict__ pc_min, uint32_t *__restrict__ pc_meta,
+                                 uint64_t max_pieces, const Counters *cnt)
+{
+    const uint64_t c_id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c_id >= cnt->n_clusters) return;
+    const uint32_t i0 = cl_first[c_id];
+    const uint32_t i1 = (c_id + 1 < cnt->n_clusters) ? cl_first[c_id + 1] : (uint32_t)cnt->n_valid;
+    const uint32_t r = hrec[i0];
+    const uint64_t rb = rec_begin[r], n = rec_end[r] - rb;
+    const uint64_t d = (uint64_t)(k - m), K = n - k + 1;
+    const uint32_t input = rec_input[r];
+    uint32_t np = 0, nk = 0;
+    uint64_t out = WRITE ? cl_poff[c_id] : 0;
+    auto emit = [&](uint64_t first, uint64_t last, uint32_t mn, bool rev) {
+        if (WRITE) {
+            if (out < max_pieces) {
+                pc_first[out] = rb + first;
+                pc_nk[out] = (uint32_t)(last - first + 1);
+                pc_min[out] = mn;
+                pc_meta[out] = (input << 1) | (rev ? 1u : 0u);
+            }
+            out++;
+        }
+        np++;
+        nk += (uint32_t)(last - first + 1);
+    };
+    const uint64_t p_first = key[i0] - rb, p_last = key[i1 - 1] - rb;
+    uint32_t lo = i0, hi = i0;                      // hits with pos in [c, c+d] are [lo, hi)
+    auto window = [&](uint64_t c) {
+        while (hi < i1 && key[hi] - rb <= c + d) hi++;
+        while (lo < hi && key[lo] - rb < c) lo++;
+    };
+    Track cur{false, 0, 0, 0, false};
+    bool old_valid = false, old_rev = false, is_rev = false;
+    uint32_t old_min = 0;
+    uint64_t last = 0, c;
+    if (p_first <= d) {
+        // the record's first k-mer already sees a hit: initial rescan (:359-365)
+        window(0);
+        cur = pp_rescan(key, val, hash, rb, lo, hi, 0, d);
+        old_valid = cur.valid; old_rev = cur.rev; is_rev = cur.rev; old_min = cur.canon;
+        last = 0;
+        c = 1;
+    } else {
+        c = p_first - d;                          // the first hit enters on the right
+    }
+    const uint64_t c_end = p_last < K - 1 ? p_last : K - 1;   // after p_last the window holds no hit of this cluster
+    for (; c <= c_end; c++) {
+        window(c);
+        const uint64_t p = c + d;
+        bool dump = false;
+        const bool ent = hi > lo && key[hi - 1] - rb == p;
+        if (ent && (!cur.valid || hash[hi - 1] < cur.hash)) {                // :374-388
+            cur.valid = true; cur.canon = val[hi - 1] >> 1; cur.hash = hash[hi - 1]; cur.posmin = p;
+            cur.rev = val[hi - 1] & 1u; is_rev = cur.rev;
+        } else if (cur.valid && c - 1 >= cur.posmin) {                       // :391-398
+            cur = pp_rescan(key, val, hash, rb, lo, hi, c, d);
+            if (cur.valid) is_rev = cur.rev;
+            dump = true;
+        }
+        const bool changed = (old_valid != cur.valid) || (cur.valid && old_min != cur.canon);
+        if (changed || dump) {                                               // :401-435
+            if (old_valid) emit(last, c - 1, old_min, old_rev);
+            last = c;
+            old_valid = cur.valid; old_min = cur.canon; old_rev = is_rev;
+        }
+    }
+    // leaving the cluster: either the record ends here (:441-450), or at c_end + 1 the window holds no hit
+    // any more (the next hit is more than d + 1 away), the tracked minimizer is outdated (posmin <= p_last)
+    // and the rescan finds a non-selected one: the piece ends at c_end in both cases.
+    if (old_valid) emit(last, c_end, old_min, old_rev);
+    if (!WRITE) { cl_np[c_id] = np; cl_nk[c_id] = nk; }
+}
+
+// ---------------------------------------------------------- K4 k-mer entries
+
+// handle_superkmer (SubSampler.cpp:243-302): entry t is the (t - first entry of
+// its piece)-th k-mer of the oriented piece; key as oriented, pos_min = leftmost
+// occurrence of the minimizer in it.
+__global__ void pp_entries_kernel(const uint32_t *__restrict__ packed, const uint64_t *__restrict__ pc_first,
+                                  const uint32_t *__restrict__ pc_nk, const uint32_t *__restrict__ pc_min,
+                                  const uint32_t *__restrict__ pc_meta, const uint32_t *__restrict__ pc_eoff, int k, int m,
+                                  uint64_t bound, int input_shift, uint64_t *__restrict__ eA, uint64_t *__restrict__ eklo,
+                                  uint64_t *__restrict__ ekhi, uint8_t *__restrict__ epm, uint32_t *__restrict__ idx,
+                                  unsigned long long *__restrict__ in_sel, const Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bound) return;
+    idx[t] = (uint32_t)t;
+    if (t >= cnt->n_entries) {
+        eA[t] = ~0ULL; eklo[t] = ~0ULL;
+        if (ekhi) ekhi[t] = ~0ULL;
+        epm[t] = 0;
+        return;
+    }
+    // piece = last one whose first entry is <= t
+    uint64_t lo = 0, hi = cnt->n_pieces;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)pc_eoff[mid] <= t) lo = mid + 1; else hi = mid;
+    }
+    const uint64_t pc = lo - 1;
+    const uint32_t j = (uint32_t)(t - pc_eoff[pc]), nk = pc_nk[pc], mn = pc_min[pc], meta = pc_meta[pc];
+    const bool rev = meta & 1u;
+    const uint64_t pos = pc_first[pc] + (rev ? (nk - 1 - j) : j);
+    K128 key = kmer_at(packed, pos, k);
+    if (rev) key = k_rc(key, k);
+    const int d = k - m;
+    const uint32_t mmask = (1u << (2 * m)) - 1u;
+    unsigned pm = 255;
+    for (int q = 0; q <= d; q++) {
+        if (((uint32_t)k_shr(key, 2 * (d - q)).lo & mmask) == mn) { pm = (unsigned)q; break; }
+    }
+    eA[t] = ((uint64_t)(meta >> 1) << input_shift) | mn;
+    eklo[t] = key.lo;
+    if (ekhi) ekhi[t] = key.hi;
+    epm[t] = (uint8_t)pm;
+    atomicAdd(in_sel + (meta >> 1), 1ULL);
+}
+
+__global__ void pp_gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n,
+                                     uint64_t *__restrict__ dst)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[idx[t]];
+}
+
+// ------------------------------------------------------------ K5 runs / unique
+
+__global__ void pp_head_kernel(const uint64_t *__restrict__ sA, const uint32_t *__restrict__ idx,
+                               const uint64_t *__restrict__ eklo, const uint64_t *__restrict__ ekhi, uint64_t bound,
+                               uint32_t *__restrict__ head, const Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bound) return;
+    bool h = false;
+    if (t < cnt->n_entries) {
+        h = true;
+        if (t > 0) {
+            const uint32_t a = idx[t], b = idx[t - 1];
+            h = sA[t] != sA[t - 1] || eklo[a] != eklo[b] || (ekhi && ekhi[a] != ekhi[b]);
+        }
+    }
+    head[t] = h ? 1u : 0u;
+}
+
+__global__ void pp_unique_kernel(const uint64_t *__restrict__ sA, const uint32_t *__restrict__ idx,
+                                 const uint64_t *__restrict__ eklo, const uint64_t *__restrict__ ekhi,
+                                 const uint8_t *__restrict__ epm, const uint32_t *__restrict__ head,
+                                 const uint32_t *__restrict__ uid, uint64_t bound, uint64_t *__restrict__ uA,
+                                 uint64_t *__restrict__ uklo, uint64_t *__restrict__ ukhi, uint32_t *__restrict__ ufirst,
+                                 uint8_t *__restrict__ upm, uint32_t *__restrict__ uhead, Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bound || t >= cnt->n_entries) return;
+    if (head[t]) {
+        const uint32_t u = uid[t], e = idx[t];      // stable sorts: the run's first entry has the smallest order
+        uA[u] = sA[t]; uklo[u] = eklo[e];
+        if (ukhi) ukhi[u] = ekhi[e];
+        ufirst[u] = e; upm[u] = epm[e]; uhead[u] = (uint32_t)t;
+    }
+    if (t + 1 == cnt->n_entries) cnt->n_unique = uid[t] + head[t];
+}
+
+// count (mod 256, SubSampler.h:24) + bucket heads + keys for the insertion-order sort
+__global__ void pp_unique_finish_kernel(const uint64_t *__restrict__ uA, const uint32_t *__restrict__ uhead,
+                                        const uint32_t *__restrict__ ufirst, uint64_t bound, uint8_t *__restrict__ ucnt,
+                                        uint32_t *__restrict__ bflag, uint32_t *__restrict__ ukey32,
+                                        uint32_t *__restrict__ uidx, uint8_t *__restrict__ seen, const Counters *cnt)
+{
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= bound) return;
+    uidx[u] = (uint32_t)u;
+    seen[u] = 0;
+    if (u >= cnt->n_unique) { bflag[u] = 0; ukey32[u] = 0xFFFFFFFFu; return; }
+    const uint64_t next = (u + 1 < cnt->n_unique) ? uhead[u + 1] : cnt->n_entries;
+    ucnt[u] = (uint8_t)((next - uhead[u]) & 0xFF);
+    bflag[u] = (u == 0 || uA[u] != uA[u - 1]) ? 1u : 0u;
+    ukey32[u] = ufirst[u];
+}
+
+__global__ void pp_bucket_start_kernel(const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid, uint64_t bound,
+                                       uint32_t *__restrict__ bstart, Counters *cnt)
+{
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= bound || u >= cnt->n_unique) return;
+    if (bflag[u]) bstart[bid[u]] = (uint32_t)u;
+    if (u + 1 == cnt->n_unique) cnt->n_buckets = bid[u] + bflag[u];
+}
+
+__global__ void pp_gather_uA_kernel(const uint64_t *__restrict__ uA, const uint32_t *__restrict__ uidx, uint64_t bound,
+                                    uint64_t *__restrict__ dst, const Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bound) return;
+    const uint32_t u = uidx[t];
+    dst[t] = u < cnt->n_unique ? uA[u] : ~0ULL;
+}
+
+// -------------------------------------------------------- K6 reconstruction
+
+struct BucketView {
+    const uint64_t *uklo, *ukhi;
+    const uint8_t *ucnt;
+    uint8_t *seen;
+    uint32_t bs, be;
+    unsigned abundance;
+    int k;
+};
+
+__device__ __forceinline__ K128 bv_key(const BucketView &v, uint32_t u)
+{
+    return K128{v.uklo[u], v.ukhi ? v.ukhi[u] : 0};
+}
+// binary search in the bucket's key-sorted unique list
+__device__ __forceinline__ int bv_find(const BucketView &v, const K128 &key)
+{
+    uint32_t lo = v.bs, hi = v.be;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (k_lt(bv_key(v, mid), key)) lo = mid + 1; else hi = mid;
+    }
+    return (lo < v.be && k_eq(bv_key(v, lo), key)) ? (int)lo : -1;
+}
+// find_next (SubSampler.cpp:566-602): probe order A,T,C,G (:568)
+__device__ __forceinline__ int bv_step(const BucketView &v, const K128 &cur, bool left, K128 *out)
+{
+    const int k = v.k;
+    const K128 kmask = k_shr(K128{~0ULL, ~0ULL}, 128 - 2 * k);
+#pragma unroll 1
+    for (int t = 0; t < 4; t++) {
+        const uint64_t o = (t == 0) ? 0 : (t == 1) ? 2 : (t == 2) ? 1 : 3;
+        K128 nx;
+        if (left) {
+            nx = k_shr(cur, 2);
+            K128 top = k_shl(K128{o, 0}, 2 * k - 2);
+            nx.lo |= top.lo; nx.hi |= top.hi;
+        } else {
+            nx = k_shl(cur, 2);
+            nx.lo |= o;
+            nx.lo &= kmask.lo; nx.hi &= kmask.hi;
+        }
+        int u = bv_find(v, nx);
+        if (u >= 0 && !v.seen[u] && v.ucnt[u] >= v.abundance) {
+            v.seen[u] = 1;
+            *out = nx;
+            return u;
+        }
+    }
+    return -1;
+}
+
+// Writer loop + reconstruct_superkmer (SubSampler.cpp:459-504, :512-564) for one
+// bucket.  WRITE = false computes the byte size; WRITE = true emits the bytes.
+template <bool WRITE>
+__global__ void pp_reconstruct_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo,
+                                      const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
+                                      const uint8_t *__restrict__ upm, uint8_t *__restrict__ seen,
+                                      const uint32_t *__restrict__ ins, const uint32_t *__restrict__ bstart, int k, int m,
+                                      unsigned abundance, int input_shift, uint32_t *__restrict__ bbytes,
+                                      uint32_t *__restrict__ bnmax, const uint64_t *__restrict__ boff,
+                                      uint8_t *__restrict__ body, unsigned long long *__restrict__ in_bytes,
+                                      const Counters *cnt)
+{
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= cnt->n_buckets) return;
+    const uint32_t bs = bstart[b], be = (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
+    const int d = k - m, full = 2 * k - m;
+    BucketView v{uklo, ukhi, ucnt, seen, bs, be, abundance, k};
+    const uint32_t minimizer = (uint32_t)(uA[bs] & ((1ULL << input_shift) - 1));
+    const uint32_t mmask = (1u << (2 * m)) - 1u;
+    uint32_t n_max = 0, text_len = 0;
+    uint8_t *p_max = nullptr, *p_txt = nullptr;
+    if (WRITE) {
+        uint8_t *o = body + boff[b];
+        for (int i = 0; i < m; i++) o[i] = "ACTG"[(minimizer >> (2 * (m - 1 - i))) & 3];
+        const uint32_t nm = bnmax[b];
+        const uint32_t sz = nm ? 1 + nm * (uint32_t)(2 * d) / 4 : 0;          // strCompressor: mod byte + 4 bases/byte
+        o[m] = (uint8_t)sz; o[m + 1] = (uint8_t)(sz >> 8); o[m + 2] = (uint8_t)(sz >> 16); o[m + 3] = (uint8_t)(sz >> 24);
+        p_max = o + m + 4;
+        if (sz) *p_max++ = 0;                                               // 2d is a multiple of 4: mod byte 0
+        p_txt = o + m + 4 + sz;
+    }
+    uint8_t sk[192];                                                        // 2-bit codes of the super-k-mer (grows both ways from 64)
+    uint32_t cursor = bs;
+    for (;;) {
+        // find_first_kmer (:604-620): first unseen entry in insertion order
+        while (cursor < be && (seen[ins[cursor]] || ucnt[ins[cursor]] < abundance)) cursor++;
+        if (cursor >= be) break;
+        const uint32_t start = ins[cursor];
+        seen[start] = 1;
+        const K128 skey = bv_key(v, start);
+        int lo = 64, hi = 64 + k;
+        for (int i = 0; i < k; i++) sk[64 + i] = (uint8_t)(k_shr(skey, 2 * (k - 1 - i)).lo & 3);
+        uint64_t n_left = (uint64_t)d - upm[start], n_right = upm[start];
+        K128 cur = skey;
+        while (hi - lo != full) {
+            if (n_left != 0) {
+                K128 nx;
+                int u = bv_step(v, cur, true, &nx);
+                n_left--;
+                if (u >= 0) sk[--lo] = (uint8_t)(k_shr(nx, 2 * k - 2).lo & 3);
+                else n_left = 0;
+                cur = (n_left == 0) ? skey : nx;
+            } else if (n_right != 0) {
+                K128 nx;
+                int u = bv_step(v, cur, false, &nx);
+                n_right--;
+                if (u < 0) break;
+                sk[hi++] = (uint8_t)(nx.lo & 3);
+                cur = nx;
+            } else {
+                break;
+            }
+        }
+        const int len = hi - lo;
+        if (len == full) {                                                  // :479-485
+            if (WRITE) {
+                // prefix(d) + suffix(d), 4 bases per byte, first base in bits 7-6
+                uint32_t acc = 0;
+                int nb = 0;
+                for (int i = 0; i < 2 * d; i++) {
+                    const uint8_t c = (i < d) ? sk[lo + i] : sk[lo + k + (i - d)];
+                    acc = (acc << 2) | c;
+                    if (++nb == 4) { *p_max++ = (uint8_t)acc; acc = 0; nb = 0; }
+                }
+            }
+            n_max++;
+        } else {                                                            // :486-494
+            int q = -1;
+            uint32_t win = 0;
+            for (int t = 0; t < len; t++) {
+                win = ((win << 2) | sk[lo + t]) & mmask;
+                if (t + 1 >= m && win == minimizer) { q = t + 1 - m; break; }
+            }
+            if (q < 0) {
+                if (WRITE) { for (int t = 0; t < len; t++) *p_txt++ = "ACTG"[sk[lo + t]]; *p_txt++ = '\n'; *p_txt++ = '\n'; }
+                text_len += (uint32_t)len + 2;
+            } else {
+                if (WRITE) {
+                    for (int t = 0; t < q; t++) *p_txt++ = "ACTG"[sk[lo + t]];
+                    *p_txt++ = '\n';
+                    for (int t = q + m; t < len; t++) *p_txt++ = "ACTG"[sk[lo + t]];
+                    *p_txt++ = '\n';
+                }
+                text_len += (uint32_t)(len - m) + 2;
+            }
+        }
+    }
+    if (WRITE) {
+        *p_txt++ = '\n'; *p_txt++ = '\n';
+    } else {
+        const uint32_t sz = n_max ? 1 + n_max * (uint32_t)(2 * d) / 4 : 0;
+        const uint32_t bytes = (uint32_t)m + 4 + sz + text_len + 2;
+        bbytes[b] = bytes;
+        bnmax[b] = n_max;
+        atomicAdd(in_bytes + (uA[bs] >> input_shift), (unsigned long long)bytes);
+    }
+}
+
+__global__ void pp_clear_seen_kernel(uint8_t *__restrict__ seen, uint64_t bound)
+{
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < bound) seen[u] = 0;
+}
+
+// ------------------------------------------------------ K7 compare elements
+
+// What the comparator decodes from the sketch (Comparator.cpp:97-264): the
+// distinct canonical k-mers of every bucket.  A unique oriented k-mer is in the
+// sketch iff count >= abundance; two orientations of one k-mer collapse.
+__global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo,
+                                       const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
+                                       const uint32_t *__restrict__ bid, const uint32_t *__restrict__ bstart, int k,
+                                       unsigned abundance, int input_shift, uint64_t bound, uint32_t *__restrict__ eflag,
+                                       unsigned long long *__restrict__ in_elems, uint8_t *__restrict__ seen,
+                                       const Counters *cnt)
+{
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= bound) return;
+    bool keep = false;
+    if (u < cnt->n_unique && ucnt[u] >= abundance) {
+        keep = true;
+        const K128 key{uklo[u], ukhi ? ukhi[u] : 0};
+        const K128 rc = k_rc(key, k);
+        if (k_lt(rc, key)) {
+            // non-canonical orientation: drop it if the canonical one is in the bucket too
+            const uint32_t b = bid[u];
+            BucketView v{uklo, ukhi, ucnt, seen, bstart[b],
+                         (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique, abundance, k};
+            int o = bv_find(v, rc);
+            if (o >= 0 && ucnt[o] >= abundance) keep = false;
+        }
+        if (keep) atomicAdd(in_elems + (uA[u] >> input_shift), 1ULL);
+    }
+    eflag[u] = keep ? 1u : 0u;
+}
+
+__global__ void pp_element_write_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo,
+                                        const uint64_t *__restrict__ ukhi, const uint32_t *__restrict__ eflag,
+                                        const uint32_t *__restrict__ eoff, int k, int input_shift, uint64_t bound,
+                                        uint32_t *__restrict__ el_min, uint64_t *__restrict__ el_klo,
+                                        uint64_t *__restrict__ el_khi, Counters *cnt)
+{
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= bound) return;
+    if (u < cnt->n_unique && eflag[u]) {
+        K128 key{uklo[u], ukhi ? ukhi[u] : 0};
+        const K128 rc = k_rc(key, k);
+        if (k_lt(rc, key)) key = rc;
+        const uint32_t o = eoff[u];
+        el_min[o] = (uint32_t)(uA[u] & ((1ULL << input_shift) - 1));
+        el_klo[o] = key.lo;
+        if (el_khi) el_khi[o] = key.hi;
+    }
+    if (u + 1 == bound) cnt->n_elems = eoff[u] + eflag[u];
+}
+
+__global__ void pp_totals_kernel(const uint32_t *__restrict__ cl_np, const uint32_t *__restrict__ cl_nk,
+                                 const uint32_t *__restrict__ cl_poff, const uint32_t *__restrict__ cl_eoff, Counters *cnt)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long nc = cnt->n_clusters;
+        cnt->n_pieces = nc ? (unsigned long long)cl_poff[nc - 1] + cl_np[nc - 1] : 0;
+        cnt->n_entries = nc ? (unsigned long long)cl_eoff[nc - 1] + cl_nk[nc - 1] : 0;
+    }
+}
+
+__global__ void pp_body_total_kernel(const uint64_t *__restrict__ boff, const uint32_t *__restrict__ bbytes, Counters *cnt)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long nb = cnt->n_buckets;
+        cnt->body_bytes = nb ? boff[nb - 1] + bbytes[nb - 1] : 0;
+    }
+}
+
+__global__ void pp_piece_offsets_kernel(const uint32_t *__restrict__ pc_nk, uint64_t bound, uint32_t *__restrict__ tmp,
+                                        const Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < bound) tmp[t] = t < cnt->n_pieces ? pc_nk[t] : 0;
+}
+
+// ---------------------------------------------------------------- driver
+
+#define PP_CK(call)                                  \
+    do {                                             \
+        cudaError_t e_ = (call);                     \
+        if (e_ != cudaSuccess) return e_;            \
+    } while (0)
+
+static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t ? (n + t - 1) / t : 1); }
+
+template <class K, class V>
+static cudaError_t sort_pairs(PostpassBuffers *b, const K *kin, K *kout, const V *vin, V *vout, uint64_t n, int begin_bit,
+                              int end_bit, cudaStream_t st)
+{
+    size_t bytes = 0;
+    PP_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, begin_bit, end_bit, st));
+    PP_CK(b->cubtmp.ensure(bytes));
+    return cub::DeviceRadixSort::SortPairs(b->cubtmp.p, bytes, kin, kout, vin, vout, (int)n, begin_bit, end_bit, st);
+}
+template <class T, class O>
+static cudaError_t excl_sum(PostpassBuffers *b, const T *in, O *out, uint64_t n, cudaStream_t st)
+{
+    size_t bytes = 0;
+    PP_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st));
+    PP_CK(b->cubtmp.ensure(bytes));
+    return cub::DeviceScan::ExclusiveSum(b->cubtmp.p, bytes, in, out, (int)n, st);
+}
+
+static int bits_for(uint64_t v)
+{
+    int b = 0;
+    while (b < 64 && (v >> b)) b++;
+    return b ? b : 1;
+}
+
+cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *out, cudaStream_t st)
+{
+    const int k = in.k, m = in.m, d = k - m;
+    const bool hi128 = k > 32;
+    const uint64_t nh = in.n_hits;
+    uint32_t launched = 0;
+    // every k-mer is in at most one piece: entries <= min(hits * (d+1), bases)
+    uint64_t bound = nh * (uint64_t)(d + 1);
+    if (bound > in.n_bases) bound = in.n_bases;
+    if (bound < 1) bound = 1;
+    if (bound >= (1ULL << 31)) return cudaErrorInvalidValue;        // caller falls back to the host post-pass
+    const uint64_t nhb = nh ? nh : 1;
+    const int input_shift = 30;                                      // bucket id = input << 30 | minimizer (m <= 15)
+    const int a_bits = input_shift + bits_for(in.n_inputs ? in.n_inputs - 1 : 0) + 1;   // +1: padding entries sort last
+
+    PP_CK(b->cnt.ensure(sizeof(Counters)));
+    Counters *cnt = b->cnt.as<Counters>();
+    PP_CK(cudaMemsetAsync(cnt, 0, sizeof(Counters), st));
+    const size_t nin = in.n_inputs ? in.n_inputs : 1;
+    PP_CK(b->in_bytes.ensure(nin * 8)); PP_CK(b->in_sel.ensure(nin * 8)); PP_CK(b->in_elems.ensure(nin * 8));
+    PP_CK(cudaMemsetAsync(b->in_bytes.p, 0, nin * 8, st));
+    PP_CK(cudaMemsetAsync(b->in_sel.p, 0, nin * 8, st));
+    PP_CK(cudaMemsetAsync(b->in_elems.p, 0, nin * 8, st));
+
+    // ---- hits: classify, sort by position, clusters
+    PP_CK(b->hkey.ensure(nhb * 8)); PP_CK(b->hval.ensure(nhb * 4)); PP_CK(b->hkey2.ensure(nhb * 8)); PP_CK(b->hval2.ensure(nhb * 4));
+    PP_CK(b->hhash.ensure(nhb * 8)); PP_CK(b->hrec.ensure(nhb * 4)); PP_CK(b->cflag.ensure(nhb * 4)); PP_CK(b->cid.ensure(nhb * 4));
+    PP_CK(b->cl_first.ensure(nhb * 4)); PP_CK(b->cl_np.ensure(nhb * 4)); PP_CK(b->cl_nk.ensure(nhb * 4));
+    PP_CK(b->cl_poff.ensure(nhb * 4)); PP_CK(b->cl_eoff.ensure(nhb * 4));
+    if (nh) {
+        pp_classify_kernel<<<nblk(nh), 256, 0, st>>>(in.d_hits, nh, in.d_rec_begin, in.d_rec_end, in.n_rec, k, m,
+                                                     b->hkey.as<uint64_t>(), b->hval.as<uint32_t>(), cnt);
+        launched++;
+        PP_CK(sort_pairs(b, b->hkey.as<uint64_t>(), b->hkey2.as<uint64_t>(), b->hval.as<uint32_t>(), b->hval2.as<uint32_t>(),
+                         nh, 0, 64, st));
+        const uint64_t *key = b->hkey2.as<uint64_t>();
+        const uint32_t *val = b->hval2.as<uint32_t>();
+        pp_cluster_flag_kernel<<<nblk(nh), 256, 0, st>>>(key, val, nh, in.d_rec_begin, in.n_rec, d, b->hrec.as<uint32_t>(),
+                                                         b->hhash.as<uint64_t>(), b->cflag.as<uint32_t>(), cnt);
+        PP_CK(excl_sum(b, b->cflag.as<uint32_t>(), b->cid.as<uint32_t>(), nh, st));
+        pp_cluster_first_kernel<<<nblk(nh), 256, 0, st>>>(b->cflag.as<uint32_t>(), b->cid.as<uint32_t>(), nh,
+                                                          b->cl_first.as<uint32_t>(), cnt);
+        launched += 2;
+        // ---- replay: count, offsets, write
+        PP_CK(cudaMemsetAsync(b->cl_np.p, 0, nhb * 4, st));
+        PP_CK(cudaMemsetAsync(b->cl_nk.p, 0, nhb * 4, st));
+        PP_CK(b->pc_first.ensure(bound * 8)); PP_CK(b->pc_nk.ensure(bound * 4)); PP_CK(b->pc_min.ensure(bound * 4));
+        PP_CK(b->pc_meta.ensure(bound * 4)); PP_CK(b->pc_eoff.ensure(bound * 4));
+        pp_replay_kernel<false><<<nblk(nh, 128), 128, 0, st>>>(key, val, b->hhash.as<uint64_t>(), b->hrec.as<uint32_t>(),
+            b->cl_first.as<uint32_t>(), in.d_rec_begin, in.d_rec_end, in.d_rec_input, k, m, b->cl_np.as<uint32_t>(),
+            b->cl_nk.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, bound, cnt);
+        PP_CK(excl_sum(b, b->cl_np.as<uint32_t>(), b->cl_poff.as<uint32_t>(), nh, st));
+        PP_CK(excl_sum(b, b->cl_nk.as<uint32_t>(), b->cl_eoff.as<uint32_t>(), nh, st));
+        pp_totals_kernel<<<1, 32, 0, st>>>(b->cl_np.as<uint32_t>(), b->cl_nk.as<uint32_t>(), b->cl_poff.as<uint32_t>(),
+                                           b->cl_eoff.as<uint32_t>(), cnt);
+        pp_replay_kernel<true><<<nblk(nh, 128), 128, 0, st>>>(key, val, b->hhash.as<uint64_t>(), b->hrec.as<uint32_t>(),
+            b->cl_first.as<uint32_t>(), in.d_rec_begin, in.d_rec_end, in.d_rec_input, k, m, b->cl_np.as<uint32_t>(),
+            b->cl_nk.as<uint32_t>(), b->cl_poff.as<uint32_t>(), b->pc_first.as<uint64_t>(), b->pc_nk.as<uint32_t>(),
+            b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), bound, cnt);
+        launched += 3;
+    } else {
+        PP_CK(b->pc_first.ensure(8)); PP_CK(b->pc_nk.ensure(4)); PP_CK(b->pc_min.ensure(4)); PP_CK(b->pc_meta.ensure(4));
+        PP_CK(b->pc_eoff.ensure(4));
+    }
+    // ---- entries
+    PP_CK(b->eA.ensure(bound * 8)); PP_CK(b->eklo.ensure(bound * 8)); if (hi128) PP_CK(b->ekhi.ensure(bound * 8));
+    PP_CK(b->epm.ensure(bound)); PP_CK(b->idx0.ensure(bound * 4)); PP_CK(b->idx1.ensure(bound * 4)); PP_CK(b->idx2.ensure(bound * 4));
+    PP_CK(b->skey.ensure(bound * 8)); PP_CK(b->skey2.ensure(bound * 8)); PP_CK(b->head.ensure(bound * 4)); PP_CK(b->uid.ensure(bound * 4));
+    {
+        // entry offset of every piece (exclusive scan of piece sizes)
+        uint32_t *tmp = b->head.as<uint32_t>();
+        pp_piece_offsets_kernel<<<nblk(bound), 256, 0, st>>>(b->pc_nk.as<uint32_t>(), bound, tmp, cnt);
+        PP_CK(excl_sum(b, tmp, b->pc_eoff.as<uint32_t>(), bound, st));
+        launched++;
+    }
+    uint64_t *ekhi = hi128 ? b->ekhi.as<uint64_t>() : nullptr;
+    pp_entries_kernel<<<nblk(bound), 256, 0, st>>>(in.d_packed, b->pc_first.as<uint64_t>(), b->pc_nk.as<uint32_t>(),
+        b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), b->pc_eoff.as<uint32_t>(), k, m, bound, input_shift,
+        b->eA.as<uint64_t>(), b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(), b->idx0.as<uint32_t>(),
+        b->in_sel.as<unsigned long long>(), cnt);
+    launched++;
+    // stable LSD sorts: (bucket, key, order) with order = entry index
+    uint32_t *idx_cur = b->idx1.as<uint32_t>(), *idx_alt = b->idx2.as<uint32_t>();
+    PP_CK(sort_pairs(b, b->eklo.as<uint64_t>(), b->skey.as<uint64_t>(), b->idx0.as<uint32_t>(), idx_cur, bound, 0,
+                     hi128 ? 64 : 2 * k, st));
+    if (hi128) {
+        pp_gather_u64_kernel<<<nblk(bound), 256, 0, st>>>(ekhi, idx_cur, bound, b->skey.as<uint64_t>());
+        PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->skey2.as<uint64_t>(), idx_cur, idx_alt, bound, 0, 2 * k - 64, st));
+        std::swap(idx_cur, idx_alt);
+        launched++;
+    }
+    pp_gather_u64_kernel<<<nblk(bound), 256, 0, st>>>(b->eA.as<uint64_t>(), idx_cur, bound, b->skey.as<uint64_t>());
+    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->skey2.as<uint64_t>(), idx_cur, idx_alt, bound, 0, a_bits, st));
+    std::swap(idx_cur, idx_alt);
+    launched++;
+    const uint64_t *sA = b->skey2.as<uint64_t>();
+    // ---- unique k-mers
+    PP_CK(b->uA.ensure(bound * 8)); PP_CK(b->uklo.ensure(bound * 8)); if (hi128) PP_CK(b->ukhi.ensure(bound * 8));
+    PP_CK(b->ufirst.ensure(bound * 4)); PP_CK(b->upm.ensure(bound)); PP_CK(b->ucnt.ensure(bound)); PP_CK(b->uhead.ensure(bound * 4));
+    PP_CK(b->bflag.ensure(bound * 4)); PP_CK(b->bidm.ensure(bound * 4)); PP_CK(b->bstart.ensure(bound * 4));
+    PP_CK(b->ukey32.ensure(bound * 4)); PP_CK(b->ukey32b.ensure(bound * 4)); PP_CK(b->uidx0.ensure(bound * 4));
+    PP_CK(b->uidx1.ensure(bound * 4)); PP_CK(b->uidx2.ensure(bound * 4)); PP_CK(b->seen.ensure(bound));
+    uint64_t *ukhi = hi128 ? b->ukhi.as<uint64_t>() : nullptr;
+    pp_head_kernel<<<nblk(bound), 256, 0, st>>>(sA, idx_cur, b->eklo.as<uint64_t>(), ekhi, bound, b->head.as<uint32_t>(), cnt);
+    PP_CK(excl_sum(b, b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound, st));
+    pp_unique_kernel<<<nblk(bound), 256, 0, st>>>(sA, idx_cur, b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(),
+        b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound, b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
+        b->ufirst.as<uint32_t>(), b->upm.as<uint8_t>(), b->uhead.as<uint32_t>(), cnt);
+    pp_unique_finish_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uhead.as<uint32_t>(), b->ufirst.as<uint32_t>(),
+        bound, b->ucnt.as<uint8_t>(), b->bflag.as<uint32_t>(), b->ukey32.as<uint32_t>(), b->uidx0.as<uint32_t>(),
+        b->seen.as<uint8_t>(), cnt);
+    PP_CK(excl_sum(b, b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), bound, st));
+    pp_bucket_start_kernel<<<nblk(bound), 256, 0, st>>>(b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), bound,
+                                                        b->bstart.as<uint32_t>(), cnt);
+    launched += 4;
+    // insertion order inside each bucket: stable sort by first order, then by bucket
+    PP_CK(sort_pairs(b, b->ukey32.as<uint32_t>(), b->ukey32b.as<uint32_t>(), b->uidx0.as<uint32_t>(), b->uidx1.as<uint32_t>(),
+                     bound, 0, 32, st));
+    pp_gather_uA_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uidx1.as<uint32_t>(), bound,
+                                                     b->skey.as<uint64_t>(), cnt);
+    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->eA.as<uint64_t>(), b->uidx1.as<uint32_t>(), b->uidx2.as<uint32_t>(), bound, 0,
+                     a_bits, st));
+    launched++;
+    const uint32_t *ins = b->uidx2.as<uint32_t>();
+    // ---- reconstruction: sizes, offsets, bytes
+    PP_CK(b->bbytes.ensure(bound * 4)); PP_CK(b->bnmax.ensure(bound * 4)); PP_CK(b->boff.ensure(bound * 8));
+    PP_CK(cudaMemsetAsync(b->bbytes.p, 0, bound * 4, st));
+    pp_reconstruct_kernel<false><<<nblk(bound, 64), 64, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
+        b->ucnt.as<uint8_t>(), b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), ins, b->bstart.as<uint32_t>(), k, m, in.abundance,
+        input_shift, b->bbytes.as<uint32_t>(), b->bnmax.as<uint32_t>(), nullptr, nullptr, b->in_bytes.as<unsigned long long>(), cnt);
+    PP_CK(excl_sum(b, b->bbytes.as<uint32_t>(), b->boff.as<uint64_t>(), bound, st));
+    pp_body_total_kernel<<<1, 32, 0, st>>>(b->boff.as<uint64_t>(), b->bbytes.as<uint32_t>(), cnt);
+    pp_clear_seen_kernel<<<nblk(bound), 256, 0, st>>>(b->seen.as<uint8_t>(), bound);
+    launched += 3;
+    // ---- compare elements (needs the bucket tables, not the bytes)
+    PP_CK(b->eflag.ensure(bound * 4)); PP_CK(b->eoff.ensure(bound * 4));
+    PP_CK(b->el_min.ensure(bound * 4)); PP_CK(b->el_klo.ensure(bound * 8)); if (hi128) PP_CK(b->el_khi.ensure(bound * 8));
+    pp_element_flag_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->ucnt.as<uint8_t>(),
+        b->bidm.as<uint32_t>(), b->bstart.as<uint32_t>(), k, in.abundance, input_shift, bound, b->eflag.as<uint32_t>(),
+        b->in_elems.as<unsigned long long>(), b->seen.as<uint8_t>(), cnt);
+    PP_CK(excl_sum(b, b->eflag.as<uint32_t>(), b->eoff.as<uint32_t>(), bound, st));
+    pp_element_write_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->eflag.as<uint32_t>(),
+        b->eoff.as<uint32_t>(), k, input_shift, bound, b->el_min.as<uint32_t>(), b->el_klo.as<uint64_t>(),
+        hi128 ? b->el_khi.as<uint64_t>() : nullptr, cnt);
+    launched += 2;
+    // ---- sizes to the host, then the bytes
+    PP_CK(b->h_cnt.ensure(sizeof(Counters))); PP_CK(b->h_in.ensure(nin * 8 * 3)); PP_CK(b->h_off.ensure((nin + 1) * 8 * 2));
+    PP_CK(cudaMemcpyAsync(b->h_cnt.p, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    unsigned long long *h_in = b->h_in.as<unsigned long long>();
+    PP_CK(cudaMemcpyAsync(h_in, b->in_bytes.p, nin * 8, cudaMemcpyDeviceToHost, st));
+    PP_CK(cudaMemcpyAsync(h_in + nin, b->in_sel.p, nin * 8, cudaMemcpyDeviceToHost, st));
+    PP_CK(cudaMemcpyAsync(h_in + 2 * nin, b->in_elems.p, nin * 8, cudaMemcpyDeviceToHost, st));
+    PP_CK(cudaStreamSynchronize(st));
+    const Counters hc = *b->h_cnt.as<Counters>();
+    if (hc.n_pieces > bound || hc.n_entries > bound) return cudaErrorUnknown;    // cannot happen: bound is exact
+    PP_CK(b->body.ensure(hc.body_bytes ? hc.body_bytes : 1));
+    PP_CK(b->h_body.ensure(hc.body_bytes ? hc.body_bytes : 1));
+    pp_reconstruct_kernel<true><<<nblk(bound, 64), 64, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
+        b->ucnt.as<uint8_t>(), b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), ins, b->bstart.as<uint32_t>(), k, m, in.abundance,
+        input_shift, b->bbytes.as<uint32_t>(), b->bnmax.as<uint32_t>(), b->boff.as<uint64_t>(), b->body.as<uint8_t>(),
+        b->in_bytes.as<unsigned long long>(), cnt);
+    launched++;
+    if (hc.body_bytes) PP_CK(cudaMemcpyAsync(b->h_body.p, b->body.p, hc.body_bytes, cudaMemcpyDeviceToHost, st));
+    PP_CK(cudaStreamSynchronize(st));
+    uint64_t *off = b->h_off.as<uint64_t>();
+    uint64_t *eoffh = off + (nin + 1);
+    off[0] = 0; eoffh[0] = 0;
+    for (uint32_t i = 0; i < in.n_inputs; i++) { off[i + 1] = off[i] + h_in[i]; eoffh[i + 1] = eoffh[i] + h_in[2 * nin + i]; }
+    out->h_body = b->h_body.as<uint8_t>();
+    out->h_body_off = off;
+    out->h_selected = reinterpret_cast<const uint64_t *>(h_in + nin);
+    out->h_elem_off = eoffh;
+    out->d_minim = b->el_min.as<uint32_t>();
+    out->d_klo = b->el_klo.as<uint64_t>();
+    out->d_khi = hi128 ? b->el_khi.as<uint64_t>() : nullptr;
+    out->n_elems = hc.n_elems;
+    out->kernels_launched = launched;
+    return cudaGetLastError();
+}
+
+}  // namespace spsp

@@ -234,3 +234,60 @@ def test_full_size_properties(oracle):
     # intersections never exceed the smaller set
     iu = np.triu_indices(len(sks), 1)
     assert (inter[iu] <= np.minimum(sizes[iu[0]], sizes[iu[1]])).all()
+
+
+# ---------------------------------------------------------------- whole-batch device path
+
+def _batch(inputs, k):
+    ws, ros = [], []
+    for inp in inputs:
+        w, nb, ro = S.pack_fasta(build_input(inp), k)
+        ws.append(w); ros.append(ro)
+    return S.batch_layout(ws, ros)
+
+
+@pytest.mark.parametrize("k,m,s,a,inputs", [
+    (31, 11, 1000, 1, ["c1", "c1mut", "nasty", "tiny", "empty", "reads"]),
+    (31, 11, 100, 1, ["fam12_0", "fam12_1", "nasty", "multi", "reads", "noheader"]),
+    (31, 11, 10, 1, ["nasty", "multi", "reads"]),
+    (31, 11, 2, 1, ["nasty", "multi"]),
+    (31, 11, 1, 1, ["nasty", "wrap256", "wrap257"]),
+    (31, 11, 1, 2, ["wrap257", "nasty"]),
+    (21, 9, 5, 1, ["nasty", "nasty21", "multi", "fam12_3"]),
+    (15, 5, 3, 1, ["nasty", "multi"]),
+    (63, 15, 10, 1, ["nasty", "multi", "fam12_2"]),
+    (41, 13, 7, 1, ["nasty", "reads"]),
+    (31, 13, 200, 1, ["c1", "nasty"]),
+    (33, 13, 4, 1, ["nasty"]),
+    (61, 15, 3, 1, ["nasty", "multi"]),
+    (17, 15, 6, 1, ["nasty"]),
+])
+def test_device_postpass_matches_oracle(k, m, s, a, inputs, oracle):
+    """Scan + device post-pass of a whole batch: sketch bytes of every input are
+    the oracle's, and the device-resident compare elements give the oracle's counts."""
+    words, nb, rb, re_, ri = _batch(inputs, k)
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+    info = {}
+    sks = ctx.sketch_batch(words, nb, rb, re_, ri, len(inputs), s, a, info=info)
+    want = [oracle.sketch(build_input(i), k, m, s, a)[0] for i in inputs]
+    for i, (g, w) in enumerate(zip(sks, want)):
+        assert g == w, (inputs[i], len(g), len(w))
+    # sketch -> compare hand-off on the device
+    ctx.cmp_load_batch()
+    n = len(inputs)
+    inter = ctx.cmp_run((0, n), (0, n), True)
+    o_inter, o_sizes, _, _ = oracle.compare(want)
+    assert np.array_equal(np.diff(np.array(info["elem_off"], np.uint64)), o_sizes)
+    assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    ctx.close()
+
+
+def test_device_postpass_golden_and_host_agree(golden):
+    """Every golden sketch case through the batch path, one input per batch."""
+    for name in sorted(SKETCH_CASES):
+        inp, k, m, s, a = SKETCH_CASES[name]
+        words, nb, rb, re_, ri = _batch([inp], k)
+        ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+        sk = ctx.sketch_batch(words, nb, rb, re_, ri, 1, s, a)[0]
+        ctx.close()
+        assert sha(sk) == golden["sketch"][name]["sha256"], name
