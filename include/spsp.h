@@ -169,6 +169,10 @@ int spsp_sketch_batch_device(spsp_ctx *ctx, int slot, const uint32_t *d_packed, 
 /* Load the compare stage with the elements the last batch on `slot` left on the
  * device (one sketch per input): the sketch -> compare hand-off without files. */
 int spsp_cmp_load_batch(spsp_ctx *ctx, int slot);
+/* Copy the last batch's elements to the host (n_elems entries each; kmer_hi may
+ * be NULL when k <= 32) and/or return the device pointers (any argument may be NULL). */
+int spsp_batch_elements(spsp_ctx *ctx, int slot, uint32_t *minimizer, uint64_t *kmer_lo, uint64_t *kmer_hi,
+                        const uint32_t **d_minimizer, const uint64_t **d_kmer_lo, const uint64_t **d_kmer_hi);
 
 /* Number of kernels this library launched on the context since creation. */
 int spsp_launch_count(spsp_ctx *ctx, uint64_t *n);

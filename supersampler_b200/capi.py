@@ -91,6 +91,8 @@ def device_lib():
                                         C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
         L.spsp_sketch_batch_device.argtypes = L.spsp_sketch_batch.argtypes
         L.spsp_cmp_load_batch.argtypes = [C.c_void_p, C.c_int]
+        L.spsp_batch_elements.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         _dev = L
     return _dev
 
@@ -475,6 +477,20 @@ class DeviceContext:
             info.update(n_hits=int(res.n_hits), n_elems=int(res.n_elems), scan_ms=float(res.scan_ms),
                         post_ms=float(res.post_ms), elem_off=[int(res.elem_off[i]) for i in range(n_inputs + 1)])
         return out
+
+    def batch_elements(self, n_elems: int, slot: int = 0, want_hi: bool = False):
+        """Host copy of the last batch's elements: (minimizer u32[], kmer_lo u64[], kmer_hi u64[] | None)."""
+        mn = np.zeros(n_elems, np.uint32); lo = np.zeros(n_elems, np.uint64)
+        hi = np.zeros(n_elems, np.uint64) if want_hi else None
+        _dcheck(self.L.spsp_batch_elements(self.h, slot, mn.ctypes.data, lo.ctypes.data,
+                                           hi.ctypes.data if want_hi else None, None, None, None), "spsp_batch_elements")
+        return mn, lo, hi
+
+    def batch_element_ptrs(self, slot: int = 0):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _dcheck(self.L.spsp_batch_elements(self.h, slot, None, None, None, C.byref(a), C.byref(b), C.byref(c)),
+                "spsp_batch_elements")
+        return a.value, b.value, c.value
 
     def cmp_load_batch(self, slot: int = 0):
         _dcheck(self.L.spsp_cmp_load_batch(self.h, slot), "spsp_cmp_load_batch")

@@ -665,6 +665,26 @@ extern "C" int spsp_cmp_load_batch(spsp_ctx *c, int slot)
                                 s.last_batch.d_khi);
 }
 
+extern "C" int spsp_batch_elements(spsp_ctx *c, int slot, uint32_t *minimizer, uint64_t *kmer_lo, uint64_t *kmer_hi,
+                                   const uint32_t **d_minimizer, const uint64_t **d_kmer_lo, const uint64_t **d_kmer_hi)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_batch_elements: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (!s.has_batch) return fail(-3, "spsp_batch_elements: no batch on this slot");
+    CK(cudaSetDevice(c->device));
+    const uint64_t n = s.last_batch.n_elems;
+    if (n) {
+        if (minimizer) CK(cudaMemcpyAsync(minimizer, s.last_batch.d_minim, n * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (kmer_lo) CK(cudaMemcpyAsync(kmer_lo, s.last_batch.d_klo, n * 8, cudaMemcpyDeviceToHost, s.stream));
+        if (kmer_hi && s.last_batch.d_khi) CK(cudaMemcpyAsync(kmer_hi, s.last_batch.d_khi, n * 8, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    if (d_minimizer) *d_minimizer = s.last_batch.d_minim;
+    if (d_kmer_lo) *d_kmer_lo = s.last_batch.d_klo;
+    if (d_kmer_hi) *d_kmer_hi = s.last_batch.d_khi;
+    return 0;
+}
+
 extern "C" int spsp_launch_count(spsp_ctx *c, uint64_t *n)
 {
     if (!c || !n) return fail(-3, "spsp_launch_count: bad args");

@@ -607,7 +607,8 @@ __global__ void pp_clear_seen_kernel(uint8_t *__restrict__ seen, uint64_t bound)
 // sketch iff count >= abundance; two orientations of one k-mer collapse.
 __global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo,
                                        const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
-                                       const uint32_t *__restrict__ bid, const uint32_t *__restrict__ bstart, int k,
+                                       const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid,
+                                       const uint32_t *__restrict__ bstart, int k,
                                        unsigned abundance, int input_shift, uint64_t bound, uint32_t *__restrict__ eflag,
                                        unsigned long long *__restrict__ in_elems, uint8_t *__restrict__ seen,
                                        const Counters *cnt)
@@ -621,7 +622,7 @@ __global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const ui
         const K128 rc = k_rc(key, k);
         if (k_lt(rc, key)) {
             // non-canonical orientation: drop it if the canonical one is in the bucket too
-            const uint32_t b = bid[u];
+            const uint32_t b = bid[u] + bflag[u] - 1;      // bid = exclusive scan of the bucket-head flags
             BucketView v{uklo, ukhi, ucnt, seen, bstart[b],
                          (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique, abundance, k};
             int o = bv_find(v, rc);
@@ -850,7 +851,8 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->eflag.ensure(bound * 4)); PP_CK(b->eoff.ensure(bound * 4));
     PP_CK(b->el_min.ensure(bound * 4)); PP_CK(b->el_klo.ensure(bound * 8)); if (hi128) PP_CK(b->el_khi.ensure(bound * 8));
     pp_element_flag_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->ucnt.as<uint8_t>(),
-        b->bidm.as<uint32_t>(), b->bstart.as<uint32_t>(), k, in.abundance, input_shift, bound, b->eflag.as<uint32_t>(),
+        b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), b->bstart.as<uint32_t>(), k, in.abundance, input_shift, bound,
+        b->eflag.as<uint32_t>(),
         b->in_elems.as<unsigned long long>(), b->seen.as<uint8_t>(), cnt);
     PP_CK(excl_sum(b, b->eflag.as<uint32_t>(), b->eoff.as<uint32_t>(), bound, st));
     pp_element_write_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->eflag.as<uint32_t>(),
