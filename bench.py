@@ -7,11 +7,14 @@ genomes (default: BASELINE config 2, 64 x 5 Mbp, k31 m11 s1000) and compare
 the G sketches all-vs-all.
 
   value : inputs (2-bit packed genomes) resident in HBM; per step: one scan
-          launch over the batch, hits D2H, exact host post-pass to sketch
-          bytes, sketch decode + upload + compare kernel + matrix D2H.
-  e2e   : the same work through the host API with HOST buffers: FASTA text in
-          host memory -> clean/pack into pinned memory -> H2D -> scan -> D2H ->
-          post-pass -> compare; copies inside the timed region.
+          launch over the batch, the exact post-pass on the device (hits ->
+          super-k-mers -> buckets -> sketch bytes), sketch bytes D2H, compare
+          kernel on the device-resident elements, matrix D2H.
+  e2e   : the same work through the public host API with HOST buffers
+          (supersampler_b200.Pipeline): FASTA text in host memory -> host
+          threads clean/pack into pinned memory -> async H2D per input -> scan ->
+          device post-pass -> sketch bytes D2H -> compare -> matrix D2H; all
+          copies inside the timed region.
   --impl reference : the unmodified reference binaries (oracle/_ref, built from
           /root/reference in the build container) on this box's host cores,
           same files / parameters; C restatement if the binaries are absent.
@@ -236,7 +239,7 @@ def workload_config(args, world):
 def b200_arm(args, rank, world, local_rank):
     import torch
     import supersampler_b200 as S
-    from supersampler_b200 import capi
+    from supersampler_b200 import distributed as D
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -254,91 +257,86 @@ def b200_arm(args, rank, world, local_rank):
     k, m, s = args.k, args.m, args.s
     fastas, names = make_fastas(args.genomes, args.bases, rank * args.genomes)
     total_bases_rank = sum(args.bases for _ in fastas)
+    n_in = len(fastas)
 
-    sketcher = S.Sketcher(k, m, s, device=local_rank, threads=threads)
-    comparer = S.Comparer(1, threads)
-    dctx = sketcher.device_context()
-
-    # ---- device-resident inputs: all genomes packed back to back, R replicas
-    ws, base_off, nbs, ro, off = [], [], [], [], 0
+    # host-buffer path: the public pipeline (pack on host threads -> pinned -> H2D -> scan -> post-pass -> compare)
+    pipe = S.Pipeline(k, m, s, device=local_rank, threads=threads)
+    pctx = pipe.device_context()
+    # device-resident path: a context of its own; all genomes packed back to back, R replicas in HBM
+    dctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
+    ws, ros = [], []
     for fa in fastas:
         w, nb, offs = S.pack_fasta(fa, k)
-        ws.append(w); base_off.append(off); nbs.append(nb); ro.append(offs)
-        off += w.size * 16
-    packed = np.concatenate(ws + [np.zeros(64, np.uint32)])     # tail padding the kernels may read
+        ws.append(w); ros.append(offs)
+    packed, n_total, rec_begin, rec_end, rec_input = S.batch_layout(ws, ros)
     del ws
-    n_total = (packed.size - 64) * 16            # one scan launch covers every genome (and the gaps between them)
-    rec_off = np.concatenate(ro)
-    rec_first = np.array([0] + list(np.cumsum([r.size for r in ro])), np.uint64)
-    base_off = np.array(base_off, np.uint64); nbs = np.array(nbs, np.uint64)
     packed_bytes = packed.size * 4
     replicas = max(2, int(np.ceil(160e6 / packed_bytes)) + 1)
     h_packed = torch.from_numpy(packed.view(np.int32))
     d_packed = [h_packed.cuda() for _ in range(replicas)]
-    thr = S.threshold(k, m, s)
-    exp_hits = int(n_total * (thr / 2.0 ** 64) * 2) + 65536
-    d_hits = torch.empty(exp_hits * 16, dtype=torch.uint8, device="cuda")
-    d_count = torch.zeros(1, dtype=torch.int64, device="cuda")
-    h_hits = torch.empty(exp_hits * 16, dtype=torch.uint8).pin_memory()
-    h_count = torch.zeros(1, dtype=torch.int64).pin_memory()
-    ext = torch.cuda.ExternalStream(dctx.stream(0))
+    torch.cuda.synchronize()
 
-    stats = {"scan_ms": [], "cmp_ms": [], "hits": 0, "launches": 0, "sketch_s": [], "compare_s": []}
+    stats = {"scan_ms": [], "post_ms": [], "cmp_ms": [], "hits": 0, "launches": 0, "sketch_s": [], "compare_s": [],
+             "d2h": 0, "e2e": []}
+
+    def compare_device(ctx, elem_off, cinfo):
+        """Compare stage from the elements the batch left on `ctx`'s device."""
+        if dist is None:
+            l0 = ctx.launches()
+            ctx.cmp_load_batch()
+            inter = ctx.cmp_run((0, n_in), (0, n_in), True)
+            cinfo.update(kernel_ms=ctx.cmp_kernel_ms(), launches=ctx.launches() - l0)
+            return inter, np.diff(np.asarray(elem_off, np.uint64)), False
+        return D.allgather_compare_device(elem_off, ctx, rank, world, cinfo)
 
     def resident_step(i, record):
         t0 = time.perf_counter()
-        with torch.cuda.stream(ext):
-            dctx.scan_device(d_packed[i % replicas].data_ptr(), n_total, d_hits.data_ptr(), exp_hits, d_count.data_ptr(), 0)
-            h_count.copy_(d_count, non_blocking=True)
-            ext.synchronize()
-            n = int(h_count[0])
-            assert n <= exp_hits, "hit buffer too small"
-            h_hits[: n * 16].copy_(d_hits[: n * 16], non_blocking=True)
-            ext.synchronize()
-        hits = np.frombuffer(h_hits.numpy()[: n * 16].tobytes(), capi.HIT_DTYPE)
-        sks = S.postpass_batch(packed, base_off, nbs, rec_off, rec_first, hits, k, m, s, threads=threads)
+        info, cinfo = {}, {}
+        l0 = dctx.launches()
+        sks = dctx.sketch_batch(None, n_total, rec_begin, rec_end, rec_input, n_in, s,
+                                device_ptr=d_packed[i % replicas].data_ptr(), info=info)
+        nl = dctx.launches() - l0
         t1 = time.perf_counter()
-        cinfo = {}
-        res = compare_step(sks, cinfo)
+        res = compare_device(dctx, info["elem_off"], cinfo)
         t2 = time.perf_counter()
         if record:
-            stats["scan_ms"].append(dctx.scan_kernel_ms(0))
+            stats["scan_ms"].append(info["scan_ms"]); stats["post_ms"].append(info["post_ms"])
             stats["cmp_ms"].append(cinfo.get("kernel_ms", 0.0))
-            stats["hits"] = n
-            stats["launches"] += 1 + cinfo.get("launches", 0)
+            stats["hits"] = info["n_hits"]
+            stats["launches"] += nl + cinfo.get("launches", 0)
             stats["sketch_s"].append(t1 - t0); stats["compare_s"].append(t2 - t1)
+            stats["d2h"] = sum(len(x) for x in sks) + res[0].size * 4
         return sks, res
 
-    def compare_step(sks, cinfo):
-        if dist is None:
-            return comparer.run(sks, info=cinfo)
-        from supersampler_b200 import distributed as D
-        return D.allgather_compare(sks, k, m, rank, world, dctx, cinfo)
-
-    def e2e_step(record):
+    def e2e_step(i, record):
         info, cinfo = {}, {}
-        sks = sketcher.run(fastas, info=info)
-        res = compare_step(sks, cinfo)
+        sks = pipe.sketch(fastas, info=info)
+        if dist is None:
+            res = pipe.compare(info=cinfo)
+        else:
+            off, on_dev = pipe.elem_off()
+            assert on_dev
+            res = D.allgather_compare_device(off, pctx, rank, world, cinfo)
         if record:
-            stats.setdefault("e2e_launches", 0)
-            stats["e2e_launches"] += info.get("launches", 0) + cinfo.get("launches", 0)
-            stats["e2e_pack_s"] = info.get("pack_s"); stats["e2e_scan_s"] = info.get("scan_s")
-            stats["e2e_post_s"] = info.get("post_s")
+            info["cmp_kernel_ms"] = cinfo.get("kernel_ms"); info["launches"] += cinfo.get("launches", 0)
+            info["d2h_bytes"] += res[0].size * 4
+            stats["e2e"].append(info)
         return sks, res
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, ctx):
+        """K steps bracketed by barrier + synchronize; CUDA events on the stream the kernels are launched on;
+        every step ends with a device->host read of its result, so wall time >= device time."""
+        ext = torch.cuda.ExternalStream(ctx.stream(0))
         for i in range(warmup):
             fn(i, False)
         barrier(); torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        with torch.cuda.stream(ext):
-            ev0.record()
+        ev0.record(ext)
         out = None
         for i in range(steps):
             out = fn(warmup + i, True)
-        with torch.cuda.stream(ext):
-            ev1.record()
+        ev1.record(ext)
         torch.cuda.synchronize(); barrier()
         wall = time.perf_counter() - t0
         dev = ev0.elapsed_time(ev1) / 1e3
@@ -352,13 +350,13 @@ def b200_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    t_res, (sks_res, cmp_res) = timed(resident_step, args.steps, args.warmup)
-    t_e2e, (sks_e2e, cmp_e2e) = timed(lambda i, rec: e2e_step(rec), args.steps, max(1, args.warmup - 2))
+    t_res, (sks_res, cmp_res) = timed(resident_step, args.steps, args.warmup, dctx)
+    t_e2e, (sks_e2e, cmp_e2e) = timed(e2e_step, args.steps, args.warmup, pctx)
     clocks = sampler.stop() if rank == 0 else None
 
     # both paths must produce the same bytes / counts
     assert sks_res == sks_e2e, "device-resident and host-buffer paths disagree"
-    assert np.array_equal(cmp_res[0], cmp_e2e[0])
+    assert np.array_equal(cmp_res[0], cmp_e2e[0]) and np.array_equal(cmp_res[1], cmp_e2e[1])
 
     if rank != 0:
         if dist is not None:
@@ -374,18 +372,21 @@ def b200_arm(args, rank, world, local_rank):
     algo_bytes = n_total / 4 + 16 * stats["hits"]
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
     sizes = cmp_res[1]
-    elem_bytes = int(sizes.sum()) * 12
-    h2d = packed_bytes + elem_bytes
-    d2h = stats["hits"] * 16 + cmp_res[0].size * 4
+    e2 = stats["e2e"]
+    mean = lambda key: statistics.mean(x[key] for x in e2)
     line = {
         "metric": METRIC, "value": total_bases / step_s / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
-        "e2e": {"value": total_bases / (t_e2e / args.steps) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3, "host_threads": threads,
-                "pack_thread_s": stats.get("e2e_pack_s"), "scan_thread_s": stats.get("e2e_scan_s"),
-                "post_thread_s": stats.get("e2e_post_s")},
+        "e2e": {"value": total_bases / (t_e2e / args.steps) / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(mean("h2d_bytes")), "d2h_bytes_per_step": int(mean("d2h_bytes")),
+                "ms_per_step": t_e2e / args.steps * 1e3, "host_threads": threads,
+                "phases_ms": {"pack_and_h2d": mean("pack_s") * 1e3, "device": mean("device_s") * 1e3,
+                              "assemble": mean("assemble_s") * 1e3, "scan_kernel": mean("scan_ms"),
+                              "postpass_device": mean("post_ms"), "compare_kernel": mean("cmp_kernel_ms")},
+                "gpu_launches": int(sum(x["launches"] for x in e2)),
+                "api": "supersampler_b200.Pipeline.sketch(FASTA bytes in host memory) + .compare()"},
         "gpu_launches": stats["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(n_total)[0], "traffic_source": measured_traffic(n_total)[1],
@@ -394,7 +395,9 @@ def b200_arm(args, rank, world, local_rank):
                      "kernel_tbp_per_s": n_total / (scan_ms * 1e-3) / 1e12},
         "phases_ms": {"sketch": statistics.mean(stats["sketch_s"]) * 1e3,
                       "compare": statistics.mean(stats["compare_s"]) * 1e3,
-                      "scan_kernel": scan_ms, "compare_kernel": statistics.mean(stats["cmp_ms"])},
+                      "scan_kernel": scan_ms, "postpass_device": statistics.mean(stats["post_ms"]),
+                      "compare_kernel": statistics.mean(stats["cmp_ms"])},
+        "d2h_bytes_per_step": int(stats["d2h"]),
         "compare": {"pairs": pairs, "pairs_per_s": pairs / statistics.mean(stats["compare_s"]),
                     "kernel_pairs_per_s": pairs / max(1e-9, statistics.mean(stats["cmp_ms"]) * 1e-3),
                     "elements": int(sizes.sum())},

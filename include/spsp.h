@@ -166,6 +166,17 @@ int spsp_sketch_batch(spsp_ctx *ctx, int slot, const uint32_t *packed, uint64_t 
 int spsp_sketch_batch_device(spsp_ctx *ctx, int slot, const uint32_t *d_packed, uint64_t n_bases,
                              const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input,
                              uint64_t n_rec, uint32_t n_inputs, unsigned abundance, spsp_batch_result *res);
+/* Staged variant for host pipelines that pack inputs concurrently: reserve the
+ * slot's device buffer once (total_words uint32 words, synchronises the slot),
+ * let any number of host threads upload finished regions (async H2D on the
+ * slot's stream; host_words pinned for true overlap; thread-safe), then run the
+ * batch on what was uploaded.  Regions never uploaded hold stale bytes: they
+ * must not be covered by a record. */
+int spsp_batch_reserve(spsp_ctx *ctx, int slot, uint64_t total_words);
+int spsp_batch_upload(spsp_ctx *ctx, int slot, uint64_t word_off, const uint32_t *host_words, uint64_t n_words);
+int spsp_sketch_batch_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const uint64_t *rec_begin,
+                             const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                             unsigned abundance, spsp_batch_result *res);
 /* Load the compare stage with the elements the last batch on `slot` left on the
  * device (one sketch per input): the sketch -> compare hand-off without files. */
 int spsp_cmp_load_batch(spsp_ctx *ctx, int slot);

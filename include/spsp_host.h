@@ -97,6 +97,32 @@ int spsph_comparer_run(spsph_comparer *c, uint32_t n, uint32_t query_size, const
                        const size_t *len, uint32_t *inter, uint64_t *sizes, int *full_rows, float *kernel_ms,
                        uint64_t *launches, double *timings);
 
+/* Batch pipeline (csrc/host/pipeline.h): the GPU-shaped `sub_sampler -f`.  Host
+ * threads clean + pack all inputs into one pinned staging buffer (async H2D per
+ * finished input), one scan + device post-pass yields every sketch, and the
+ * compare stage starts from the elements left on the device. */
+typedef struct spsph_pipeline spsph_pipeline;
+int spsph_pipeline_create(int device, int k, int m, double s, unsigned abundance, int threads, spsph_pipeline **out);
+int spsph_pipeline_destroy(spsph_pipeline *p);
+spsp_ctx *spsph_pipeline_ctx(spsph_pipeline *p);
+/* Upper bound of one device batch in bases (default 2^30); larger jobs run as several batches. */
+int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t bases);
+/* Input i is fasta[i]/len[i] (FASTA text in memory) or, when fasta is NULL or
+ * fasta[i] is NULL, the FASTA(.gz) file paths[i].  out/out_len as in
+ * spsph_sketch_buffers; ok[i] = 0 for an unopenable file (may be NULL).
+ * stats (may be NULL, 12 doubles): prep s, pack s, device s, assemble s, scan ms,
+ * post-pass ms, hits, compare elements, H2D bytes, D2H bytes, batches, bases. */
+int spsph_pipeline_sketch(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
+                          const char *const *paths, uint8_t **out, size_t *out_len, int *ok, double *stats,
+                          uint64_t *launches);
+/* Element offsets (n + 1 entries) of the last spsph_pipeline_sketch call; *on_device = 1 when the
+ * elements are still resident on the GPU (single batch: spsp_batch_elements on slot 0 of spsph_pipeline_ctx). */
+int spsph_pipeline_elem_off(spsph_pipeline *p, uint64_t *off, int *on_device);
+/* Compare the sketches of the last spsph_pipeline_sketch call (contract of
+ * spsph_compare_buffers: inter rows x n with rows = n or query_size). */
+int spsph_pipeline_compare(spsph_pipeline *p, uint32_t query_size, uint32_t *inter, uint64_t *sizes, int *full_rows,
+                           float *kernel_ms, uint64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,17 @@ def host_lib():
         L.spsph_compare_buffers.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p),
                                             C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                             C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        L.spsph_pipeline_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
+        L.spsph_pipeline_destroy.argtypes = [C.c_void_p]
+        L.spsph_pipeline_ctx.restype = C.c_void_p
+        L.spsph_pipeline_ctx.argtypes = [C.c_void_p]
+        L.spsph_pipeline_set_max_batch_bases.argtypes = [C.c_void_p, C.c_uint64]
+        L.spsph_pipeline_sketch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                            C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                            C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.spsph_pipeline_elem_off.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.spsph_pipeline_compare.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
         _host = L
     return _host
 
@@ -288,6 +299,83 @@ class Sketcher:
     def device_context(self) -> "DeviceContext":
         """Borrowed view of the sketcher's spsp_ctx (not destroyed by the view)."""
         return DeviceContext._borrow(self.L.spsph_sketcher_ctx(self.h), self.k, self.m)
+
+
+class Pipeline:
+    """Batch pipeline (csrc/host/pipeline.h): pack all inputs on host threads into one
+    pinned staging buffer, one scan + device post-pass, compare from the device-resident
+    elements.  Inputs are FASTA texts (bytes) or file paths (str)."""
+
+    STAT_NAMES = ("prep_s", "pack_s", "device_s", "assemble_s", "scan_ms", "post_ms", "hits", "elems", "h2d_bytes",
+                  "d2h_bytes", "batches", "bases")
+
+    def __init__(self, k: int = 31, m: int = 11, s: float = 1000.0, abundance: int = 1, device: int = 0,
+                 threads: int = 8, max_batch_bases: Optional[int] = None):
+        self.L = host_lib()
+        self.h = C.c_void_p()
+        self.k, self.m, self.s = k, m, s
+        _hcheck(self.L.spsph_pipeline_create(device, k, m, _f32(s), abundance, threads, C.byref(self.h)), "pipeline_create")
+        if max_batch_bases is not None:
+            _hcheck(self.L.spsph_pipeline_set_max_batch_bases(self.h, max_batch_bases), "pipeline_set_max_batch_bases")
+        self.n_last = 0
+
+    def close(self):
+        if self.h:
+            self.L.spsph_pipeline_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sketch(self, inputs: Sequence, info: Optional[dict] = None) -> List[Optional[bytes]]:
+        """-> sketch bytes (before gzip) per input; None for a file that cannot be opened."""
+        n = len(inputs)
+        data = (C.c_char_p * n)(*[x if isinstance(x, (bytes, bytearray)) else None for x in inputs])
+        lens = (C.c_size_t * n)(*[len(x) if isinstance(x, (bytes, bytearray)) else 0 for x in inputs])
+        paths = (C.c_char_p * n)(*[os.fsencode(x) if not isinstance(x, (bytes, bytearray)) else None for x in inputs])
+        outs = (C.c_void_p * n)()
+        olens = (C.c_size_t * n)()
+        ok = (C.c_int * n)()
+        st = (C.c_double * 12)()
+        nl = C.c_uint64()
+        _hcheck(self.L.spsph_pipeline_sketch(self.h, n, data, lens, paths, outs, olens, ok, st, C.byref(nl)),
+                "pipeline_sketch")
+        res = []
+        for i in range(n):
+            res.append((C.string_at(outs[i], olens[i]) if olens[i] else b"") if ok[i] else None)
+            self.L.spsph_free(outs[i])
+        self.n_last = n
+        if info is not None:
+            info.update({k_: float(st[i]) for i, k_ in enumerate(self.STAT_NAMES)})
+            info["launches"] = int(nl.value)
+        return res
+
+    def compare(self, query_size: Optional[int] = None, info: Optional[dict] = None):
+        """Compare the sketches of the last sketch() call -> (inter[rows, n], sizes[n], full_rows)."""
+        n = self.n_last
+        q = n if query_size is None else query_size
+        rows = n if q >= n else q
+        inter = np.zeros((rows, n), np.uint32)
+        sizes = np.zeros(n, np.uint64)
+        full, ms, nl = C.c_int(), C.c_float(), C.c_uint64()
+        _hcheck(self.L.spsph_pipeline_compare(self.h, q, inter.ctypes.data, sizes.ctypes.data, C.byref(full), C.byref(ms),
+                                              C.byref(nl)), "pipeline_compare")
+        if info is not None:
+            info.update(kernel_ms=float(ms.value), launches=int(nl.value))
+        return inter, sizes, bool(full.value)
+
+    def elem_off(self) -> Tuple[np.ndarray, bool]:
+        """(element offsets of the last sketch() call, still-on-device flag)."""
+        off = np.zeros(self.n_last + 1, np.uint64)
+        od = C.c_int()
+        _hcheck(self.L.spsph_pipeline_elem_off(self.h, off.ctypes.data, C.byref(od)), "pipeline_elem_off")
+        return off, bool(od.value)
+
+    def device_context(self) -> "DeviceContext":
+        return DeviceContext._borrow(self.L.spsph_pipeline_ctx(self.h), self.k, self.m)
 
 
 def postpass_batch(packed: np.ndarray, base_off: np.ndarray, n_bases: np.ndarray, rec_off: np.ndarray,

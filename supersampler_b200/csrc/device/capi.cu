@@ -107,6 +107,8 @@ struct spsp_ctx {
     std::mutex mu;
 };
 
+static int ensure_packed(struct Slot &s, uint64_t words);
+
 extern "C" int spsp_abi_version(void) { return SPSP_ABI_VERSION; }
 extern "C" const char *spsp_last_error(void) { return g_err.c_str(); }
 
@@ -316,13 +318,7 @@ extern "C" int spsp_scan_submit(spsp_ctx *c, int slot, const uint32_t *packed, u
     if (s.pending) return fail(-3, "spsp_scan_submit: slot busy (collect first)");
     CK(cudaSetDevice(c->device));
     uint64_t words = spsp_packed_words(n_bases);
-    if (words > s.d_packed_words) {
-        if (s.d_packed) CK(cudaFree(s.d_packed));
-        s.d_packed = nullptr; s.d_packed_words = 0;
-        uint64_t cap = words + words / 4;
-        CK(cudaMalloc(&s.d_packed, cap * sizeof(uint32_t)));
-        s.d_packed_words = cap;
-    }
+    { int rc_ = ensure_packed(s, words); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(s.d_packed, packed, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
     double p = (double)c->thr / 18446744073709551616.0;
     uint64_t guess = (uint64_t)((double)n_bases * p * 1.5) + 4096;
@@ -645,14 +641,51 @@ extern "C" int spsp_sketch_batch(spsp_ctx *c, int slot, const uint32_t *packed, 
     if (s.pending) return fail(-3, "spsp_sketch_batch: slot busy (collect first)");
     CK(cudaSetDevice(c->device));
     uint64_t words = spsp_packed_words(n_bases);
-    if (words > s.d_packed_words) {
-        if (s.d_packed) CK(cudaFree(s.d_packed));
-        s.d_packed = nullptr; s.d_packed_words = 0;
-        uint64_t cap = words + words / 4;
-        CK(cudaMalloc(&s.d_packed, cap * sizeof(uint32_t)));
-        s.d_packed_words = cap;
-    }
+    { int rc_ = ensure_packed(s, words); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(s.d_packed, packed, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+}
+
+static int ensure_packed(Slot &s, uint64_t words)
+{
+    if (words <= s.d_packed_words) return 0;
+    if (s.d_packed) CK(cudaFree(s.d_packed));
+    s.d_packed = nullptr; s.d_packed_words = 0;
+    uint64_t cap = words + words / 4;
+    CK(cudaMalloc(&s.d_packed, cap * sizeof(uint32_t)));
+    s.d_packed_words = cap;
+    return 0;
+}
+
+extern "C" int spsp_batch_reserve(spsp_ctx *c, int slot, uint64_t total_words)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_batch_reserve: bad ctx/slot");
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slots[slot];
+    CK(cudaStreamSynchronize(s.stream));          // nothing may still read the old buffer
+    return ensure_packed(s, total_words);
+}
+
+extern "C" int spsp_batch_upload(spsp_ctx *c, int slot, uint64_t word_off, const uint32_t *host_words, uint64_t n_words)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_batch_upload: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (word_off + n_words > s.d_packed_words) return fail(-3, "spsp_batch_upload: outside the reserved buffer");
+    if (!n_words) return 0;
+    if (!host_words) return fail(-3, "spsp_batch_upload: null input");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(s.d_packed + word_off, host_words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    return 0;
+}
+
+extern "C" int spsp_sketch_batch_staged(spsp_ctx *c, int slot, uint64_t n_bases, const uint64_t *rec_begin,
+                                        const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec,
+                                        uint32_t n_inputs, unsigned abundance, spsp_batch_result *res)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_sketch_batch_staged: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (spsp_packed_words(n_bases) > s.d_packed_words) return fail(-3, "spsp_sketch_batch_staged: reserve the buffer first");
+    CK(cudaSetDevice(c->device));
     return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
 }
 

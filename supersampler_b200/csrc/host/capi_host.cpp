@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "comparator.h"
+#include "pipeline.h"
 #include "postpass.h"
 #include "seqio.h"
 #include "sketchfile.h"
@@ -284,4 +285,98 @@ extern "C" int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size
     rc = spsph_comparer_run(c, n, query_size, sketch, len, inter, sizes, full_rows, kernel_ms, launches, nullptr);
     spsph_comparer_destroy(c);
     return rc;
+}
+
+// ------------------------------------------------------------ batch pipeline
+
+struct spsph_pipeline {
+    std::shared_ptr<DeviceSession> session;
+    std::unique_ptr<BatchSketcher> bs;
+};
+
+extern "C" int spsph_pipeline_create(int device, int k, int m, double s, unsigned abundance, int threads,
+                                     spsph_pipeline **out)
+{
+    try {
+        auto p = std::make_unique<spsph_pipeline>();
+        p->session = std::make_shared<DeviceSession>(device, k, m, compute_threshold(k, m, s), 1);
+        p->bs.reset(new BatchSketcher(p->session, k, m, s, abundance, threads));
+        *out = p.release();
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_pipeline_destroy(spsph_pipeline *p)
+{
+    delete p;
+    return 0;
+}
+
+extern "C" spsp_ctx *spsph_pipeline_ctx(spsph_pipeline *p) { return p ? p->session->ctx() : nullptr; }
+
+extern "C" int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t bases)
+{
+    if (!p || bases < 4096) return hfail("bad arguments");
+    p->bs->max_batch_bases = bases;
+    return 0;
+}
+
+extern "C" int spsph_pipeline_sketch(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
+                                     const char *const *paths, uint8_t **out, size_t *out_len, int *ok, double *stats,
+                                     uint64_t *launches)
+{
+    try {
+        if (!p) return hfail("null pipeline");
+        std::vector<BatchSource> src(n);
+        for (uint32_t i = 0; i < n; i++) {
+            if (fasta && fasta[i]) { src[i].data = fasta[i]; src[i].len = len[i]; }
+            else if (paths && paths[i]) src[i].path = paths[i];
+            else return hfail("input without data and without path");
+        }
+        const uint64_t l0 = p->session->launches();
+        std::vector<std::vector<uint8_t>> sk;
+        std::vector<char> okv;
+        p->bs->run(src, sk, okv);
+        for (uint32_t i = 0; i < n; i++) {
+            out[i] = dup_vec(sk[i].data(), sk[i].size());
+            out_len[i] = sk[i].size();
+            if (ok) ok[i] = okv[i];
+        }
+        if (stats) {
+            const BatchStats &st = p->bs->stats;
+            stats[0] = st.prep_s; stats[1] = st.pack_s; stats[2] = st.device_s; stats[3] = st.assemble_s;
+            stats[4] = st.scan_ms; stats[5] = st.post_ms; stats[6] = (double)st.hits; stats[7] = (double)st.elems;
+            stats[8] = (double)st.h2d_bytes; stats[9] = (double)st.d2h_bytes; stats[10] = (double)st.batches;
+            stats[11] = (double)st.bases;
+        }
+        if (launches) *launches = p->session->launches() - l0;
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_pipeline_elem_off(spsph_pipeline *p, uint64_t *off, int *on_device)
+{
+    if (!p || !off) return hfail("bad arguments");
+    const std::vector<uint64_t> &e = p->bs->elem_off();
+    memcpy(off, e.data(), e.size() * sizeof(uint64_t));
+    if (on_device) *on_device = p->bs->elems_on_device() ? 1 : 0;
+    return 0;
+}
+
+extern "C" int spsph_pipeline_compare(spsph_pipeline *p, uint32_t query_size, uint32_t *inter, uint64_t *sizes,
+                                      int *full_rows, float *kernel_ms, uint64_t *launches)
+{
+    try {
+        if (!p) return hfail("null pipeline");
+        const uint64_t l0 = p->session->launches();
+        std::vector<uint32_t> iv;
+        std::vector<uint64_t> sv;
+        bool full = false;
+        p->bs->compare_last(query_size, iv, sv, full, kernel_ms);
+        if (!iv.empty()) memcpy(inter, iv.data(), iv.size() * sizeof(uint32_t));
+        if (!sv.empty()) memcpy(sizes, sv.data(), sv.size() * sizeof(uint64_t));
+        if (full_rows) *full_rows = full ? 1 : 0;
+        if (launches) *launches = p->session->launches() - l0;
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
 }

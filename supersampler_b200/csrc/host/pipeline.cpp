@@ -1,0 +1,270 @@
+#include "pipeline.h"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+
+namespace spsp_host {
+
+using clk = std::chrono::steady_clock;
+static double secs(clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
+void parallel_for(int threads, size_t n, const std::function<void(size_t)> &fn)
+{
+    if (n == 0) return;
+    size_t nw = (size_t)(threads < 1 ? 1 : threads);
+    if (nw > n) nw = n;
+    std::atomic<size_t> next{0};
+    std::mutex mu;
+    std::string error;
+    auto work = [&]() {
+        try {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                fn(i);
+            }
+        } catch (const std::exception &e) {
+            std::lock_guard<std::mutex> g(mu);
+            if (error.empty()) error = e.what();
+            next.store(n);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < nw; w++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (!error.empty()) throw std::runtime_error(error);
+}
+
+struct BatchSketcher::Prepared {
+    uint64_t len = 0;                  // upper bound of the number of bases (= text bytes)
+    bool ok = true, from_file = false;
+    std::vector<uint8_t> text;         // inflated gzip input
+    // filled by the pack phase
+    uint64_t word_off = 0, n_bases = 0;
+    std::vector<uint64_t> rec_off;
+};
+
+BatchSketcher::BatchSketcher(std::shared_ptr<DeviceSession> session, int k, int m, double s, unsigned abundance, int threads)
+    : session_(std::move(session)), k_(k), m_(m), threads_(threads < 1 ? 1 : threads), s_(s), abundance_(abundance)
+{
+}
+
+BatchSketcher::~BatchSketcher()
+{
+    if (stage_) spsp_host_free(stage_);
+}
+
+static bool file_is_gzip(int fd)
+{
+    unsigned char mg[2] = {0, 0};
+    return pread(fd, mg, 2, 0) == 2 && mg[0] == 0x1f && mg[1] == 0x8b;
+}
+
+void BatchSketcher::run(const std::vector<BatchSource> &src, std::vector<std::vector<uint8_t>> &sketches, std::vector<char> &ok)
+{
+    stats = BatchStats();
+    const size_t n = src.size();
+    sketches.assign(n, std::vector<uint8_t>());
+    ok.assign(n, 1);
+    selected.assign(n, 0);
+    elem_off_.assign(1, 0);
+    h_minim_.clear(); h_klo_.clear(); h_khi_.clear();
+    elems_on_device_ = false;
+    n_last_ = (uint32_t)n;
+    if (n == 0) return;
+
+    // ---- prepare: sizes; gzip inputs are inflated here (their size is unknown before)
+    auto t0 = clk::now();
+    std::vector<Prepared> prep(n);
+    parallel_for(threads_, n, [&](size_t i) {
+        Prepared &p = prep[i];
+        if (src[i].data) { p.len = src[i].len; return; }
+        p.from_file = true;
+        int fd = open(src[i].path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) {
+            if (fd >= 0) close(fd);
+            p.ok = false;
+            return;
+        }
+        const bool gz = file_is_gzip(fd);
+        close(fd);
+        if (gz) {
+            if (!read_file_maybe_gz(src[i].path, p.text)) { p.ok = false; return; }
+            p.from_file = false;
+            p.len = p.text.size();
+        } else {
+            p.len = (uint64_t)st.st_size;
+        }
+    });
+    stats.prep_s = secs(t0, clk::now());
+    for (size_t i = 0; i < n; i++) ok[i] = prep[i].ok ? 1 : 0;
+
+    // ---- batches of consecutive inputs
+    std::vector<std::pair<size_t, size_t>> batches;
+    size_t first = 0;
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t need = 16 * spsp_packed_words(prep[i].len);
+        if (i > first && acc + need > max_batch_bases) {
+            batches.emplace_back(first, i);
+            first = i; acc = 0;
+        }
+        acc += need;
+    }
+    batches.emplace_back(first, n);
+    const bool multi = batches.size() > 1;
+    for (auto &b : batches) run_batch(src, prep, b.first, b.second, sketches, multi);
+    elems_on_device_ = !multi;
+    stats.batches = batches.size();
+}
+
+void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last,
+                              std::vector<std::vector<uint8_t>> &sketches, bool keep_host_elems)
+{
+    spsp_ctx *ctx = session_->ctx();
+    const size_t nb = last - first;
+    auto t0 = clk::now();
+    uint64_t total_words = 0;
+    for (size_t i = first; i < last; i++) {
+        prep[i].word_off = total_words;
+        total_words += spsp_packed_words(prep[i].ok ? prep[i].len : 0);
+    }
+    const uint64_t n_total = 16 * total_words;               // one scan covers every region
+    const uint64_t need_words = spsp_packed_words(n_total);
+    if (need_words > stage_words_) {
+        if (stage_) spsp_host_free(stage_);
+        stage_ = nullptr; stage_words_ = 0;
+        void *v = nullptr;
+        const uint64_t cap = need_words + need_words / 8;
+        if (spsp_host_alloc(&v, cap * sizeof(uint32_t)) != 0) throw_spsp("spsp_host_alloc");
+        stage_ = static_cast<uint32_t *>(v);
+        stage_words_ = cap;
+    }
+    if (spsp_batch_reserve(ctx, 0, need_words) != 0) throw_spsp("spsp_batch_reserve");
+
+    // ---- pack: every worker cleans + packs whole inputs into their regions and queues the copy
+    parallel_for(threads_, nb, [&](size_t j) {
+        Prepared &p = prep[first + j];
+        const BatchSource &sc = src[first + j];
+        PackedInput in(false);
+        in.words.attach(stage_ + p.word_off, spsp_packed_words(p.ok ? p.len : 0));
+        {
+            FastaPacker pk(in, (uint32_t)k_);
+            if (!p.ok) {
+            } else if (!p.from_file) {
+                const uint8_t *d = sc.data ? sc.data : p.text.data();
+                const size_t len = sc.data ? sc.len : p.text.size();
+                pk.feed(d, len);
+            } else {
+                int fd = open(sc.path.c_str(), O_RDONLY);
+                if (fd < 0) throw std::runtime_error("cannot reopen " + sc.path);
+                std::vector<uint8_t> buf(1u << 20);
+                uint64_t got = 0;
+                while (got < p.len) {                        // never more than the size the region was cut for
+                    ssize_t r = read(fd, buf.data(), (size_t)std::min<uint64_t>(buf.size(), p.len - got));
+                    if (r <= 0) break;
+                    pk.feed(buf.data(), (size_t)r);
+                    got += (uint64_t)r;
+                }
+                close(fd);
+            }
+            pk.finish();
+        }
+        p.n_bases = in.n_bases;
+        p.rec_off.swap(in.rec_off);
+        const uint64_t words = spsp_packed_words(p.n_bases);
+        if (spsp_batch_upload(ctx, 0, p.word_off, stage_ + p.word_off, words) != 0) throw_spsp("spsp_batch_upload");
+        in.words.detach();
+        std::vector<uint8_t>().swap(p.text);
+    });
+    auto t1 = clk::now();
+    stats.pack_s += secs(t0, t1);
+
+    // ---- records of the batch, ascending
+    std::vector<uint64_t> rb, re;
+    std::vector<uint32_t> ri;
+    for (size_t i = first; i < last; i++) {
+        const Prepared &p = prep[i];
+        const uint64_t base = 16 * p.word_off;
+        for (size_t r = 0; r + 1 < p.rec_off.size(); r++) {
+            rb.push_back(base + p.rec_off[r]);
+            re.push_back(base + p.rec_off[r + 1]);
+            ri.push_back((uint32_t)(i - first));
+        }
+        stats.bases += p.n_bases;
+        stats.h2d_bytes += spsp_packed_words(p.n_bases) * 4;
+    }
+    spsp_batch_result res{};
+    if (spsp_sketch_batch_staged(ctx, 0, n_total, rb.data(), re.data(), ri.data(), rb.size(), (uint32_t)nb, abundance_,
+                                 &res) != 0)
+        throw_spsp("spsp_sketch_batch_staged");
+    auto t2 = clk::now();
+    stats.device_s += secs(t1, t2);
+    stats.scan_ms += res.scan_ms; stats.post_ms += res.post_ms;
+    stats.hits += res.n_hits; stats.elems += res.n_elems;
+    stats.h2d_bytes += rb.size() * 20;
+    stats.d2h_bytes += res.body_off[nb] + nb * 24;
+
+    // ---- header line + body (SubSampler.cpp:459-460)
+    for (size_t j = 0; j < nb; j++) {
+        if (!prep[first + j].ok) continue;
+        char hdr[96];
+        const int hl = snprintf(hdr, sizeof hdr, "%d %d %llu %f\n", 2 * k_ - m_, m_, (unsigned long long)res.selected[j], s_);
+        std::vector<uint8_t> &o = sketches[first + j];
+        const uint64_t b0 = res.body_off[j], b1 = res.body_off[j + 1];
+        o.resize((size_t)hl + (size_t)(b1 - b0));
+        memcpy(o.data(), hdr, (size_t)hl);
+        if (b1 > b0) memcpy(o.data() + hl, res.body + b0, (size_t)(b1 - b0));
+        selected[first + j] = res.selected[j];
+    }
+    const uint64_t e0 = elem_off_.back();
+    for (size_t j = 0; j < nb; j++) elem_off_.push_back(e0 + res.elem_off[j + 1]);
+    if (keep_host_elems && res.n_elems) {
+        const size_t old = h_minim_.size(), ne = (size_t)res.n_elems;
+        h_minim_.resize(old + ne); h_klo_.resize(old + ne);
+        if (k_ > 32) h_khi_.resize(old + ne);
+        if (spsp_batch_elements(ctx, 0, h_minim_.data() + old, h_klo_.data() + old, k_ > 32 ? h_khi_.data() + old : nullptr,
+                                nullptr, nullptr, nullptr) != 0)
+            throw_spsp("spsp_batch_elements");
+        stats.d2h_bytes += ne * (k_ > 32 ? 20 : 12);
+    }
+    stats.assemble_s += secs(t2, clk::now());
+}
+
+void BatchSketcher::compare_last(unsigned query_size, std::vector<uint32_t> &inter, std::vector<uint64_t> &sizes,
+                                 bool &full_rows, float *kernel_ms)
+{
+    spsp_ctx *ctx = session_->ctx();
+    const uint32_t n = n_last_;
+    sizes.assign(n, 0);
+    for (uint32_t i = 0; i < n; i++) sizes[i] = elem_off_[i + 1] - elem_off_[i];
+    if (query_size > n) query_size = n;
+    full_rows = query_size < n;
+    const uint32_t rows = full_rows ? query_size : n;
+    inter.assign((size_t)rows * n, 0);
+    if (kernel_ms) *kernel_ms = 0;
+    if (rows == 0) return;
+    if (elems_on_device_) {
+        if (spsp_cmp_load_batch(ctx, 0) != 0) throw_spsp("spsp_cmp_load_batch");
+    } else {
+        const uint32_t one32 = 0; const uint64_t one64 = 0;
+        if (spsp_cmp_load(ctx, n, elem_off_.data(), h_minim_.empty() ? &one32 : h_minim_.data(),
+                          h_klo_.empty() ? &one64 : h_klo_.data(), k_ > 32 ? (h_khi_.empty() ? &one64 : h_khi_.data()) : nullptr) != 0)
+            throw_spsp("spsp_cmp_load");
+    }
+    if (spsp_cmp_run(ctx, 0, rows, 0, n, full_rows ? 0 : 1, 0, 1, inter.data(), n) != 0) throw_spsp("spsp_cmp_run");
+    if (kernel_ms) spsp_cmp_last_kernel_ms(ctx, kernel_ms);
+}
+
+}  // namespace spsp_host

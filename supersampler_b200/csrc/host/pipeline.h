@@ -1,0 +1,81 @@
+// Batch pipeline of the sketch stage: the GPU-shaped form of the reference's
+// `sub_sampler -f` loop (SubSampler.cpp:761-801).  Where the reference gives
+// every file to one OpenMP thread that runs the whole per-base loop, here host
+// threads only clean + pack their files (getLineFasta / clean_dna,
+// utils.cpp:675-718) straight into one pinned staging buffer, each finished
+// region is copied to the device asynchronously while the other files are
+// still being packed, and ONE scan + device post-pass (include/spsp.h,
+// spsp_sketch_batch_staged) produces the sketch bytes of every file.  The
+// compare stage can start from the elements the batch left on the device.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "seqio.h"
+#include "session.h"
+
+namespace spsp_host {
+
+struct BatchSource {
+    const uint8_t *data = nullptr;    // FASTA text in memory ...
+    size_t len = 0;
+    std::string path;                 // ... or a FASTA(.gz) file when data == nullptr
+};
+
+struct BatchStats {
+    double prep_s = 0, pack_s = 0, device_s = 0, assemble_s = 0;   // wall seconds, summed over batches
+    double scan_ms = 0, post_ms = 0;                               // CUDA events
+    uint64_t hits = 0, elems = 0, bases = 0, batches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+class BatchSketcher {
+public:
+    // Uses slot 0 of `session` (the compare stage's stream, so the hand-off needs no extra sync).
+    BatchSketcher(std::shared_ptr<DeviceSession> session, int k, int m, double s, unsigned abundance, int threads);
+    ~BatchSketcher();
+    BatchSketcher(const BatchSketcher &) = delete;
+    BatchSketcher &operator=(const BatchSketcher &) = delete;
+
+    // Sketch bytes (before gzip) of every source, in order.  ok[i] = 0 for a file that
+    // cannot be opened (its sketch stays empty), like SubSampler.cpp:313-322.
+    void run(const std::vector<BatchSource> &src, std::vector<std::vector<uint8_t>> &sketches, std::vector<char> &ok);
+
+    // All-vs-all (query_size >= n) or query-vs-all compare of the sketches of the last
+    // run(), starting from the elements the batch left on the device (several batches:
+    // from their host copies).  inter: rows x n, sizes: n (Comparator.cpp:39-74 semantics).
+    void compare_last(unsigned query_size, std::vector<uint32_t> &inter, std::vector<uint64_t> &sizes, bool &full_rows,
+                      float *kernel_ms);
+
+    // Element offsets (n + 1 entries) of the last run(); on the device only when it was one batch.
+    const std::vector<uint64_t> &elem_off() const { return elem_off_; }
+    bool elems_on_device() const { return elems_on_device_; }
+
+    BatchStats stats;                          // last run()
+    uint64_t max_batch_bases = 1ull << 30;     // upper bound of one batch (bases incl. padding)
+    std::vector<uint64_t> selected;            // header field 3 of every source, last run()
+
+private:
+    struct Prepared;
+    void run_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last,
+                   std::vector<std::vector<uint8_t>> &sketches, bool keep_host_elems);
+    std::shared_ptr<DeviceSession> session_;
+    int k_, m_, threads_;
+    double s_;
+    unsigned abundance_;
+    uint32_t *stage_ = nullptr;                // pinned staging buffer (grow-only)
+    uint64_t stage_words_ = 0;
+    // elements of the last run
+    bool elems_on_device_ = false;
+    uint32_t n_last_ = 0;
+    std::vector<uint64_t> elem_off_;
+    std::vector<uint32_t> h_minim_;
+    std::vector<uint64_t> h_klo_, h_khi_;
+};
+
+// Runs fn(i) for i in [0, n) on up to `threads` host threads (the caller is one of them).
+void parallel_for(int threads, size_t n, const std::function<void(size_t)> &fn);
+
+}  // namespace spsp_host

@@ -4,6 +4,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 
 #include <cstdio>
 #include <cstdlib>
@@ -16,15 +19,26 @@ namespace spsp_host {
 
 // ---------------------------------------------------------------- WordBuf
 
-WordBuf::~WordBuf()
+WordBuf::~WordBuf() { detach(); }
+
+void WordBuf::detach()
 {
-    if (!p_) return;
-    if (pinned_) spsp_host_free(p_); else free(p_);
+    if (p_ && !external_) {
+        if (pinned_) spsp_host_free(p_); else free(p_);
+    }
+    p_ = nullptr; cap_ = 0; external_ = false;
+}
+
+void WordBuf::attach(uint32_t *p, uint64_t words)
+{
+    detach();
+    p_ = p; cap_ = words; external_ = true;
 }
 
 void WordBuf::reserve(uint64_t words)
 {
     if (words <= cap_) return;
+    if (external_) throw std::runtime_error("packed region too small for this input");
     uint64_t ncap = cap_ ? cap_ : 1024;
     while (ncap < words) ncap += ncap / 2 + 1024;
     uint32_t *np = nullptr;
@@ -63,7 +77,7 @@ const Lut kLut;
 FastaPacker::FastaPacker(PackedInput &out, uint32_t min_len) : out_(out), min_len_(min_len)
 {
     out_.clear();
-    out_.words.reserve(1024);
+    out_.words.reserve(spsp_packed_words(0));
 }
 
 inline void FastaPacker::flush_word()
@@ -88,11 +102,83 @@ void FastaPacker::end_record()
     ck_acc_ = acc_; ck_fill_ = fill_; ck_word_idx_ = word_idx_;
 }
 
+// Append 16 packed bases (first base in the MSBs of v) behind `pb` pending bits.
+static inline void append16(uint32_t *w, uint64_t &widx, uint32_t &acc, int pb, uint32_t v)
+{
+    const uint64_t x = ((uint64_t)acc << 32) | v;
+    w[widx++] = (uint32_t)(x >> pb);
+    acc = v & ((1u << pb) - 1u);
+}
+
+// One run of sequence bytes without '\n' (part of a FASTA line): valid bases are
+// appended, everything else is deleted (clean_dna, utils.cpp:675-702).  32 bytes
+// per step with AVX2: validity by a nibble LUT, codes (c>>1)&3 packed 4 per byte
+// by two multiply-adds; a block holding any other byte takes the scalar path.
+static inline void pack_run(const uint8_t *p, const uint8_t *end, uint32_t *w, uint64_t &widx, uint32_t &acc,
+                            int &fill, uint64_t &nb)
+{
+#if defined(__AVX2__)
+    const __m256i lut = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
+                                         -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i up = _mm256_set1_epi8((char)0xDF), three = _mm256_set1_epi8(3);
+    const __m256i w41 = _mm256_set1_epi16(0x0104), w161 = _mm256_set1_epi32(0x00010010);
+    const __m256i pick = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                          12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    while (end - p >= 32) {
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+        const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), _mm256_and_si256(c, up));
+        if (_mm256_movemask_epi8(ok) != -1) {
+            for (int i = 0; i < 32; i++) {
+                const uint8_t code = kLut.v[p[i]];
+                if (code < 4) {
+                    acc = (acc << 2) | code;
+                    nb++;
+                    if (++fill == 16) { w[widx++] = acc; acc = 0; fill = 0; }
+                }
+            }
+            p += 32;
+            continue;
+        }
+        const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(c, 1), three);
+        const __m256i b4 = _mm256_madd_epi16(_mm256_maddubs_epi16(codes, w41), w161);   // one byte per 4 bases
+        const __m256i pk = _mm256_shuffle_epi8(b4, pick);
+        const uint32_t v0 = (uint32_t)_mm256_extract_epi32(pk, 0), v1 = (uint32_t)_mm256_extract_epi32(pk, 4);
+        const int pb = 2 * fill;
+        append16(w, widx, acc, pb, v0);
+        append16(w, widx, acc, pb, v1);
+        nb += 32;
+        p += 32;
+    }
+    if (end - p >= 16) {
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
+        const __m128i ok = _mm_cmpeq_epi8(_mm_shuffle_epi8(_mm256_castsi256_si128(lut), c),
+                                          _mm_and_si128(c, _mm256_castsi256_si128(up)));
+        if (_mm_movemask_epi8(ok) == 0xFFFF) {
+            const __m128i codes = _mm_and_si128(_mm_srli_epi16(c, 1), _mm256_castsi256_si128(three));
+            const __m128i b4 = _mm_madd_epi16(_mm_maddubs_epi16(codes, _mm256_castsi256_si128(w41)),
+                                              _mm256_castsi256_si128(w161));
+            const uint32_t v = (uint32_t)_mm_cvtsi128_si32(_mm_shuffle_epi8(b4, _mm256_castsi256_si128(pick)));
+            append16(w, widx, acc, 2 * fill, v);
+            nb += 16;
+            p += 16;
+        }
+    }
+#endif
+    for (; p < end; p++) {
+        const uint8_t code = kLut.v[*p];
+        if (code < 4) {
+            acc = (acc << 2) | code;
+            nb++;
+            if (++fill == 16) { w[widx++] = acc; acc = 0; fill = 0; }
+        }
+    }
+}
+
 void FastaPacker::feed(const uint8_t *p, size_t n)
 {
     if (!n) return;
     any_input_ = true;
-    out_.words.reserve(word_idx_ + n / 16 + 16);
+    out_.words.reserve(word_idx_ + n / 16 + 2);       // every byte is at most one base
     uint32_t *w = out_.words.data();
     const uint8_t *end = p + n;
     uint32_t acc = acc_;
@@ -100,19 +186,11 @@ void FastaPacker::feed(const uint8_t *p, size_t n)
     uint64_t widx = word_idx_, nb = out_.n_bases;
     while (p < end) {
         if (state_ == SEQ) {
-            // hot loop: bases of one line
-            while (p < end) {
-                uint8_t c = *p++;
-                uint8_t code = kLut.v[c];
-                if (code < 4) {
-                    acc = (acc << 2) | code;
-                    nb++;
-                    if (++fill == 16) { w[widx++] = acc; acc = 0; fill = 0; }
-                } else if (c == '\n') {
-                    state_ = LINE_START;
-                    break;
-                }
-            }
+            // bases up to the end of the line (or of this chunk)
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(p, '\n', (size_t)(end - p)));
+            const uint8_t *stop = nl ? nl : end;
+            pack_run(p, stop, w, widx, acc, fill, nb);
+            if (nl) { state_ = LINE_START; p = nl + 1; } else { p = end; }
         } else if (state_ == HEADER) {
             const void *nl = memchr(p, '\n', (size_t)(end - p));
             if (!nl) { p = end; break; }

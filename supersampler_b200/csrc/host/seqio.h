@@ -18,6 +18,10 @@ public:
     WordBuf(const WordBuf &) = delete;
     WordBuf &operator=(const WordBuf &) = delete;
     void reserve(uint64_t words);
+    // Use caller-owned memory of fixed size (a region of a batch staging buffer);
+    // reserve() beyond it throws.  detach() before the owner frees it.
+    void attach(uint32_t *p, uint64_t words);
+    void detach();
     uint32_t *data() { return p_; }
     const uint32_t *data() const { return p_; }
     uint64_t capacity() const { return cap_; }
@@ -26,6 +30,7 @@ private:
     uint32_t *p_ = nullptr;
     uint64_t cap_ = 0;
     bool pinned_;
+    bool external_ = false;
 };
 
 // All records of one input that are at least `min_len` bases long, packed back

@@ -1,5 +1,7 @@
 #include "subsampler.h"
 
+#include "pipeline.h"
+
 #include <getopt.h>
 #include <sys/stat.h>
 
@@ -220,40 +222,56 @@ int sub_sampler_main(int argc, char **argv)
             std::ofstream out_fof(get_out_name(inputfof, output) + ".txt");
             for (const auto &f : files) out_fof << get_out_name(f, output) + ".gz\n";
         }
-        unsigned workers = std::min<unsigned>(c, (unsigned)std::max<size_t>(files.size(), 1));
-        std::vector<std::shared_ptr<DeviceSession>> sessions;
-        for (unsigned g = 0; g < gpus; g++) {
-            unsigned slots = (workers + gpus - 1 - g) / gpus;
-            if (slots == 0) break;
-            sessions.push_back(std::make_shared<DeviceSession>((int)g, (int)k, (int)m1, thr, (int)slots));
-        }
-        std::atomic<size_t> next{0};
+        // Files are dealt round-robin to the GPUs (sketching shards by input file, no collective);
+        // per GPU one batch pipeline: -t host threads pack, one scan + device post-pass per batch.
+        for (const auto &f : files) std::cout << f << std::endl;
+        const unsigned per_gpu = std::max(1u, c / gpus);
+        std::vector<std::string> errors(gpus);
         std::mutex cout_mu;
-        std::vector<std::thread> pool;
-        std::vector<std::string> errors(workers);
-        for (unsigned w = 0; w < workers; w++) {
-            pool.emplace_back([&, w]() {
-                try {
-                    auto &session = sessions[w % sessions.size()];
-                    Subsampler ss(k, m1, s, c, type, abundance, session, (int)(w / sessions.size()));
-                    for (;;) {
-                        size_t i = next.fetch_add(1);
-                        if (i >= files.size()) break;
-                        {
-                            std::lock_guard<std::mutex> g(cout_mu);
-                            std::cout << files[i] << std::endl;
-                        }
-                        ss.parse_fasta_test(files[i], output);
-                        if (verbose) {
-                            std::lock_guard<std::mutex> g(cout_mu);
-                            ss.print_stat();
-                        }
+        auto gpu_work = [&](unsigned g) {
+            try {
+                std::vector<size_t> mine;
+                for (size_t i = g; i < files.size(); i += gpus) mine.push_back(i);
+                if (mine.empty()) return;
+                auto session = std::make_shared<DeviceSession>((int)g, (int)k, (int)m1, thr, 1);
+                BatchSketcher bs(session, (int)k, (int)m1, s, abundance, (int)per_gpu);
+                std::vector<BatchSource> src(mine.size());
+                for (size_t j = 0; j < mine.size(); j++) src[j].path = files[mine[j]];
+                std::vector<std::vector<uint8_t>> sk;
+                std::vector<char> ok;
+                bs.run(src, sk, ok);
+                parallel_for((int)per_gpu, mine.size(), [&](size_t j) {
+                    const std::string &f = files[mine[j]];
+                    if (!ok[j]) {
+                        std::lock_guard<std::mutex> lk(cout_mu);
+                        std::cout << "Can't open file: " << f << std::endl;
+                        return;
                     }
-                } catch (const std::exception &e) {
-                    errors[w] = e.what();
+                    const std::string name = get_out_name(f, output) + ".gz";
+                    if (!write_gz(name, sk[j].data(), sk[j].size(), 6)) {
+                        std::lock_guard<std::mutex> lk(cout_mu);
+                        std::cout << "Can't write file: " << name << std::endl;
+                    }
+                });
+                if (verbose) {
+                    std::lock_guard<std::mutex> lk(cout_mu);
+                    for (size_t j = 0; j < mine.size(); j++)
+                        if (ok[j])
+                            std::cout << files[mine[j]] << ": I selected " << with_commas(bs.selected[j]) << " kmers, sketch of "
+                                      << with_commas(sk[j].size()) << " bytes" << std::endl;
+                    const BatchStats &st = bs.stats;
+                    std::cout << "GPU " << g << ": " << with_commas(st.bases) << " bases in " << st.batches << " batch(es), "
+                              << with_commas(st.hits) << " selected m-mer positions; pack " << st.pack_s * 1e3 << " ms, device "
+                              << st.device_s * 1e3 << " ms (scan kernel " << st.scan_ms << " ms, post-pass " << st.post_ms
+                              << " ms)" << std::endl;
                 }
-            });
-        }
+            } catch (const std::exception &e) {
+                errors[g] = e.what();
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned g = 1; g < gpus; g++) pool.emplace_back(gpu_work, g);
+        gpu_work(0);
         for (auto &t : pool) t.join();
         for (const auto &e : errors)
             if (!e.empty()) throw std::runtime_error(e);

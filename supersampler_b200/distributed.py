@@ -71,6 +71,74 @@ def exchange_elements(sizes: np.ndarray, mn: np.ndarray, lo: np.ndarray, hi: Opt
     return np.concatenate(all_sizes), d_mn, d_lo, d_hi
 
 
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def exchange_device_elements(sizes: np.ndarray, d_mn: int, d_lo: int, d_hi: Optional[int], device):
+    """All-gather of element arrays that already live on this rank's GPU (device
+    pointers from spsp_batch_elements): sizes first, then padded payloads, NCCL
+    over NVLink.  Same return value as exchange_elements."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t_sizes = torch.from_numpy(np.ascontiguousarray(sizes, np.int64)).to(device)
+    all_sizes = [torch.empty_like(t_sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, t_sizes)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    e_rank = [int(x.sum()) for x in all_sizes]
+    e_mine = int(np.asarray(sizes).sum())
+    e_max = max(max(e_rank), 1)
+
+    def gather(ptr, typestr, t_dtype):
+        buf = torch.zeros(e_max, dtype=t_dtype, device=device)
+        if e_mine:
+            buf[:e_mine] = torch.as_tensor(_DevArray(ptr, e_mine, typestr), device=device)
+        out = torch.empty(world * e_max, dtype=t_dtype, device=device)
+        dist.all_gather_into_tensor(out, buf)
+        if all(e == e_max for e in e_rank):
+            return out
+        return torch.cat([out[r * e_max: r * e_max + e_rank[r]] for r in range(world)]).contiguous()
+
+    g_mn = gather(d_mn, "<i4", torch.int32)
+    g_lo = gather(d_lo, "<i8", torch.int64)
+    g_hi = gather(d_hi, "<i8", torch.int64) if d_hi else None
+    return all_sizes.reshape(-1), g_mn, g_lo, g_hi
+
+
+def compare_gathered(all_sizes, d_mn, d_lo, d_hi, rank: int, world: int, dctx, info: Optional[dict] = None):
+    """Tiles dealt to this rank on the gathered elements, then sum-reduce to rank 0."""
+    import torch
+    import torch.distributed as dist
+    dev = d_mn.device
+    n = int(all_sizes.size)
+    sk_off = np.concatenate([[0], np.cumsum(all_sizes)]).astype(np.uint64)
+    d_out = torch.zeros(n * n, dtype=torch.int32, device=dev)
+    torch.cuda.current_stream().synchronize()
+    l0 = dctx.launches()
+    dctx.cmp_load_device(sk_off, d_mn.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr() if d_hi is not None else None)
+    dctx.cmp_run_device((0, n), (0, n), True, rank, world, d_out.data_ptr(), n)   # synchronises its stream
+    if info is not None:
+        info.update(kernel_ms=dctx.cmp_kernel_ms(), launches=dctx.launches() - l0)
+    dist.reduce(d_out, dst=0, op=dist.ReduceOp.SUM)
+    inter = d_out.cpu().numpy().view(np.uint32).reshape(n, n)
+    return inter, all_sizes.astype(np.uint64), False
+
+
+def allgather_compare_device(elem_off, dctx, rank: int, world: int, info: Optional[dict] = None, slot: int = 0):
+    """Compare stage of a multi-GPU job whose sketches were just built by a device
+    batch on every rank (elements still resident): all-gather + tiles + reduce."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sizes = np.diff(np.asarray(elem_off, np.int64))
+    d_mn, d_lo, d_hi = dctx.batch_element_ptrs(slot)
+    all_sizes, g_mn, g_lo, g_hi = exchange_device_elements(sizes, d_mn, d_lo, d_hi if dctx.k > 32 else None, dev)
+    return compare_gathered(all_sizes, g_mn, g_lo, g_hi, rank, world, dctx, info)
+
+
 def allgather_compare(sketches: Sequence[bytes], k: int, m: int, rank: int, world: int, dctx, info: Optional[dict] = None):
     """All-vs-all compare of the union of all ranks' sketches (rank-major order).
     Returns (inter[N,N] uint32 -- complete on rank 0 --, sizes[N] uint64, False)."""

@@ -291,3 +291,100 @@ def test_device_postpass_golden_and_host_agree(golden):
         sk = ctx.sketch_batch(words, nb, rb, re_, ri, 1, s, a)[0]
         ctx.close()
         assert sha(sk) == golden["sketch"][name]["sha256"], name
+
+
+# ---------------------------------------------------------------- batch pipeline (host threads + one device batch)
+
+def _golden_groups():
+    groups = {}
+    for name in sorted(SKETCH_CASES):
+        inp, k, m, s, a = SKETCH_CASES[name]
+        groups.setdefault((k, m, s, a), []).append((name, inp))
+    return groups
+
+
+def test_pipeline_matches_reference_goldens(golden):
+    """Every golden sketch case through the batch pipeline, cases of one (k, m, s, a) in one batch."""
+    for (k, m, s, a), cases in _golden_groups().items():
+        pl = S.Pipeline(k, m, s, a, threads=4)
+        info = {}
+        sks = pl.sketch([build_input(inp) for _, inp in cases], info=info)
+        pl.close()
+        assert info["batches"] == 1
+        for (name, _), sk in zip(cases, sks):
+            assert sha(sk) == golden["sketch"][name]["sha256"], name
+
+
+def test_pipeline_files_gz_missing_and_compare(tmp_path, golden, oracle):
+    """File inputs (plain, gzip, unopenable) + device-resident hand-off to the compare stage."""
+    name = "fam12_s100"
+    inputs, k, m, s, nq, prec, thr = COMPARE_CASES[name]
+    paths = []
+    for i, inp in enumerate(inputs):
+        p = tmp_path / (inp + (".fa.gz" if i % 3 == 1 else ".fa"))
+        data = build_input(inp)
+        if i % 3 == 1:
+            with gzip.open(p, "wb", compresslevel=1) as f:
+                f.write(data)
+        else:
+            p.write_bytes(data)
+        paths.append(str(p))
+    g = golden["compare"][name]
+    pl = S.Pipeline(k, m, s, threads=5)
+    sks = pl.sketch(paths)
+    assert [sha(x) for x in sks] == g["sketch_sha256"]
+    inter, sizes, full = pl.compare()
+    o_inter, o_sizes, _, _ = oracle.compare(sks)
+    assert not full
+    assert np.array_equal(sizes, o_sizes)
+    assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    names = [i + ".gz" for i in inputs]
+    assert sha(S.format_csv(names, len(names), inter, full, sizes, False, prec, thr)) == g["containment_sha256"]
+    assert sha(S.format_csv(names, len(names), inter, full, sizes, True, prec, thr)) == g["jaccard_sha256"]
+    # query mode on the same device-resident elements
+    inter_q, _, full_q = pl.compare(3)
+    assert full_q
+    want = (o_inter + o_inter.T)[:3]
+    got = inter_q.copy()
+    np.fill_diagonal(got[:, :3], 0)
+    assert np.array_equal(got, want)
+    # an unopenable file is skipped, the others are unaffected (SubSampler.cpp:313-322)
+    mixed = pl.sketch([paths[0], str(tmp_path / "nope.fa"), build_input(inputs[2])])
+    assert mixed[1] is None and sha(mixed[0]) == g["sketch_sha256"][0] and sha(mixed[2]) == g["sketch_sha256"][2]
+    pl.close()
+
+
+def test_pipeline_several_batches(oracle):
+    """A job cut into several device batches gives the same bytes and counts as one batch."""
+    fas = [synth.fasta_bytes([(nm, g)]) for nm, g in synth.genome_family(20, 60_000, seed=11)]
+    fas.insert(7, build_input("reads"))
+    fas.insert(3, build_input("empty"))
+    k, m, s = 31, 11, 20
+    one = S.Pipeline(k, m, s, threads=6)
+    many = S.Pipeline(k, m, s, threads=3, max_batch_bases=200_000)
+    i1, i2 = {}, {}
+    a = one.sketch(fas, info=i1)
+    b = many.sketch(fas, info=i2)
+    assert i1["batches"] == 1 and i2["batches"] > 3
+    assert a == b
+    assert a == S.sketch_buffers(fas, k, m, s, threads=4)          # per-file path with the host post-pass
+    ra, rb = one.compare(), many.compare()
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    o_inter, o_sizes, _, _ = oracle.compare(a)
+    assert np.array_equal(ra[1], o_sizes)
+    assert np.array_equal(np.triu(ra[0], 1), np.triu(o_inter, 1))
+    one.close(); many.close()
+
+
+def test_pipeline_k63(oracle):
+    fas = [build_input("nasty"), build_input("multi"), build_input("fam12_2")]
+    k, m, s = 63, 15, 10
+    for mb in (None, 100_000):
+        pl = S.Pipeline(k, m, s, threads=2, max_batch_bases=mb)
+        sks = pl.sketch(fas)
+        assert sks == [oracle.sketch(f, k, m, s)[0] for f in fas]
+        inter, sizes, _ = pl.compare()
+        o_inter, o_sizes, _, _ = oracle.compare(sks)
+        assert np.array_equal(sizes, o_sizes)
+        assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+        pl.close()
