@@ -13,9 +13,12 @@
 #include "postpass.cuh"
 
 #include <algorithm>
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace spsp {
 
@@ -64,7 +67,7 @@ struct PostpassBuffers {
     DBuf pc_first, pc_nk, pc_min, pc_meta, pc_eoff;
     DBuf eA, eklo, ekhi, epm, idx0, idx1, idx2, skey, skey2, head, uid;
     DBuf uA, uklo, ukhi, ufirst, upm, ucnt, uhead, bflag, bidm, bstart, ukey32, ukey32b, uidx0, uidx1, uidx2, ins, seen;
-    DBuf bbytes, bnmax, boff, body, in_bytes, in_sel, in_elems, eflag, eoff, el_min, el_klo, el_khi, cubtmp;
+    DBuf visit, bbytes, bnmax, boff, body, in_bytes, in_sel, in_elems, eflag, eoff, el_min, el_klo, el_khi, cubtmp;
     HBuf h_cnt, h_body, h_in, h_off;
 };
 
@@ -136,7 +139,8 @@ __device__ __forceinline__ long long find_rec(const uint64_t *__restrict__ rec_b
 // (host: build_sketch_t drops hits that straddle a record / records < k).
 __global__ void pp_classify_kernel(const spsp_hit *__restrict__ hits, uint64_t n_hits, const uint64_t *__restrict__ rec_begin,
                                    const uint64_t *__restrict__ rec_end, uint64_t n_rec, int k, int m,
-                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, Counters *cnt)
+                                   uint64_t invalid_key, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
+                                   Counters *cnt)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_hits) return;
@@ -149,7 +153,7 @@ __global__ void pp_classify_kernel(const spsp_hit *__restrict__ hits, uint64_t n
             valid = pos + (uint64_t)m <= e && e - b >= (uint64_t)k;
         }
     }
-    key[i] = valid ? pos : ~0ULL;
+    key[i] = valid ? pos : invalid_key;             // sorts behind every position
     val[i] = (hits[i].canon << 1) | (hits[i].rev & 1u);
     if (valid) atomicAdd(&cnt->n_valid, 1ULL);
 }
@@ -235,7 +239,7 @@ __global__ void pp_replay_kernel(const uint64_t *__restrict__ key, const uint32_
                                  uint32_t *__restrict__ cl_np, uint32_t *__restrict__ cl_nk,
                                  const uint32_t *__restrict__ cl_poff, uint64_t *__restrict__ pc_first,
                                  uint32_t *__restrict__ pc_nk, uint32_t *__restrict__ pc_min, uint32_t *__restrict__ pc_meta,
-                                 uint64_t max_pieces, const Counters *cnt)
+                                 uint64_t max_pieces, unsigned long long *__restrict__ in_sel, const Counters *cnt)
 {
     const uint64_t c_id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c_id >= cnt->n_clusters) return;
@@ -305,7 +309,10 @@ __global__ void pp_replay_kernel(const uint64_t *__restrict__ key, const uint32_
     // any more (the next hit is more than d + 1 away), the tracked minimizer is outdated (posmin <= p_last)
     // and the rescan finds a non-selected one: the piece ends at c_end in both cases.
     if (old_valid) emit(last, c_end, old_min, old_rev);
-    if (!WRITE) { cl_np[c_id] = np; cl_nk[c_id] = nk; }
+    if (!WRITE) {
+        cl_np[c_id] = np; cl_nk[c_id] = nk;
+        if (nk) atomicAdd(in_sel + input, (unsigned long long)nk);     // header field 3: selected k-mer occurrences
+    }
 }
 
 // ---------------------------------------------------------- K4 k-mer entries
@@ -318,7 +325,7 @@ __global__ void pp_entries_kernel(const uint32_t *__restrict__ packed, const uin
                                   const uint32_t *__restrict__ pc_meta, const uint32_t *__restrict__ pc_eoff, int k, int m,
                                   uint64_t bound, int input_shift, uint64_t *__restrict__ eA, uint64_t *__restrict__ eklo,
                                   uint64_t *__restrict__ ekhi, uint8_t *__restrict__ epm, uint32_t *__restrict__ idx,
-                                  unsigned long long *__restrict__ in_sel, const Counters *cnt)
+                                  const Counters *cnt)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bound) return;
@@ -344,14 +351,17 @@ __global__ void pp_entries_kernel(const uint32_t *__restrict__ packed, const uin
     const int d = k - m;
     const uint32_t mmask = (1u << (2 * m)) - 1u;
     unsigned pm = 255;
-    for (int q = 0; q <= d; q++) {
-        if (((uint32_t)k_shr(key, 2 * (d - q)).lo & mmask) == mn) { pm = (unsigned)q; break; }
+    if (k <= 32) {
+        for (int q = 0; q <= d; q++)
+            if (((uint32_t)(key.lo >> (2 * (d - q))) & mmask) == mn) { pm = (unsigned)q; break; }
+    } else {
+        for (int q = 0; q <= d; q++)
+            if (((uint32_t)k_shr(key, 2 * (d - q)).lo & mmask) == mn) { pm = (unsigned)q; break; }
     }
     eA[t] = ((uint64_t)(meta >> 1) << input_shift) | mn;
     eklo[t] = key.lo;
     if (ekhi) ekhi[t] = key.hi;
     epm[t] = (uint8_t)pm;
-    atomicAdd(in_sel + (meta >> 1), 1ULL);
 }
 
 __global__ void pp_gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n,
@@ -408,7 +418,7 @@ __global__ void pp_unique_finish_kernel(const uint64_t *__restrict__ uA, const u
     if (u >= bound) return;
     uidx[u] = (uint32_t)u;
     seen[u] = 0;
-    if (u >= cnt->n_unique) { bflag[u] = 0; ukey32[u] = 0xFFFFFFFFu; return; }
+    if (u >= cnt->n_unique) { bflag[u] = 0; ukey32[u] = (uint32_t)bound; return; }     // padding sorts last
     const uint64_t next = (u + 1 < cnt->n_unique) ? uhead[u + 1] : cnt->n_entries;
     ucnt[u] = (uint8_t)((next - uhead[u]) & 0xFF);
     bflag[u] = (u == 0 || uA[u] != uA[u - 1]) ? 1u : 0u;
@@ -435,169 +445,393 @@ __global__ void pp_gather_uA_kernel(const uint64_t *__restrict__ uA, const uint3
 
 // -------------------------------------------------------- K6 reconstruction
 
+// One bucket's unique k-mers, sorted by key; indices are bucket-relative.  The
+// arrays live in shared memory (small buckets, staged by the warp) or in global
+// memory (buckets larger than RC_CAP).
 struct BucketView {
-    const uint64_t *uklo, *ukhi;
-    const uint8_t *ucnt;
+    const uint64_t *klo, *khi;     // khi null when k <= 32
+    const uint8_t *cnt;
     uint8_t *seen;
-    uint32_t bs, be;
+    uint32_t n;
     unsigned abundance;
     int k;
 };
 
 __device__ __forceinline__ K128 bv_key(const BucketView &v, uint32_t u)
 {
-    return K128{v.uklo[u], v.ukhi ? v.ukhi[u] : 0};
+    return K128{v.klo[u], v.khi ? v.khi[u] : 0};
 }
 // binary search in the bucket's key-sorted unique list
 __device__ __forceinline__ int bv_find(const BucketView &v, const K128 &key)
 {
-    uint32_t lo = v.bs, hi = v.be;
+    uint32_t lo = 0, hi = v.n;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if (k_lt(bv_key(v, mid), key)) lo = mid + 1; else hi = mid;
     }
-    return (lo < v.be && k_eq(bv_key(v, lo), key)) ? (int)lo : -1;
+    return (lo < v.n && k_eq(bv_key(v, lo), key)) ? (int)lo : -1;
 }
-// find_next (SubSampler.cpp:566-602): probe order A,T,C,G (:568)
-__device__ __forceinline__ int bv_step(const BucketView &v, const K128 &cur, bool left, K128 *out)
+__device__ __forceinline__ K128 bv_neighbour(const K128 &cur, bool left, int t, int k)
 {
-    const int k = v.k;
-    const K128 kmask = k_shr(K128{~0ULL, ~0ULL}, 128 - 2 * k);
-#pragma unroll 1
-    for (int t = 0; t < 4; t++) {
-        const uint64_t o = (t == 0) ? 0 : (t == 1) ? 2 : (t == 2) ? 1 : 3;
-        K128 nx;
-        if (left) {
-            nx = k_shr(cur, 2);
-            K128 top = k_shl(K128{o, 0}, 2 * k - 2);
-            nx.lo |= top.lo; nx.hi |= top.hi;
-        } else {
-            nx = k_shl(cur, 2);
-            nx.lo |= o;
-            nx.lo &= kmask.lo; nx.hi &= kmask.hi;
-        }
-        int u = bv_find(v, nx);
-        if (u >= 0 && !v.seen[u] && v.ucnt[u] >= v.abundance) {
-            v.seen[u] = 1;
-            *out = nx;
-            return u;
-        }
+    const uint64_t o = (0x3120u >> (4 * t)) & 3u;                          // A, T, C, G (SubSampler.cpp:568)
+    K128 nx;
+    if (left) {
+        nx = k_shr(cur, 2);
+        K128 top = k_shl(K128{o, 0}, 2 * k - 2);
+        nx.lo |= top.lo; nx.hi |= top.hi;
+    } else {
+        const K128 kmask = k_shr(K128{~0ULL, ~0ULL}, 128 - 2 * k);
+        nx = k_shl(cur, 2);
+        nx.lo |= o;
+        nx.lo &= kmask.lo; nx.hi &= kmask.hi;
     }
-    return -1;
+    return nx;
+}
+constexpr int RC_CAP = 256;          // bucket size staged in shared memory
+constexpr int RC_SLOTS = 512;        // open-addressing table over the staged bucket (load <= 0.5)
+constexpr int RC_WARPS = 4;          // buckets in flight per CTA (one warp each)
+constexpr int RC_SK = 192;           // 2-bit codes of a super-k-mer (2k-m <= 123, grows both ways from 64)
+constexpr uint32_t VISIT_START = 0u << 30, VISIT_LEFT = 1u << 30, VISIT_RIGHT = 2u << 30, VISIT_MASK = (1u << 30) - 1u;
+constexpr uint32_t VISIT_END = 0xFFFFFFFFu;
+constexpr uint16_t ADJ_NONE = 0xFFFF;
+
+// Shared-memory slice of one warp of pp_chain_kernel.
+struct RcSmem {
+    uint64_t *klo, *khi;
+    uint32_t *slot;
+    uint16_t *adj;               // [u][left 0..3, right 0..3] neighbour index in probe order A,T,C,G
+    uint16_t *ins;
+    uint8_t *cnt, *seen, *pm;
+};
+static size_t rc_smem_bytes(bool hi128)
+{
+    return (size_t)RC_WARPS * (RC_CAP * (8 + (hi128 ? 8 : 0) + 16 + 2 + 3) + RC_SLOTS * 4);
+}
+__device__ __forceinline__ RcSmem rc_carve(uint8_t *base, int wi, bool hi128)
+{
+    RcSmem r;
+    r.klo = reinterpret_cast<uint64_t *>(base) + (size_t)wi * RC_CAP;
+    base += (size_t)RC_WARPS * RC_CAP * 8;
+    r.khi = nullptr;
+    if (hi128) { r.khi = reinterpret_cast<uint64_t *>(base) + (size_t)wi * RC_CAP; base += (size_t)RC_WARPS * RC_CAP * 8; }
+    r.adj = reinterpret_cast<uint16_t *>(base) + (size_t)wi * RC_CAP * 8;
+    base += (size_t)RC_WARPS * RC_CAP * 16;
+    r.slot = reinterpret_cast<uint32_t *>(base) + (size_t)wi * RC_SLOTS;
+    base += (size_t)RC_WARPS * RC_SLOTS * 4;
+    r.ins = reinterpret_cast<uint16_t *>(base) + (size_t)wi * RC_CAP;
+    base += (size_t)RC_WARPS * RC_CAP * 2;
+    r.cnt = base + (size_t)wi * RC_CAP;
+    r.seen = base + (size_t)(RC_WARPS + wi) * RC_CAP;
+    r.pm = base + (size_t)(2 * RC_WARPS + wi) * RC_CAP;
+    return r;
+}
+__device__ __forceinline__ uint32_t rc_hash(const K128 &key)
+{
+    return (uint32_t)(((key.lo ^ (key.hi * 0xC2B2AE3D27D4EB4FULL)) * 0x9E3779B97F4A7C15ULL) >> (64 - 9));
+}
+static_assert(RC_SLOTS == 512, "rc_hash yields 9 bits");
+
+// Index of `key` in the staged bucket, or -1.
+__device__ __forceinline__ int rc_lookup(const RcSmem &sm, const K128 &key)
+{
+    uint32_t s = rc_hash(key);
+    for (;;) {
+        const uint32_t idx = sm.slot[s];
+        if (idx == 0xFFFFFFFFu) return -1;
+        if (sm.klo[idx] == key.lo && (!sm.khi || sm.khi[idx] == key.hi)) return (int)idx;
+        s = (s + 1) & (RC_SLOTS - 1);
+    }
 }
 
-// Writer loop + reconstruct_superkmer (SubSampler.cpp:459-504, :512-564) for one
-// bucket.  WRITE = false computes the byte size; WRITE = true emits the bytes.
-template <bool WRITE>
-__global__ void pp_reconstruct_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo,
-                                      const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
-                                      const uint8_t *__restrict__ upm, uint8_t *__restrict__ seen,
-                                      const uint32_t *__restrict__ ins, const uint32_t *__restrict__ bstart, int k, int m,
-                                      unsigned abundance, int input_shift, uint32_t *__restrict__ bbytes,
-                                      uint32_t *__restrict__ bnmax, const uint64_t *__restrict__ boff,
-                                      uint8_t *__restrict__ body, unsigned long long *__restrict__ in_bytes,
-                                      const Counters *cnt)
+// find_first_kmer + reconstruct_superkmer + find_next (SubSampler.cpp:512-620) on a
+// bucket staged in shared memory.  The four neighbour look-ups of every k-mer in
+// both directions are done up front by the whole warp (hash table); the greedy
+// chain itself -- inherently sequential -- then only follows indices and `seen`
+// flags on lane 0, which records the visit order with each k-mer's role.
+__device__ __forceinline__ void rc_walk_staged(const RcSmem &sm, uint32_t nb, int k, int m, unsigned abundance,
+                                               uint32_t *__restrict__ visit)
 {
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= cnt->n_buckets) return;
-    const uint32_t bs = bstart[b], be = (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
-    const int d = k - m, full = 2 * k - m;
-    BucketView v{uklo, ukhi, ucnt, seen, bs, be, abundance, k};
-    const uint32_t minimizer = (uint32_t)(uA[bs] & ((1ULL << input_shift) - 1));
-    const uint32_t mmask = (1u << (2 * m)) - 1u;
-    uint32_t n_max = 0, text_len = 0;
-    uint8_t *p_max = nullptr, *p_txt = nullptr;
-    if (WRITE) {
-        uint8_t *o = body + boff[b];
-        for (int i = 0; i < m; i++) o[i] = "ACTG"[(minimizer >> (2 * (m - 1 - i))) & 3];
-        const uint32_t nm = bnmax[b];
-        const uint32_t sz = nm ? 1 + nm * (uint32_t)(2 * d) / 4 : 0;          // strCompressor: mod byte + 4 bases/byte
-        o[m] = (uint8_t)sz; o[m + 1] = (uint8_t)(sz >> 8); o[m + 2] = (uint8_t)(sz >> 16); o[m + 3] = (uint8_t)(sz >> 24);
-        p_max = o + m + 4;
-        if (sz) *p_max++ = 0;                                               // 2d is a multiple of 4: mod byte 0
-        p_txt = o + m + 4 + sz;
+    const int lane = threadIdx.x & 31;
+    const int d = k - m;
+    const bool hi128 = sm.khi != nullptr;
+    for (uint32_t idx = lane; idx < nb * 8; idx += 32) {
+        const uint32_t u = idx >> 3, t = idx & 3;
+        const bool left = !(idx & 4);
+        const K128 cand = bv_neighbour(K128{sm.klo[u], hi128 ? sm.khi[u] : 0}, left, (int)t, k);
+        const int w = rc_lookup(sm, cand);
+        sm.adj[idx] = (w >= 0 && sm.cnt[w] >= abundance) ? (uint16_t)w : ADJ_NONE;
     }
-    uint8_t sk[192];                                                        // 2-bit codes of the super-k-mer (grows both ways from 64)
-    uint32_t cursor = bs;
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t nv = 0, cursor = 0;
+        for (;;) {
+            // find_first_kmer (:604-620): first unseen entry in insertion order
+            uint32_t start = 0;
+            for (; cursor < nb; cursor++) {
+                start = sm.ins[cursor];
+                if (!sm.seen[start] && sm.cnt[start] >= abundance) break;
+            }
+            if (cursor >= nb) break;
+            sm.seen[start] = 1;
+            visit[nv++] = start | VISIT_START;
+            const uint8_t pms = sm.pm[start];
+            uint64_t n_left = (uint64_t)d - pms, n_right = pms;
+            uint32_t cur = start, ext = 0;                   // ext = k-mers added to the start k-mer
+            while (ext != (uint32_t)d) {                     // |sk| != 2k-m
+                const bool left = n_left != 0;
+                if (!left && n_right == 0) break;
+                // find_next (:566-602): first neighbour in probe order that is in the bucket and unseen
+                const uint2 pk = *reinterpret_cast<const uint2 *>(sm.adj + cur * 8 + (left ? 0 : 4));
+                int found = -1;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t c = ((t < 2 ? pk.x : pk.y) >> (16 * (t & 1))) & 0xFFFFu;
+                    if (found < 0 && c != ADJ_NONE && !sm.seen[c]) found = (int)c;
+                }
+                if (found >= 0) sm.seen[found] = 1;
+                if (left) {
+                    n_left--;
+                    if (found >= 0) { visit[nv++] = (uint32_t)found | VISIT_LEFT; ext++; }
+                    else n_left = 0;
+                    cur = (n_left == 0) ? start : (uint32_t)found;
+                } else {
+                    n_right--;
+                    if (found < 0) break;
+                    visit[nv++] = (uint32_t)found | VISIT_RIGHT;
+                    ext++;
+                    cur = (uint32_t)found;
+                }
+            }
+        }
+        if (nv < nb) visit[nv] = VISIT_END;                  // k-mers below the abundance are never visited
+    }
+    __syncwarp();
+}
+
+// Same walk for a bucket too large to stage: global memory, binary search, lanes
+// 0..3 probing the four neighbours at once.
+__device__ __forceinline__ int rc_step_global(const BucketView &v, const K128 &cur, bool left, K128 *out)
+{
+    const int lane = threadIdx.x & 31;
+    int u = -1;
+    if (lane < 4) {
+        u = bv_find(v, bv_neighbour(cur, left, lane, v.k));
+        if (u >= 0 && (v.seen[u] || v.cnt[u] < v.abundance)) u = -1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, u >= 0);
+    if (!bal) return -1;
+    const int t = __ffs(bal) - 1;
+    u = __shfl_sync(0xffffffffu, u, t);
+    if (lane == 0) v.seen[u] = 1;
+    __syncwarp();
+    *out = bv_neighbour(cur, left, t, v.k);
+    return u;
+}
+__device__ __forceinline__ void rc_walk_global(const BucketView &v, const uint8_t *__restrict__ pm,
+                                               const uint32_t *__restrict__ ins_g, uint32_t ins_base, int k, int m,
+                                               uint32_t *__restrict__ visit)
+{
+    const int lane = threadIdx.x & 31;
+    const int d = k - m;
+    const uint32_t nb = v.n;
+    uint32_t nv = 0, cursor = 0;
     for (;;) {
-        // find_first_kmer (:604-620): first unseen entry in insertion order
-        while (cursor < be && (seen[ins[cursor]] || ucnt[ins[cursor]] < abundance)) cursor++;
-        if (cursor >= be) break;
-        const uint32_t start = ins[cursor];
-        seen[start] = 1;
+        uint32_t start = 0;
+        for (; cursor < nb; cursor++) {
+            start = ins_g[cursor] - ins_base;
+            if (!v.seen[start] && v.cnt[start] >= v.abundance) break;
+        }
+        if (cursor >= nb) break;
+        __syncwarp();
+        if (lane == 0) { v.seen[start] = 1; visit[nv] = start | VISIT_START; }
+        __syncwarp();
+        nv++;
         const K128 skey = bv_key(v, start);
-        int lo = 64, hi = 64 + k;
-        for (int i = 0; i < k; i++) sk[64 + i] = (uint8_t)(k_shr(skey, 2 * (k - 1 - i)).lo & 3);
-        uint64_t n_left = (uint64_t)d - upm[start], n_right = upm[start];
+        uint64_t n_left = (uint64_t)d - pm[start], n_right = pm[start];
         K128 cur = skey;
-        while (hi - lo != full) {
+        uint32_t ext = 0;
+        while (ext != (uint32_t)d) {
             if (n_left != 0) {
                 K128 nx;
-                int u = bv_step(v, cur, true, &nx);
+                const int u = rc_step_global(v, cur, true, &nx);
                 n_left--;
-                if (u >= 0) sk[--lo] = (uint8_t)(k_shr(nx, 2 * k - 2).lo & 3);
-                else n_left = 0;
+                if (u >= 0) {
+                    if (lane == 0) visit[nv] = (uint32_t)u | VISIT_LEFT;
+                    nv++; ext++;
+                } else {
+                    n_left = 0;
+                }
                 cur = (n_left == 0) ? skey : nx;
             } else if (n_right != 0) {
                 K128 nx;
-                int u = bv_step(v, cur, false, &nx);
+                const int u = rc_step_global(v, cur, false, &nx);
                 n_right--;
                 if (u < 0) break;
-                sk[hi++] = (uint8_t)(nx.lo & 3);
+                if (lane == 0) visit[nv] = (uint32_t)u | VISIT_RIGHT;
+                nv++; ext++;
                 cur = nx;
             } else {
                 break;
             }
         }
-        const int len = hi - lo;
-        if (len == full) {                                                  // :479-485
-            if (WRITE) {
-                // prefix(d) + suffix(d), 4 bases per byte, first base in bits 7-6
-                uint32_t acc = 0;
-                int nb = 0;
-                for (int i = 0; i < 2 * d; i++) {
-                    const uint8_t c = (i < d) ? sk[lo + i] : sk[lo + k + (i - d)];
-                    acc = (acc << 2) | c;
-                    if (++nb == 4) { *p_max++ = (uint8_t)acc; acc = 0; nb = 0; }
-                }
-            }
-            n_max++;
-        } else {                                                            // :486-494
-            int q = -1;
-            uint32_t win = 0;
-            for (int t = 0; t < len; t++) {
-                win = ((win << 2) | sk[lo + t]) & mmask;
-                if (t + 1 >= m && win == minimizer) { q = t + 1 - m; break; }
-            }
-            if (q < 0) {
-                if (WRITE) { for (int t = 0; t < len; t++) *p_txt++ = "ACTG"[sk[lo + t]]; *p_txt++ = '\n'; *p_txt++ = '\n'; }
-                text_len += (uint32_t)len + 2;
-            } else {
-                if (WRITE) {
-                    for (int t = 0; t < q; t++) *p_txt++ = "ACTG"[sk[lo + t]];
-                    *p_txt++ = '\n';
-                    for (int t = q + m; t < len; t++) *p_txt++ = "ACTG"[sk[lo + t]];
-                    *p_txt++ = '\n';
-                }
-                text_len += (uint32_t)(len - m) + 2;
-            }
-        }
     }
-    if (WRITE) {
-        *p_txt++ = '\n'; *p_txt++ = '\n';
-    } else {
-        const uint32_t sz = n_max ? 1 + n_max * (uint32_t)(2 * d) / 4 : 0;
-        const uint32_t bytes = (uint32_t)m + 4 + sz + text_len + 2;
-        bbytes[b] = bytes;
-        bnmax[b] = n_max;
-        atomicAdd(in_bytes + (uA[bs] >> input_shift), (unsigned long long)bytes);
+    if (lane == 0 && nv < nb) visit[nv] = VISIT_END;
+}
+
+// One bucket per warp: the visit order of its k-mers (start / left extension /
+// right extension of each super-k-mer), everything pp_measure_kernel and
+// pp_emit_kernel need to size and write the bytes without another look-up.
+__global__ void __launch_bounds__(RC_WARPS * 32)
+pp_chain_kernel(const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
+                const uint8_t *__restrict__ upm, uint8_t *__restrict__ seen_g, const uint32_t *__restrict__ ins,
+                const uint32_t *__restrict__ bstart, int k, int m, unsigned abundance, uint32_t *__restrict__ visit,
+                const Counters *cnt)
+{
+    extern __shared__ __align__(16) uint8_t rc_smem[];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const RcSmem sm = rc_carve(rc_smem, wi, ukhi != nullptr);
+    const uint64_t n_buckets = cnt->n_buckets;
+    for (uint64_t b = (uint64_t)blockIdx.x * RC_WARPS + wi; b < n_buckets; b += (uint64_t)gridDim.x * RC_WARPS) {
+        const uint32_t bs = bstart[b], be = (b + 1 < n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
+        const uint32_t nb = be - bs;
+        __syncwarp();
+        if (nb <= (uint32_t)RC_CAP) {
+            for (int i = lane; i < RC_SLOTS; i += 32) sm.slot[i] = 0xFFFFFFFFu;
+            for (uint32_t i = lane; i < nb; i += 32) {
+                sm.klo[i] = uklo[bs + i];
+                if (ukhi) sm.khi[i] = ukhi[bs + i];
+                sm.cnt[i] = ucnt[bs + i];
+                sm.pm[i] = upm[bs + i];
+                sm.seen[i] = 0;
+                sm.ins[i] = (uint16_t)(ins[bs + i] - bs);
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < nb; i += 32) {                          // keys of a bucket are distinct
+                uint32_t s = rc_hash(K128{sm.klo[i], ukhi ? sm.khi[i] : 0});
+                while (atomicCAS(&sm.slot[s], 0xFFFFFFFFu, i) != 0xFFFFFFFFu) s = (s + 1) & (RC_SLOTS - 1);
+            }
+            __syncwarp();
+            rc_walk_staged(sm, nb, k, m, abundance, visit + bs);
+        } else {
+            BucketView v{uklo + bs, ukhi ? ukhi + bs : nullptr, ucnt + bs, seen_g + bs, nb, abundance, k};
+            rc_walk_global(v, upm + bs, ins + bs, bs, k, m, visit + bs);
+        }
     }
 }
 
-__global__ void pp_clear_seen_kernel(uint8_t *__restrict__ seen, uint64_t bound)
+// Leftmost occurrence of the minimizer in the super-k-mer sk[lo, lo+len), -1 if none (warp-parallel find()).
+__device__ __forceinline__ int rc_find_minimizer(const uint8_t *sk, int lo, int len, int m, uint32_t minimizer)
 {
-    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < bound) seen[u] = 0;
+    const int lane = threadIdx.x & 31;
+    int best = 0x7fffffff;
+    for (int t = lane; t + m <= len; t += 32) {
+        uint32_t w = 0;
+        for (int i = 0; i < m; i++) w = (w << 2) | sk[lo + t + i];
+        if (w == minimizer) { best = t; break; }
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    return best == 0x7fffffff ? -1 : best;
+}
+
+// Writer loop (SubSampler.cpp:459-504), one bucket per warp, from the visit order:
+// minimizer text, u32 size, packed maximal super-k-mers (prefix(d) + suffix(d), 4
+// bases per byte), the others as "prefix\nsuffix\n" text split at the leftmost
+// minimizer occurrence, "\n\n".  WRITE = false only measures (bytes per bucket and
+// per input), WRITE = true emits at the offsets computed from that.
+template <bool WRITE>
+__global__ void __launch_bounds__(8 * 32)
+pp_emit_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ ukhi,
+               const uint32_t *__restrict__ visit, const uint32_t *__restrict__ bstart, int k, int m, int input_shift,
+               uint32_t *__restrict__ bbytes, uint32_t *__restrict__ bnmax, const uint64_t *__restrict__ boff,
+               uint8_t *__restrict__ body, unsigned long long *__restrict__ in_bytes, const Counters *cnt)
+{
+    __shared__ uint8_t s_sk[8][RC_SK];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    uint8_t *sk = s_sk[wi];
+    const uint64_t n_buckets = cnt->n_buckets;
+    const int d = k - m, full = 2 * k - m;
+    for (uint64_t b = (uint64_t)blockIdx.x * 8 + wi; b < n_buckets; b += (uint64_t)gridDim.x * 8) {
+        const uint32_t bs = bstart[b], be = (b + 1 < n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
+        const uint32_t nb = be - bs;
+        const uint32_t minimizer = (uint32_t)(uA[bs] & ((1ULL << input_shift) - 1));
+        uint8_t *p_max = nullptr, *p_txt = nullptr;
+        if (WRITE) {
+            uint8_t *o = body + boff[b];
+            const uint32_t nm = bnmax[b];
+            const uint32_t sz = nm ? 1 + nm * (uint32_t)(2 * d) / 4 : 0;        // strCompressor: mod byte + 4 bases/byte
+            if (lane == 0) {
+                for (int i = 0; i < m; i++) o[i] = "ACTG"[(minimizer >> (2 * (m - 1 - i))) & 3];
+                o[m] = (uint8_t)sz; o[m + 1] = (uint8_t)(sz >> 8); o[m + 2] = (uint8_t)(sz >> 16); o[m + 3] = (uint8_t)(sz >> 24);
+                if (sz) o[m + 4] = 0;                                           // 2d is a multiple of 4: mod byte 0
+            }
+            p_max = o + m + 4 + (sz ? 1 : 0);
+            p_txt = o + m + 4 + sz;
+        }
+        uint32_t n_max = 0, text_len = 0;
+        uint32_t j = 0;
+        while (j < nb) {
+            const uint32_t head = visit[bs + j];
+            if (head == VISIT_END) break;
+            // one super-k-mer: its start entry and the extensions that follow it (lefts first, then rights)
+            uint32_t e = j + 1, n_l = 0;
+            while (e < nb) {
+                const uint32_t x = visit[bs + e];
+                if (x == VISIT_END || (x >> 30) == 0) break;
+                n_l += (x >> 30) == 1;
+                e++;
+            }
+            const int lo = 64 - (int)n_l, len = k + (int)(e - j - 1);
+            if (!WRITE && len == full) { n_max++; j = e; continue; }           // :479-485, size known without the string
+            const K128 skey{uklo[bs + (head & VISIT_MASK)], ukhi ? ukhi[bs + (head & VISIT_MASK)] : 0};
+            __syncwarp();
+            for (int i = lane; i < k; i += 32) sk[64 + i] = (uint8_t)(k_shr(skey, 2 * (k - 1 - i)).lo & 3);
+            for (uint32_t t = j + 1 + lane; t < e; t += 32) {
+                const uint32_t x = visit[bs + t], u = x & VISIT_MASK;
+                const K128 key{uklo[bs + u], ukhi ? ukhi[bs + u] : 0};
+                const uint32_t r = t - (j + 1);
+                if ((x >> 30) == 1) sk[64 - 1 - r] = (uint8_t)(k_shr(key, 2 * k - 2).lo & 3);     // r-th left extension
+                else sk[64 + k + (r - n_l)] = (uint8_t)(key.lo & 3);                                // right extension
+            }
+            __syncwarp();
+            if (len == full) {
+                for (int q = lane; q < 2 * d / 4; q += 32) {
+                    uint32_t acc = 0;
+                    for (int c = 0; c < 4; c++) {
+                        const int i = 4 * q + c;
+                        acc = (acc << 2) | ((i < d) ? sk[lo + i] : sk[lo + k + (i - d)]);
+                    }
+                    p_max[q] = (uint8_t)acc;
+                }
+                p_max += 2 * d / 4;
+            } else {                                                            // :486-494
+                const int q = rc_find_minimizer(sk, lo, len, m, minimizer);
+                if (WRITE) {
+                    if (q < 0) {
+                        for (int t = lane; t < len; t += 32) p_txt[t] = "ACTG"[sk[lo + t]];
+                        if (lane == 0) { p_txt[len] = '\n'; p_txt[len + 1] = '\n'; }
+                        p_txt += len + 2;
+                    } else {
+                        for (int t = lane; t < q; t += 32) p_txt[t] = "ACTG"[sk[lo + t]];
+                        uint8_t *p2 = p_txt + q + 1;
+                        for (int t = q + m + lane; t < len; t += 32) p2[t - q - m] = "ACTG"[sk[lo + t]];
+                        if (lane == 0) { p_txt[q] = '\n'; p2[len - q - m] = '\n'; }
+                        p_txt += (len - m) + 2;
+                    }
+                }
+                text_len += (uint32_t)(q < 0 ? len : len - m) + 2;
+            }
+            j = e;
+        }
+        if (WRITE) {
+            if (lane == 0) { p_txt[0] = '\n'; p_txt[1] = '\n'; }
+        } else if (lane == 0) {
+            const uint32_t sz = n_max ? 1 + n_max * (uint32_t)(2 * d) / 4 : 0;
+            const uint32_t bytes = (uint32_t)m + 4 + sz + text_len + 2;
+            bbytes[b] = bytes;
+            bnmax[b] = n_max;
+            atomicAdd(in_bytes + (uA[bs] >> input_shift), (unsigned long long)bytes);
+        }
+    }
 }
 
 // ------------------------------------------------------ K7 compare elements
@@ -609,9 +843,8 @@ __global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const ui
                                        const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
                                        const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid,
                                        const uint32_t *__restrict__ bstart, int k,
-                                       unsigned abundance, int input_shift, uint64_t bound, uint32_t *__restrict__ eflag,
-                                       unsigned long long *__restrict__ in_elems, uint8_t *__restrict__ seen,
-                                       const Counters *cnt)
+                                       unsigned abundance, uint64_t bound, uint32_t *__restrict__ eflag,
+                                       uint8_t *__restrict__ seen, const Counters *cnt)
 {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= bound) return;
@@ -623,12 +856,11 @@ __global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const ui
         if (k_lt(rc, key)) {
             // non-canonical orientation: drop it if the canonical one is in the bucket too
             const uint32_t b = bid[u] + bflag[u] - 1;      // bid = exclusive scan of the bucket-head flags
-            BucketView v{uklo, ukhi, ucnt, seen, bstart[b],
-                         (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique, abundance, k};
+            const uint32_t bs = bstart[b], be = (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
+            BucketView v{uklo + bs, ukhi ? ukhi + bs : nullptr, ucnt + bs, seen + bs, be - bs, abundance, k};
             int o = bv_find(v, rc);
-            if (o >= 0 && ucnt[o] >= abundance) keep = false;
+            if (o >= 0 && v.cnt[o] >= abundance) keep = false;
         }
-        if (keep) atomicAdd(in_elems + (uA[u] >> input_shift), 1ULL);
     }
     eflag[u] = keep ? 1u : 0u;
 }
@@ -637,10 +869,14 @@ __global__ void pp_element_write_kernel(const uint64_t *__restrict__ uA, const u
                                         const uint64_t *__restrict__ ukhi, const uint32_t *__restrict__ eflag,
                                         const uint32_t *__restrict__ eoff, int k, int input_shift, uint64_t bound,
                                         uint32_t *__restrict__ el_min, uint64_t *__restrict__ el_klo,
-                                        uint64_t *__restrict__ el_khi, Counters *cnt)
+                                        uint64_t *__restrict__ el_khi, unsigned long long *__restrict__ in_first,
+                                        Counters *cnt)
 {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= bound) return;
+    // unique k-mers are sorted by input: the first one of an input marks where its elements begin
+    if (u < cnt->n_unique && (u == 0 || (uA[u] >> input_shift) != (uA[u - 1] >> input_shift)))
+        in_first[uA[u] >> input_shift] = eoff[u];
     if (u < cnt->n_unique && eflag[u]) {
         K128 key{uklo[u], ukhi ? ukhi[u] : 0};
         const K128 rc = k_rc(key, k);
@@ -735,7 +971,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->in_bytes.ensure(nin * 8)); PP_CK(b->in_sel.ensure(nin * 8)); PP_CK(b->in_elems.ensure(nin * 8));
     PP_CK(cudaMemsetAsync(b->in_bytes.p, 0, nin * 8, st));
     PP_CK(cudaMemsetAsync(b->in_sel.p, 0, nin * 8, st));
-    PP_CK(cudaMemsetAsync(b->in_elems.p, 0, nin * 8, st));
+    PP_CK(cudaMemsetAsync(b->in_elems.p, 0xFF, nin * 8, st));       // first element of each input; ~0 = none
 
     // ---- hits: classify, sort by position, clusters
     PP_CK(b->hkey.ensure(nhb * 8)); PP_CK(b->hval.ensure(nhb * 4)); PP_CK(b->hkey2.ensure(nhb * 8)); PP_CK(b->hval2.ensure(nhb * 4));
@@ -743,11 +979,12 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->cl_first.ensure(nhb * 4)); PP_CK(b->cl_np.ensure(nhb * 4)); PP_CK(b->cl_nk.ensure(nhb * 4));
     PP_CK(b->cl_poff.ensure(nhb * 4)); PP_CK(b->cl_eoff.ensure(nhb * 4));
     if (nh) {
+        const int pos_bits = bits_for(in.n_bases);                   // radix passes only over bits a position can have
         pp_classify_kernel<<<nblk(nh), 256, 0, st>>>(in.d_hits, nh, in.d_rec_begin, in.d_rec_end, in.n_rec, k, m,
-                                                     b->hkey.as<uint64_t>(), b->hval.as<uint32_t>(), cnt);
+                                                     1ULL << pos_bits, b->hkey.as<uint64_t>(), b->hval.as<uint32_t>(), cnt);
         launched++;
         PP_CK(sort_pairs(b, b->hkey.as<uint64_t>(), b->hkey2.as<uint64_t>(), b->hval.as<uint32_t>(), b->hval2.as<uint32_t>(),
-                         nh, 0, 64, st));
+                         nh, 0, pos_bits + 1, st));
         const uint64_t *key = b->hkey2.as<uint64_t>();
         const uint32_t *val = b->hval2.as<uint32_t>();
         pp_cluster_flag_kernel<<<nblk(nh), 256, 0, st>>>(key, val, nh, in.d_rec_begin, in.n_rec, d, b->hrec.as<uint32_t>(),
@@ -763,7 +1000,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
         PP_CK(b->pc_meta.ensure(bound * 4)); PP_CK(b->pc_eoff.ensure(bound * 4));
         pp_replay_kernel<false><<<nblk(nh, 128), 128, 0, st>>>(key, val, b->hhash.as<uint64_t>(), b->hrec.as<uint32_t>(),
             b->cl_first.as<uint32_t>(), in.d_rec_begin, in.d_rec_end, in.d_rec_input, k, m, b->cl_np.as<uint32_t>(),
-            b->cl_nk.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, bound, cnt);
+            b->cl_nk.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, bound, b->in_sel.as<unsigned long long>(), cnt);
         PP_CK(excl_sum(b, b->cl_np.as<uint32_t>(), b->cl_poff.as<uint32_t>(), nh, st));
         PP_CK(excl_sum(b, b->cl_nk.as<uint32_t>(), b->cl_eoff.as<uint32_t>(), nh, st));
         pp_totals_kernel<<<1, 32, 0, st>>>(b->cl_np.as<uint32_t>(), b->cl_nk.as<uint32_t>(), b->cl_poff.as<uint32_t>(),
@@ -771,7 +1008,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
         pp_replay_kernel<true><<<nblk(nh, 128), 128, 0, st>>>(key, val, b->hhash.as<uint64_t>(), b->hrec.as<uint32_t>(),
             b->cl_first.as<uint32_t>(), in.d_rec_begin, in.d_rec_end, in.d_rec_input, k, m, b->cl_np.as<uint32_t>(),
             b->cl_nk.as<uint32_t>(), b->cl_poff.as<uint32_t>(), b->pc_first.as<uint64_t>(), b->pc_nk.as<uint32_t>(),
-            b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), bound, cnt);
+            b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), bound, nullptr, cnt);
         launched += 3;
     } else {
         PP_CK(b->pc_first.ensure(8)); PP_CK(b->pc_nk.ensure(4)); PP_CK(b->pc_min.ensure(4)); PP_CK(b->pc_meta.ensure(4));
@@ -791,8 +1028,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     uint64_t *ekhi = hi128 ? b->ekhi.as<uint64_t>() : nullptr;
     pp_entries_kernel<<<nblk(bound), 256, 0, st>>>(in.d_packed, b->pc_first.as<uint64_t>(), b->pc_nk.as<uint32_t>(),
         b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), b->pc_eoff.as<uint32_t>(), k, m, bound, input_shift,
-        b->eA.as<uint64_t>(), b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(), b->idx0.as<uint32_t>(),
-        b->in_sel.as<unsigned long long>(), cnt);
+        b->eA.as<uint64_t>(), b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(), b->idx0.as<uint32_t>(), cnt);
     launched++;
     // stable LSD sorts: (bucket, key, order) with order = entry index
     uint32_t *idx_cur = b->idx1.as<uint32_t>(), *idx_alt = b->idx2.as<uint32_t>();
@@ -830,34 +1066,46 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     launched += 4;
     // insertion order inside each bucket: stable sort by first order, then by bucket
     PP_CK(sort_pairs(b, b->ukey32.as<uint32_t>(), b->ukey32b.as<uint32_t>(), b->uidx0.as<uint32_t>(), b->uidx1.as<uint32_t>(),
-                     bound, 0, 32, st));
+                     bound, 0, bits_for(bound), st));
     pp_gather_uA_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uidx1.as<uint32_t>(), bound,
                                                      b->skey.as<uint64_t>(), cnt);
     PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->eA.as<uint64_t>(), b->uidx1.as<uint32_t>(), b->uidx2.as<uint32_t>(), bound, 0,
                      a_bits, st));
     launched++;
     const uint32_t *ins = b->uidx2.as<uint32_t>();
-    // ---- reconstruction: sizes, offsets, bytes
+    // ---- reconstruction: walk every bucket's chains once (visit order + byte sizes), offsets; bytes are emitted below
+    const size_t rc_smem = rc_smem_bytes(hi128);
+    {
+        static bool attr_done = false;
+        if (!attr_done) {
+            PP_CK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc_smem_bytes(true)));
+            attr_done = true;
+        }
+    }
+    const unsigned rc_grid = (unsigned)std::min<uint64_t>((bound + RC_WARPS - 1) / RC_WARPS, 148 * 16);
     PP_CK(b->bbytes.ensure(bound * 4)); PP_CK(b->bnmax.ensure(bound * 4)); PP_CK(b->boff.ensure(bound * 8));
+    PP_CK(b->visit.ensure(bound * 4));
     PP_CK(cudaMemsetAsync(b->bbytes.p, 0, bound * 4, st));
-    pp_reconstruct_kernel<false><<<nblk(bound, 64), 64, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
-        b->ucnt.as<uint8_t>(), b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), ins, b->bstart.as<uint32_t>(), k, m, in.abundance,
-        input_shift, b->bbytes.as<uint32_t>(), b->bnmax.as<uint32_t>(), nullptr, nullptr, b->in_bytes.as<unsigned long long>(), cnt);
+    pp_chain_kernel<<<rc_grid, RC_WARPS * 32, rc_smem, st>>>(b->uklo.as<uint64_t>(), ukhi, b->ucnt.as<uint8_t>(),
+        b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), ins, b->bstart.as<uint32_t>(), k, m, in.abundance,
+        b->visit.as<uint32_t>(), cnt);
+    const unsigned em_grid = (unsigned)std::min<uint64_t>((bound + 7) / 8, 148 * 8);
+    pp_emit_kernel<false><<<em_grid, 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->visit.as<uint32_t>(),
+        b->bstart.as<uint32_t>(), k, m, input_shift, b->bbytes.as<uint32_t>(), b->bnmax.as<uint32_t>(), nullptr, nullptr,
+        b->in_bytes.as<unsigned long long>(), cnt);
     PP_CK(excl_sum(b, b->bbytes.as<uint32_t>(), b->boff.as<uint64_t>(), bound, st));
     pp_body_total_kernel<<<1, 32, 0, st>>>(b->boff.as<uint64_t>(), b->bbytes.as<uint32_t>(), cnt);
-    pp_clear_seen_kernel<<<nblk(bound), 256, 0, st>>>(b->seen.as<uint8_t>(), bound);
     launched += 3;
     // ---- compare elements (needs the bucket tables, not the bytes)
     PP_CK(b->eflag.ensure(bound * 4)); PP_CK(b->eoff.ensure(bound * 4));
     PP_CK(b->el_min.ensure(bound * 4)); PP_CK(b->el_klo.ensure(bound * 8)); if (hi128) PP_CK(b->el_khi.ensure(bound * 8));
     pp_element_flag_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->ucnt.as<uint8_t>(),
-        b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), b->bstart.as<uint32_t>(), k, in.abundance, input_shift, bound,
-        b->eflag.as<uint32_t>(),
-        b->in_elems.as<unsigned long long>(), b->seen.as<uint8_t>(), cnt);
+        b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), b->bstart.as<uint32_t>(), k, in.abundance, bound,
+        b->eflag.as<uint32_t>(), b->seen.as<uint8_t>(), cnt);
     PP_CK(excl_sum(b, b->eflag.as<uint32_t>(), b->eoff.as<uint32_t>(), bound, st));
     pp_element_write_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->eflag.as<uint32_t>(),
         b->eoff.as<uint32_t>(), k, input_shift, bound, b->el_min.as<uint32_t>(), b->el_klo.as<uint64_t>(),
-        hi128 ? b->el_khi.as<uint64_t>() : nullptr, cnt);
+        hi128 ? b->el_khi.as<uint64_t>() : nullptr, b->in_elems.as<unsigned long long>(), cnt);
     launched += 2;
     // ---- sizes to the host, then the bytes
     PP_CK(b->h_cnt.ensure(sizeof(Counters))); PP_CK(b->h_in.ensure(nin * 8 * 3)); PP_CK(b->h_off.ensure((nin + 1) * 8 * 2));
@@ -871,17 +1119,19 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     if (hc.n_pieces > bound || hc.n_entries > bound) return cudaErrorUnknown;    // cannot happen: bound is exact
     PP_CK(b->body.ensure(hc.body_bytes ? hc.body_bytes : 1));
     PP_CK(b->h_body.ensure(hc.body_bytes ? hc.body_bytes : 1));
-    pp_reconstruct_kernel<true><<<nblk(bound, 64), 64, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
-        b->ucnt.as<uint8_t>(), b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), ins, b->bstart.as<uint32_t>(), k, m, in.abundance,
-        input_shift, b->bbytes.as<uint32_t>(), b->bnmax.as<uint32_t>(), b->boff.as<uint64_t>(), b->body.as<uint8_t>(),
-        b->in_bytes.as<unsigned long long>(), cnt);
+    pp_emit_kernel<true><<<em_grid, 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->visit.as<uint32_t>(),
+        b->bstart.as<uint32_t>(), k, m, input_shift, b->bbytes.as<uint32_t>(), b->bnmax.as<uint32_t>(), b->boff.as<uint64_t>(),
+        b->body.as<uint8_t>(), nullptr, cnt);
     launched++;
     if (hc.body_bytes) PP_CK(cudaMemcpyAsync(b->h_body.p, b->body.p, hc.body_bytes, cudaMemcpyDeviceToHost, st));
     PP_CK(cudaStreamSynchronize(st));
     uint64_t *off = b->h_off.as<uint64_t>();
     uint64_t *eoffh = off + (nin + 1);
-    off[0] = 0; eoffh[0] = 0;
-    for (uint32_t i = 0; i < in.n_inputs; i++) { off[i + 1] = off[i] + h_in[i]; eoffh[i + 1] = eoffh[i] + h_in[2 * nin + i]; }
+    off[0] = 0;
+    for (uint32_t i = 0; i < in.n_inputs; i++) off[i + 1] = off[i] + h_in[i];
+    eoffh[in.n_inputs] = hc.n_elems;
+    for (uint32_t i = in.n_inputs; i-- > 0;)            // an input without unique k-mers owns an empty range
+        eoffh[i] = h_in[2 * nin + i] == ~0ULL ? eoffh[i + 1] : h_in[2 * nin + i];
     out->h_body = b->h_body.as<uint8_t>();
     out->h_body_off = off;
     out->h_selected = reinterpret_cast<const uint64_t *>(h_in + nin);
