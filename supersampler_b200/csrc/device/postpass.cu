@@ -66,7 +66,7 @@ struct PostpassBuffers {
     DBuf cnt, hkey, hval, hkey2, hval2, hhash, hrec, cflag, cid, cl_first, cl_np, cl_nk, cl_poff, cl_eoff;
     DBuf pc_first, pc_nk, pc_min, pc_meta, pc_eoff;
     DBuf eA, eklo, ekhi, epm, idx0, idx1, idx2, skey, skey2, head, uid;
-    DBuf uA, uklo, ukhi, ufirst, upm, ucnt, uhead, bflag, bidm, bstart, ukey32, ukey32b, uidx0, uidx1, uidx2, ins, seen;
+    DBuf uA, uklo, ukhi, ufirst, upm, ucnt, uhead, bflag, bidm, bstart, uidx0, uidx2, ins, seen;
     DBuf visit, bbytes, bnmax, boff, body, in_bytes, in_sel, in_elems, eflag, eoff, el_min, el_klo, el_khi, cubtmp;
     HBuf h_cnt, h_body, h_in, h_off;
 };
@@ -408,39 +408,33 @@ __global__ void pp_unique_kernel(const uint64_t *__restrict__ sA, const uint32_t
     if (t + 1 == cnt->n_entries) cnt->n_unique = uid[t] + head[t];
 }
 
-// count (mod 256, SubSampler.h:24) + bucket heads + keys for the insertion-order sort
-__global__ void pp_unique_finish_kernel(const uint64_t *__restrict__ uA, const uint32_t *__restrict__ uhead,
-                                        const uint32_t *__restrict__ ufirst, uint64_t bound, uint8_t *__restrict__ ucnt,
-                                        uint32_t *__restrict__ bflag, uint32_t *__restrict__ ukey32,
+// count (mod 256, SubSampler.h:24) + bucket heads
+__global__ void pp_unique_finish_kernel(const uint64_t *__restrict__ uA, const uint32_t *__restrict__ uhead, uint64_t bound,
+                                        uint8_t *__restrict__ ucnt, uint32_t *__restrict__ bflag,
                                         uint32_t *__restrict__ uidx, uint8_t *__restrict__ seen, const Counters *cnt)
 {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= bound) return;
     uidx[u] = (uint32_t)u;
     seen[u] = 0;
-    if (u >= cnt->n_unique) { bflag[u] = 0; ukey32[u] = (uint32_t)bound; return; }     // padding sorts last
+    if (u >= cnt->n_unique) { bflag[u] = 0; return; }
     const uint64_t next = (u + 1 < cnt->n_unique) ? uhead[u + 1] : cnt->n_entries;
     ucnt[u] = (uint8_t)((next - uhead[u]) & 0xFF);
     bflag[u] = (u == 0 || uA[u] != uA[u - 1]) ? 1u : 0u;
-    ukey32[u] = ufirst[u];
 }
 
-__global__ void pp_bucket_start_kernel(const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid, uint64_t bound,
-                                       uint32_t *__restrict__ bstart, Counters *cnt)
+// bucket starts + the key of the insertion-order sort: (bucket, order of the first occurrence)
+__global__ void pp_bucket_start_kernel(const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid,
+                                       const uint32_t *__restrict__ ufirst, uint64_t bound, int order_bits,
+                                       uint32_t *__restrict__ bstart, uint64_t *__restrict__ okey, Counters *cnt)
 {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= bound || u >= cnt->n_unique) return;
-    if (bflag[u]) bstart[bid[u]] = (uint32_t)u;
+    if (u >= bound) return;
+    if (u >= cnt->n_unique) { okey[u] = ~0ULL; return; }            // padding sorts last
+    const uint32_t b = bid[u] + bflag[u] - 1;                      // bid = exclusive scan of the head flags
+    okey[u] = ((uint64_t)b << order_bits) | ufirst[u];
+    if (bflag[u]) bstart[b] = (uint32_t)u;
     if (u + 1 == cnt->n_unique) cnt->n_buckets = bid[u] + bflag[u];
-}
-
-__global__ void pp_gather_uA_kernel(const uint64_t *__restrict__ uA, const uint32_t *__restrict__ uidx, uint64_t bound,
-                                    uint64_t *__restrict__ dst, const Counters *cnt)
-{
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= bound) return;
-    const uint32_t u = uidx[t];
-    dst[t] = u < cnt->n_unique ? uA[u] : ~0ULL;
 }
 
 // -------------------------------------------------------- K6 reconstruction
@@ -961,7 +955,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     if (bound < 1) bound = 1;
     if (bound >= (1ULL << 31)) return cudaErrorInvalidValue;        // caller falls back to the host post-pass
     const uint64_t nhb = nh ? nh : 1;
-    const int input_shift = 30;                                      // bucket id = input << 30 | minimizer (m <= 15)
+    const int input_shift = 2 * m;                                   // bucket id = input << 2m | minimizer
     const int a_bits = input_shift + bits_for(in.n_inputs ? in.n_inputs - 1 : 0) + 1;   // +1: padding entries sort last
 
     PP_CK(b->cnt.ensure(sizeof(Counters)));
@@ -1049,29 +1043,23 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->uA.ensure(bound * 8)); PP_CK(b->uklo.ensure(bound * 8)); if (hi128) PP_CK(b->ukhi.ensure(bound * 8));
     PP_CK(b->ufirst.ensure(bound * 4)); PP_CK(b->upm.ensure(bound)); PP_CK(b->ucnt.ensure(bound)); PP_CK(b->uhead.ensure(bound * 4));
     PP_CK(b->bflag.ensure(bound * 4)); PP_CK(b->bidm.ensure(bound * 4)); PP_CK(b->bstart.ensure(bound * 4));
-    PP_CK(b->ukey32.ensure(bound * 4)); PP_CK(b->ukey32b.ensure(bound * 4)); PP_CK(b->uidx0.ensure(bound * 4));
-    PP_CK(b->uidx1.ensure(bound * 4)); PP_CK(b->uidx2.ensure(bound * 4)); PP_CK(b->seen.ensure(bound));
+    PP_CK(b->uidx0.ensure(bound * 4)); PP_CK(b->uidx2.ensure(bound * 4)); PP_CK(b->seen.ensure(bound));
     uint64_t *ukhi = hi128 ? b->ukhi.as<uint64_t>() : nullptr;
     pp_head_kernel<<<nblk(bound), 256, 0, st>>>(sA, idx_cur, b->eklo.as<uint64_t>(), ekhi, bound, b->head.as<uint32_t>(), cnt);
     PP_CK(excl_sum(b, b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound, st));
     pp_unique_kernel<<<nblk(bound), 256, 0, st>>>(sA, idx_cur, b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(),
         b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound, b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
         b->ufirst.as<uint32_t>(), b->upm.as<uint8_t>(), b->uhead.as<uint32_t>(), cnt);
-    pp_unique_finish_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uhead.as<uint32_t>(), b->ufirst.as<uint32_t>(),
-        bound, b->ucnt.as<uint8_t>(), b->bflag.as<uint32_t>(), b->ukey32.as<uint32_t>(), b->uidx0.as<uint32_t>(),
-        b->seen.as<uint8_t>(), cnt);
+    pp_unique_finish_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uhead.as<uint32_t>(), bound,
+        b->ucnt.as<uint8_t>(), b->bflag.as<uint32_t>(), b->uidx0.as<uint32_t>(), b->seen.as<uint8_t>(), cnt);
     PP_CK(excl_sum(b, b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), bound, st));
-    pp_bucket_start_kernel<<<nblk(bound), 256, 0, st>>>(b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), bound,
-                                                        b->bstart.as<uint32_t>(), cnt);
+    const int order_bits = bits_for(bound);
+    pp_bucket_start_kernel<<<nblk(bound), 256, 0, st>>>(b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), b->ufirst.as<uint32_t>(),
+        bound, order_bits, b->bstart.as<uint32_t>(), b->skey.as<uint64_t>(), cnt);
     launched += 4;
-    // insertion order inside each bucket: stable sort by first order, then by bucket
-    PP_CK(sort_pairs(b, b->ukey32.as<uint32_t>(), b->ukey32b.as<uint32_t>(), b->uidx0.as<uint32_t>(), b->uidx1.as<uint32_t>(),
-                     bound, 0, bits_for(bound), st));
-    pp_gather_uA_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uidx1.as<uint32_t>(), bound,
-                                                     b->skey.as<uint64_t>(), cnt);
-    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->eA.as<uint64_t>(), b->uidx1.as<uint32_t>(), b->uidx2.as<uint32_t>(), bound, 0,
-                     a_bits, st));
-    launched++;
+    // insertion order inside each bucket: one sort by (bucket, first order); +1 bit so that the padding sorts last
+    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->eA.as<uint64_t>(), b->uidx0.as<uint32_t>(), b->uidx2.as<uint32_t>(), bound, 0,
+                     std::min(64, 2 * order_bits + 1), st));
     const uint32_t *ins = b->uidx2.as<uint32_t>();
     // ---- reconstruction: walk every bucket's chains once (visit order + byte sizes), offsets; bytes are emitted below
     const size_t rc_smem = rc_smem_bytes(hi128);

@@ -110,13 +110,28 @@ static inline void append16(uint32_t *w, uint64_t &widx, uint32_t &acc, int pb, 
     acc = v & ((1u << pb) - 1u);
 }
 
-// One run of sequence bytes without '\n' (part of a FASTA line): valid bases are
-// appended, everything else is deleted (clean_dna, utils.cpp:675-702).  32 bytes
-// per step with AVX2: validity by a nibble LUT, codes (c>>1)&3 packed 4 per byte
-// by two multiply-adds; a block holding any other byte takes the scalar path.
-static inline void pack_run(const uint8_t *p, const uint8_t *end, uint32_t *w, uint64_t &widx, uint32_t &acc,
-                            int &fill, uint64_t &nb)
+// Append `nbits` (< 64, even) packed bases held in the low bits of `bits` behind the pending ones.
+static inline void append_bits(uint32_t *w, uint64_t &widx, uint32_t &acc, int &fill, uint64_t bits, int nbits)
 {
+    unsigned __int128 x = ((unsigned __int128)acc << nbits) | bits;
+    int total = 2 * fill + nbits;
+    while (total >= 32) {
+        w[widx++] = (uint32_t)(x >> (total - 32));
+        total -= 32;
+    }
+    acc = (uint32_t)x & (uint32_t)((1ull << total) - 1);
+    fill = total / 2;
+}
+
+// Sequence bytes of a FASTA record from p: valid bases are appended, '\n' ends the
+// line (returns the position behind it, *eol = true), every other byte is deleted
+// (clean_dna, utils.cpp:675-702).  32 bytes per step with AVX2: validity by a
+// nibble LUT, codes (c>>1)&3 packed 4 per byte by two multiply-adds; a block that
+// holds another byte contributes its leading valid bases and restarts behind it.
+static inline const uint8_t *pack_seq(const uint8_t *p, const uint8_t *end, uint32_t *w, uint64_t &widx, uint32_t &acc,
+                                      int &fill, uint64_t &nb, bool *eol)
+{
+    *eol = false;
 #if defined(__AVX2__)
     const __m256i lut = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
                                          -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
@@ -127,51 +142,47 @@ static inline void pack_run(const uint8_t *p, const uint8_t *end, uint32_t *w, u
     while (end - p >= 32) {
         const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
         const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), _mm256_and_si256(c, up));
-        if (_mm256_movemask_epi8(ok) != -1) {
-            for (int i = 0; i < 32; i++) {
-                const uint8_t code = kLut.v[p[i]];
-                if (code < 4) {
-                    acc = (acc << 2) | code;
-                    nb++;
-                    if (++fill == 16) { w[widx++] = acc; acc = 0; fill = 0; }
-                }
-            }
-            p += 32;
-            continue;
-        }
+        const uint32_t okm = (uint32_t)_mm256_movemask_epi8(ok);
         const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(c, 1), three);
         const __m256i b4 = _mm256_madd_epi16(_mm256_maddubs_epi16(codes, w41), w161);   // one byte per 4 bases
         const __m256i pk = _mm256_shuffle_epi8(b4, pick);
         const uint32_t v0 = (uint32_t)_mm256_extract_epi32(pk, 0), v1 = (uint32_t)_mm256_extract_epi32(pk, 4);
-        const int pb = 2 * fill;
-        append16(w, widx, acc, pb, v0);
-        append16(w, widx, acc, pb, v1);
-        nb += 32;
-        p += 32;
-    }
-    if (end - p >= 16) {
-        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
-        const __m128i ok = _mm_cmpeq_epi8(_mm_shuffle_epi8(_mm256_castsi256_si128(lut), c),
-                                          _mm_and_si128(c, _mm256_castsi256_si128(up)));
-        if (_mm_movemask_epi8(ok) == 0xFFFF) {
-            const __m128i codes = _mm_and_si128(_mm_srli_epi16(c, 1), _mm256_castsi256_si128(three));
-            const __m128i b4 = _mm_madd_epi16(_mm_maddubs_epi16(codes, _mm256_castsi256_si128(w41)),
-                                              _mm256_castsi256_si128(w161));
-            const uint32_t v = (uint32_t)_mm_cvtsi128_si32(_mm_shuffle_epi8(b4, _mm256_castsi256_si128(pick)));
-            append16(w, widx, acc, 2 * fill, v);
-            nb += 16;
-            p += 16;
+        if (okm == 0xFFFFFFFFu) {
+            const int pb = 2 * fill;
+            const uint64_t x0 = ((uint64_t)acc << 32) | v0;
+            w[widx] = (uint32_t)(x0 >> pb);
+            const uint64_t x1 = ((uint64_t)(v0 & ((1u << pb) - 1u)) << 32) | v1;
+            w[widx + 1] = (uint32_t)(x1 >> pb);
+            widx += 2;
+            acc = v1 & ((1u << pb) - 1u);
+            nb += 32;
+            p += 32;
+            continue;
         }
+        const unsigned n = (unsigned)__builtin_ctz(~okm);            // leading valid bases, < 32
+        if (n) {
+            const uint64_t v = ((uint64_t)v0 << 32) | v1;
+            append_bits(w, widx, acc, fill, v >> (64 - 2 * n), 2 * (int)n);
+            nb += n;
+        }
+        p += n;
+        if (*p == '\n') { *eol = true; return p + 1; }
+        p++;                                                         // a deleted byte
     }
 #endif
     for (; p < end; p++) {
-        const uint8_t code = kLut.v[*p];
+        const uint8_t c = *p;
+        const uint8_t code = kLut.v[c];
         if (code < 4) {
             acc = (acc << 2) | code;
             nb++;
             if (++fill == 16) { w[widx++] = acc; acc = 0; fill = 0; }
+        } else if (c == '\n') {
+            *eol = true;
+            return p + 1;
         }
     }
+    return end;
 }
 
 void FastaPacker::feed(const uint8_t *p, size_t n)
@@ -186,11 +197,13 @@ void FastaPacker::feed(const uint8_t *p, size_t n)
     uint64_t widx = word_idx_, nb = out_.n_bases;
     while (p < end) {
         if (state_ == SEQ) {
-            // bases up to the end of the line (or of this chunk)
-            const uint8_t *nl = static_cast<const uint8_t *>(memchr(p, '\n', (size_t)(end - p)));
-            const uint8_t *stop = nl ? nl : end;
-            pack_run(p, stop, w, widx, acc, fill, nb);
-            if (nl) { state_ = LINE_START; p = nl + 1; } else { p = end; }
+            bool eol;
+            p = pack_seq(p, end, w, widx, acc, fill, nb, &eol);
+            if (eol) {
+                // next line of the same record unless it starts a new one
+                if (p < end && *p != '>') continue;
+                state_ = LINE_START;
+            }
         } else if (state_ == HEADER) {
             const void *nl = memchr(p, '\n', (size_t)(end - p));
             if (!nl) { p = end; break; }
