@@ -4,10 +4,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
-#if defined(__AVX2__)
+#if defined(__x86_64__)
 #include <immintrin.h>
 #endif
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -80,13 +81,6 @@ FastaPacker::FastaPacker(PackedInput &out, uint32_t min_len) : out_(out), min_le
     out_.words.reserve(spsp_packed_words(0));
 }
 
-inline void FastaPacker::flush_word()
-{
-    out_.words.data()[word_idx_++] = acc_;
-    acc_ = 0;
-    fill_ = 0;
-}
-
 void FastaPacker::end_record()
 {
     uint64_t len = out_.n_bases - rec_start_;
@@ -102,107 +96,115 @@ void FastaPacker::end_record()
     ck_acc_ = acc_; ck_fill_ = fill_; ck_word_idx_ = word_idx_;
 }
 
-// Append 16 packed bases (first base in the MSBs of v) behind `pb` pending bits.
-static inline void append16(uint32_t *w, uint64_t &widx, uint32_t &acc, int pb, uint32_t v)
+// While a buffer is being filled its words hold base j of the word at bits
+// 2j..2j+1 ("low first", what PEXT compaction produces); finish() turns every word
+// into the output order (first base in the top bits) in one vectorised sweep.
+static inline void emit64(uint32_t *w, uint64_t &widx, uint64_t acc)
 {
-    const uint64_t x = ((uint64_t)acc << 32) | v;
-    w[widx++] = (uint32_t)(x >> pb);
-    acc = v & ((1u << pb) - 1u);
+    memcpy(w + widx, &acc, 8);
+    widx += 2;
 }
-
-// Append `nbits` (< 64, even) packed bases held in the low bits of `bits` behind the pending ones.
-static inline void append_bits(uint32_t *w, uint64_t &widx, uint32_t &acc, int &fill, uint64_t bits, int nbits)
+// Reverse the 16 two-bit groups of every u32 in w[0, n).
+static void words_to_msb_first(uint32_t *w, uint64_t n)
 {
-    unsigned __int128 x = ((unsigned __int128)acc << nbits) | bits;
-    int total = 2 * fill + nbits;
-    while (total >= 32) {
-        w[widx++] = (uint32_t)(x >> (total - 32));
-        total -= 32;
-    }
-    acc = (uint32_t)x & (uint32_t)((1ull << total) - 1);
-    fill = total / 2;
-}
-
-// Sequence bytes of a FASTA record from p: valid bases are appended, '\n' ends the
-// line (returns the position behind it, *eol = true), every other byte is deleted
-// (clean_dna, utils.cpp:675-702).  32 bytes per step with AVX2: validity by a
-// nibble LUT, codes (c>>1)&3 packed 4 per byte by two multiply-adds; a block that
-// holds another byte contributes its leading valid bases and restarts behind it.
-static inline const uint8_t *pack_seq(const uint8_t *p, const uint8_t *end, uint32_t *w, uint64_t &widx, uint32_t &acc,
-                                      int &fill, uint64_t &nb, bool *eol)
-{
-    *eol = false;
+    uint64_t i = 0;
 #if defined(__AVX2__)
-    const __m256i lut = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
-                                         -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
-    const __m256i up = _mm256_set1_epi8((char)0xDF), three = _mm256_set1_epi8(3);
-    const __m256i w41 = _mm256_set1_epi16(0x0104), w161 = _mm256_set1_epi32(0x00010010);
-    const __m256i pick = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
-                                          12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
-    while (end - p >= 32) {
-        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
-        const __m256i ok = _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), _mm256_and_si256(c, up));
-        const uint32_t okm = (uint32_t)_mm256_movemask_epi8(ok);
-        const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(c, 1), three);
-        const __m256i b4 = _mm256_madd_epi16(_mm256_maddubs_epi16(codes, w41), w161);   // one byte per 4 bases
-        const __m256i pk = _mm256_shuffle_epi8(b4, pick);
-        const uint32_t v0 = (uint32_t)_mm256_extract_epi32(pk, 0), v1 = (uint32_t)_mm256_extract_epi32(pk, 4);
-        if (okm == 0xFFFFFFFFu) {
-            const int pb = 2 * fill;
-            const uint64_t x0 = ((uint64_t)acc << 32) | v0;
-            w[widx] = (uint32_t)(x0 >> pb);
-            const uint64_t x1 = ((uint64_t)(v0 & ((1u << pb) - 1u)) << 32) | v1;
-            w[widx + 1] = (uint32_t)(x1 >> pb);
-            widx += 2;
-            acc = v1 & ((1u << pb) - 1u);
-            nb += 32;
-            p += 32;
-            continue;
-        }
-        const unsigned n = (unsigned)__builtin_ctz(~okm);            // leading valid bases, < 32
-        if (n) {
-            const uint64_t v = ((uint64_t)v0 << 32) | v1;
-            append_bits(w, widx, acc, fill, v >> (64 - 2 * n), 2 * (int)n);
-            nb += n;
-        }
-        p += n;
-        if (*p == '\n') { *eol = true; return p + 1; }
-        p++;                                                         // a deleted byte
+    const __m256i rev4 = _mm256_setr_epi8(0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15,
+                                          0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15);   // nibble ab -> ba (2-bit groups)
+    const __m256i bswap = _mm256_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12,
+                                           3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12);
+    const __m256i lo4 = _mm256_set1_epi8(0x0F);
+    for (; i + 8 <= n; i += 8) {
+        __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(w + i));
+        const __m256i l = _mm256_shuffle_epi8(rev4, _mm256_and_si256(x, lo4));
+        const __m256i h = _mm256_shuffle_epi8(rev4, _mm256_and_si256(_mm256_srli_epi16(x, 4), lo4));
+        x = _mm256_or_si256(_mm256_slli_epi16(l, 4), h);                   // groups reversed inside every byte
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(w + i), _mm256_shuffle_epi8(x, bswap));
     }
 #endif
-    for (; p < end; p++) {
-        const uint8_t c = *p;
-        const uint8_t code = kLut.v[c];
-        if (code < 4) {
-            acc = (acc << 2) | code;
-            nb++;
-            if (++fill == 16) { w[widx++] = acc; acc = 0; fill = 0; }
-        } else if (c == '\n') {
-            *eol = true;
-            return p + 1;
-        }
+    for (; i < n; i++) {
+        uint32_t x = __builtin_bswap32(w[i]);
+        x = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+        x = ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
+        w[i] = x;
     }
-    return end;
+}
+
+// Whole 32-byte blocks of sequence text that hold no '>' (a possible record
+// start, left to the byte-wise state machine): every byte that is not a base --
+// line ends, N, IUPAC codes, CR -- is deleted (clean_dna, utils.cpp:675-702)
+// without a branch: validity by a nibble LUT, codes (c>>1)&3 gathered 4 per byte
+// by two multiply-adds, PEXT squeezes the deleted positions out of the 64-bit
+// code word.  Returns the first byte not consumed.
+static inline const uint8_t *pack_blocks(const uint8_t *p, const uint8_t *end, uint32_t *w, uint64_t &widx, uint64_t &acc,
+                                         int &fill, uint64_t &nb)
+{
+#if defined(__AVX2__) && defined(__BMI2__)
+    const __m256i lut = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
+                                         -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i up = _mm256_set1_epi8((char)0xDF), three = _mm256_set1_epi8(3), gt = _mm256_set1_epi8('>');
+    const __m256i w14 = _mm256_set1_epi16(0x0401), w116 = _mm256_set1_epi32(0x00100001);
+    const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                          0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    while (end - p >= 32) {
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+        if (_mm256_movemask_epi8(_mm256_cmpeq_epi8(c, gt))) break;
+        const uint32_t okm = (uint32_t)_mm256_movemask_epi8(
+            _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), _mm256_and_si256(c, up)));
+        const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(c, 1), three);
+        const __m256i b4 = _mm256_madd_epi16(_mm256_maddubs_epi16(codes, w14), w116);   // byte = c0 + 4 c1 + 16 c2 + 64 c3
+        const __m256i pk = _mm256_shuffle_epi8(b4, pick);
+        const uint64_t all = (uint64_t)(uint32_t)_mm256_extract_epi32(pk, 0) |
+                             ((uint64_t)(uint32_t)_mm256_extract_epi32(pk, 4) << 32);      // code of byte j at bits 2j
+        const uint64_t keep = _pdep_u64(okm, 0x5555555555555555ULL) * 3;                   // 2 mask bits per valid byte
+        const uint64_t v = _pext_u64(all, keep);
+        const int nbits = 2 * __builtin_popcount(okm);
+        acc |= v << fill;                                                                  // fill < 64
+        if (fill + nbits >= 64) {
+            emit64(w, widx, acc);
+            acc = fill ? v >> (64 - fill) : 0;
+            fill -= 64;
+        }
+        fill += nbits;
+        nb += (uint64_t)(nbits >> 1);
+        p += 32;
+    }
+#endif
+    (void)end; (void)w; (void)widx; (void)acc; (void)fill; (void)nb;
+    return p;
 }
 
 void FastaPacker::feed(const uint8_t *p, size_t n)
 {
     if (!n) return;
     any_input_ = true;
-    out_.words.reserve(word_idx_ + n / 16 + 2);       // every byte is at most one base
+    out_.words.reserve(word_idx_ + n / 16 + 4);       // every byte is at most one base
     uint32_t *w = out_.words.data();
-    const uint8_t *end = p + n;
-    uint32_t acc = acc_;
+    const uint8_t *const begin = p, *end = p + n;
+    uint64_t acc = acc_;
     int fill = fill_;
     uint64_t widx = word_idx_, nb = out_.n_bases;
     while (p < end) {
         if (state_ == SEQ) {
-            bool eol;
-            p = pack_seq(p, end, w, widx, acc, fill, nb, &eol);
-            if (eol) {
-                // next line of the same record unless it starts a new one
-                if (p < end && *p != '>') continue;
-                state_ = LINE_START;
+            const uint8_t *q = pack_blocks(p, end, w, widx, acc, fill, nb);
+            if (q != p) {
+                p = q;
+                if (p[-1] == '\n') state_ = LINE_START;          // the blocks ended with a line
+                continue;
+            }
+            // byte-wise to the end of this line (block with a '>' in it, or the tail of the buffer)
+            while (p < end) {
+                const uint8_t c = *p++;
+                const uint8_t code = kLut.v[c];
+                if (code < 4) {
+                    acc |= (uint64_t)code << fill;
+                    fill += 2;
+                    nb++;
+                    if (fill == 64) { emit64(w, widx, acc); acc = 0; fill = 0; }
+                } else if (c == '\n') {
+                    state_ = LINE_START;
+                    break;
+                }
             }
         } else if (state_ == HEADER) {
             const void *nl = memchr(p, '\n', (size_t)(end - p));
@@ -220,18 +222,20 @@ void FastaPacker::feed(const uint8_t *p, size_t n)
             }
         }
     }
+    (void)begin;
     acc_ = acc; fill_ = fill; word_idx_ = widx; out_.n_bases = nb;
 }
 
 void FastaPacker::finish()
 {
     end_record();
-    // left-align the last partial word, then zero padding for the kernels
     uint64_t need = spsp_packed_words(out_.n_bases);
-    out_.words.reserve(need);
+    out_.words.reserve(std::max<uint64_t>(need, word_idx_ + 2));
     uint32_t *w = out_.words.data();
     uint64_t widx = word_idx_;
-    if (fill_) w[widx++] = acc_ << (2 * (16 - fill_));
+    if (fill_) emit64(w, widx, acc_);                 // bits above fill_ are zero: left-aligned after the sweep
+    words_to_msb_first(w, widx);
+    widx = (out_.n_bases + 15) / 16;                  // zero padding for the kernels
     for (; widx < need; widx++) w[widx] = 0;
 }
 

@@ -53,16 +53,18 @@ public:
 
 private:
     void end_record();
-    void flush_word();
     PackedInput &out_;
     uint32_t min_len_;
     enum State { HEADER, LINE_START, SEQ } state_ = HEADER;
-    uint32_t acc_ = 0;
-    int fill_ = 0;                     // bases in acc_
-    uint64_t word_idx_ = 0;            // next word to write
+    // Pending bases not yet written: base j of the run at bits 2j..2j+1 (little-endian
+    // order, what PEXT compaction produces); converted to the output format (first
+    // base in the MSBs of each u32) when 32 bases are complete.
+    uint64_t acc_ = 0;
+    int fill_ = 0;                     // bits in acc_ (< 64, even); bits above are zero
+    uint64_t word_idx_ = 0;            // next u32 word to write (even until finish())
     uint64_t rec_start_ = 0;           // base offset where the current record began
-    // checkpoint of the partial word at rec_start_, to drop short records
-    uint32_t ck_acc_ = 0;
+    // checkpoint of the pending bases at rec_start_, to drop short records
+    uint64_t ck_acc_ = 0;
     int ck_fill_ = 0;
     uint64_t ck_word_idx_ = 0;
     bool any_input_ = false;
