@@ -185,6 +185,30 @@ int spsp_cmp_load_batch(spsp_ctx *ctx, int slot);
 int spsp_batch_elements(spsp_ctx *ctx, int slot, uint32_t *minimizer, uint64_t *kmer_lo, uint64_t *kmer_hi,
                         const uint32_t **d_minimizer, const uint64_t **d_kmer_lo, const uint64_t **d_kmer_hi);
 
+/* ---- dense totals ---------------------------------------------------------
+ * The part of the reference's loop that looks at EVERY k-mer, not only the
+ * selected ones (csrc/device/dense.cu): rolling canonical m-mer hash at every
+ * position, warp-shuffle sliding-window minimum over the k-m+1 m-mers of each
+ * k-mer, and an exact parallel replay of the minimizer state machine's
+ * super-k-mer boundaries (SubSampler.cpp:374-398, :401, :429-431, :441-454).
+ * Per input: total_superkmers = total_superkmer_number of print_stat
+ * (SubSampler.cpp:633-665), selected_kmers = number of k-mers whose minimizer
+ * hashes <= T (must equal the sketch header's third field).  Records as in
+ * spsp_sketch_batch; output arrays have n_inputs entries (either may be NULL);
+ * kernel_ms (may be NULL) = CUDA-event time of the kernels.  Synchronous. */
+int spsp_dense_stats(spsp_ctx *ctx, int slot, const uint32_t *packed, uint64_t n_bases, const uint64_t *rec_begin,
+                     const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                     uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms);
+/* d_packed: caller-owned DEVICE buffer. */
+int spsp_dense_stats_device(spsp_ctx *ctx, int slot, const uint32_t *d_packed, uint64_t n_bases,
+                            const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input,
+                            uint64_t n_rec, uint32_t n_inputs, uint64_t *total_superkmers, uint64_t *selected_kmers,
+                            float *kernel_ms);
+/* On what spsp_batch_upload staged on the slot (the batch just sketched). */
+int spsp_dense_stats_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const uint64_t *rec_begin,
+                            const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                            uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms);
+
 /* Number of kernels this library launched on the context since creation. */
 int spsp_launch_count(spsp_ctx *ctx, uint64_t *n);
 

@@ -91,6 +91,15 @@ def device_lib():
                                         C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
         L.spsp_sketch_batch_device.argtypes = L.spsp_sketch_batch.argtypes
         L.spsp_cmp_load_batch.argtypes = [C.c_void_p, C.c_int]
+        L.spsp_dense_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.spsp_dense_stats_device.argtypes = L.spsp_dense_stats.argtypes
+        L.spsp_dense_stats_staged.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.spsp_batch_reserve.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.spsp_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.spsp_sketch_batch_staged.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
         L.spsp_batch_elements.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         _dev = L
@@ -565,6 +574,29 @@ class DeviceContext:
             info.update(n_hits=int(res.n_hits), n_elems=int(res.n_elems), scan_ms=float(res.scan_ms),
                         post_ms=float(res.post_ms), elem_off=[int(res.elem_off[i]) for i in range(n_inputs + 1)])
         return out
+
+    def dense_stats(self, words, n_bases: int, rec_begin, rec_end, rec_input, n_inputs: int, slot: int = 0,
+                    device_ptr: Optional[int] = None, info: Optional[dict] = None):
+        """Dense totals of a batch -> (total_superkmers[n_inputs], selected_kmers[n_inputs])."""
+        rec_begin = np.ascontiguousarray(rec_begin, np.uint64)
+        rec_end = np.ascontiguousarray(rec_end, np.uint64)
+        rec_input = np.ascontiguousarray(rec_input, np.uint32)
+        tot = np.zeros(max(n_inputs, 1), np.uint64); sel = np.zeros(max(n_inputs, 1), np.uint64)
+        ms = C.c_float()
+        if device_ptr is None:
+            words = np.ascontiguousarray(words, np.uint32)
+            assert words.size >= packed_words(n_bases)
+            rc = self.L.spsp_dense_stats(self.h, slot, words.ctypes.data, n_bases, rec_begin.ctypes.data, rec_end.ctypes.data,
+                                         rec_input.ctypes.data, rec_begin.size, n_inputs, tot.ctypes.data, sel.ctypes.data,
+                                         C.byref(ms))
+        else:
+            rc = self.L.spsp_dense_stats_device(self.h, slot, device_ptr, n_bases, rec_begin.ctypes.data,
+                                                rec_end.ctypes.data, rec_input.ctypes.data, rec_begin.size, n_inputs,
+                                                tot.ctypes.data, sel.ctypes.data, C.byref(ms))
+        _dcheck(rc, "spsp_dense_stats")
+        if info is not None:
+            info.update(dense_ms=float(ms.value))
+        return tot[:n_inputs], sel[:n_inputs]
 
     def batch_elements(self, n_elems: int, slot: int = 0, want_hi: bool = False):
         """Host copy of the last batch's elements: (minimizer u32[], kmer_lo u64[], kmer_hi u64[] | None)."""

@@ -11,6 +11,7 @@
 
 #include "../../../include/spsp.h"
 #include "compare.cuh"
+#include "dense.cuh"
 #include "postpass.cuh"
 #include "scan.cuh"
 
@@ -76,6 +77,7 @@ struct Slot {
     bool timed = false;
     // whole-batch path
     PostpassBuffers *pp = nullptr;
+    DenseBuffers *dn = nullptr;
     DevBuf b_rec_begin, b_rec_end, b_rec_input;
     PostpassOut last_batch{};
     uint32_t last_batch_inputs = 0;
@@ -108,6 +110,8 @@ struct spsp_ctx {
 };
 
 static int ensure_packed(struct Slot &s, uint64_t words);
+static int check_records(const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec,
+                         uint64_t n_bases, uint32_t n_inputs, const char *who);
 
 extern "C" int spsp_abi_version(void) { return SPSP_ABI_VERSION; }
 extern "C" const char *spsp_last_error(void) { return g_err.c_str(); }
@@ -252,6 +256,7 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         if (s.ev1) cudaEventDestroy(s.ev1);
         if (s.ev2) cudaEventDestroy(s.ev2);
         if (s.pp) postpass_buffers_destroy(s.pp);
+        if (s.dn) dense_buffers_destroy(s.dn);
         s.b_rec_begin.release(); s.b_rec_end.release(); s.b_rec_input.release();
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -559,12 +564,7 @@ static int batch_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n
                       unsigned abundance, spsp_batch_result *res)
 {
     if (!res) return fail(-3, "spsp_sketch_batch: null result");
-    if (n_rec && (!rec_begin || !rec_end || !rec_input)) return fail(-3, "spsp_sketch_batch: null record arrays");
-    for (uint64_t r = 0; r < n_rec; r++) {
-        if (rec_begin[r] > rec_end[r] || rec_end[r] > n_bases || rec_input[r] >= n_inputs ||
-            (r && (rec_begin[r] < rec_end[r - 1] || rec_input[r] < rec_input[r - 1])))
-            return fail(-3, "spsp_sketch_batch: records must be ascending, disjoint and inside the buffer");
-    }
+    { int rc_ = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_sketch_batch"); if (rc_) return rc_; }
     cudaStream_t st = s.stream;
     const size_t nr = n_rec ? n_rec : 1;
     CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
@@ -687,6 +687,89 @@ extern "C" int spsp_sketch_batch_staged(spsp_ctx *c, int slot, uint64_t n_bases,
     if (spsp_packed_words(n_bases) > s.d_packed_words) return fail(-3, "spsp_sketch_batch_staged: reserve the buffer first");
     CK(cudaSetDevice(c->device));
     return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+}
+
+// ------------------------------------------------------------ dense totals
+
+static int check_records(const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec,
+                         uint64_t n_bases, uint32_t n_inputs, const char *who)
+{
+    if (n_rec && (!rec_begin || !rec_end || !rec_input)) return fail(-3, std::string(who) + ": null record arrays");
+    for (uint64_t r = 0; r < n_rec; r++) {
+        if (rec_begin[r] > rec_end[r] || rec_end[r] > n_bases || rec_input[r] >= n_inputs ||
+            (r && (rec_begin[r] < rec_end[r - 1] || rec_input[r] < rec_input[r - 1])))
+            return fail(-3, std::string(who) + ": records must be ascending, disjoint and inside the buffer");
+    }
+    return 0;
+}
+
+static int dense_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n_bases, const uint64_t *rec_begin,
+                      const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                      uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms)
+{
+    int rc = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_dense_stats");
+    if (rc) return rc;
+    cudaStream_t st = s.stream;
+    const size_t nr = n_rec ? n_rec : 1;
+    CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
+    if (n_rec) {
+        CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (!s.dn) s.dn = dense_buffers_create();
+    DenseIn in{};
+    in.d_packed = d_packed; in.n_bases = n_bases;
+    in.d_rec_begin = static_cast<const uint64_t *>(s.b_rec_begin.p);
+    in.d_rec_end = static_cast<const uint64_t *>(s.b_rec_end.p);
+    in.d_rec_input = static_cast<const uint32_t *>(s.b_rec_input.p);
+    in.n_rec = n_rec; in.n_inputs = n_inputs; in.k = c->k; in.m = c->m; in.thr = c->thr;
+    uint32_t nl = 0;
+    cudaError_t e = dense_stats_run(s.dn, in, total_superkmers, selected_kmers, kernel_ms, &nl, st);
+    if (e != cudaSuccess) return fail(-1, std::string("dense totals: ") + cudaGetErrorString(e));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->launches += nl;
+    }
+    return 0;
+}
+
+extern "C" int spsp_dense_stats(spsp_ctx *c, int slot, const uint32_t *packed, uint64_t n_bases, const uint64_t *rec_begin,
+                                const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                                uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_dense_stats: bad ctx/slot");
+    if (!packed && n_bases) return fail(-3, "spsp_dense_stats: null input");
+    Slot &s = c->slots[slot];
+    CK(cudaSetDevice(c->device));
+    const uint64_t words = spsp_packed_words(n_bases);
+    { int rc_ = ensure_packed(s, words); if (rc_) return rc_; }
+    CK(cudaMemcpyAsync(s.d_packed, packed, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    return dense_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, total_superkmers,
+                      selected_kmers, kernel_ms);
+}
+
+extern "C" int spsp_dense_stats_device(spsp_ctx *c, int slot, const uint32_t *d_packed, uint64_t n_bases,
+                                       const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input,
+                                       uint64_t n_rec, uint32_t n_inputs, uint64_t *total_superkmers,
+                                       uint64_t *selected_kmers, float *kernel_ms)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_dense_stats_device: bad ctx/slot");
+    CK(cudaSetDevice(c->device));
+    return dense_impl(c, c->slots[slot], d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs,
+                      total_superkmers, selected_kmers, kernel_ms);
+}
+
+extern "C" int spsp_dense_stats_staged(spsp_ctx *c, int slot, uint64_t n_bases, const uint64_t *rec_begin,
+                                       const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
+                                       uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_dense_stats_staged: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (spsp_packed_words(n_bases) > s.d_packed_words) return fail(-3, "spsp_dense_stats_staged: nothing staged on this slot");
+    CK(cudaSetDevice(c->device));
+    return dense_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, total_superkmers,
+                      selected_kmers, kernel_ms);
 }
 
 extern "C" int spsp_cmp_load_batch(spsp_ctx *c, int slot)

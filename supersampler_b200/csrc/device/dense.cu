@@ -1,0 +1,337 @@
+// Dense minimizer machine for sm_100a: the part of the reference's per-base
+// loop (SubSampler.cpp:367-440) that the sparse hit path does not need -- the
+// minimizer of EVERY k-mer -- restated so that it runs in parallel:
+//
+//   rows kernel      rolling canonical m-mer hash at every position (one position
+//                    per lane, 32 per warp row) and the sliding-window minimum of
+//                    the hashes over the previous k-m and k-m+1 positions, by
+//                    log-step warp shuffles (windows of 2^t doubled t times, two
+//                    overlapping power-of-two windows combined).  Two bits per
+//                    position come out: "new minimum" (h[p] < min of the previous
+//                    k-mer's k-m+1 m-mers: the branch SubSampler.cpp:374-388 takes)
+//                    and "selected" (the k-mer ending here has a minimizer hash <= T:
+//                    SURVEY App. A.2 closed form, the FracMinHash 1/s test).
+//   segments kernel  a "new minimum" resets the machine's state to a value that
+//                    depends on that position only (minimizer = the entering m-mer,
+//                    position_min = its position), so the sequence splits into
+//                    independent segments; each is replayed from its reset point:
+//                    only rescans (regular_minimizer_pos, :81-169, with its position
+//                    quirks) can happen inside, and each rescan ends a super-k-mer
+//                    ("dump", :391-398 / :401).  Counting resets + rescans + one per
+//                    record gives total_superkmer_number (:429-431, :452) exactly.
+//
+// Used for print_stat's totals and as an independent check of the hit path: the
+// number of selected k-mers must equal the sketch header's third field.
+#include "dense.cuh"
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace spsp {
+
+struct DBufD {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 1024;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    ~DBufD() { if (p) cudaFree(p); }
+};
+
+struct DenseBuffers {
+    DBufD nm, sel, totals;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~DenseBuffers()
+    {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+DenseBuffers *dense_buffers_create() { return new DenseBuffers(); }
+void dense_buffers_destroy(DenseBuffers *b) { delete b; }
+
+constexpr int DN_ROWS = 128;          // rows (of 32 positions) per warp tile
+constexpr int DN_WARM = 2;            // warm-up rows: windows reach back at most 61 positions
+
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// Value of a row-distributed array `sh` (1..32) positions earlier: from this row or the previous one.
+__device__ __forceinline__ uint64_t shift_down(uint64_t cur, uint64_t prev, int sh, int lane)
+{
+    const int src = (lane - sh) & 31;
+    const uint64_t a = __shfl_sync(0xffffffffu, cur, src);
+    const uint64_t b = __shfl_sync(0xffffffffu, prev, src);
+    return lane >= sh ? a : b;
+}
+
+// Canonical m-mer hash at global position p (positions past the end hash to +inf).
+__device__ __forceinline__ uint64_t mmer_hash_at(const uint32_t *__restrict__ packed, long long p, uint64_t n_pos, int m)
+{
+    if (p < 0 || (uint64_t)p >= n_pos) return ~0ULL;
+    const uint64_t w = (uint64_t)p >> 4;
+    const uint32_t fw = window16(__ldg(packed + w), __ldg(packed + w + 1), (int)(p & 15)) >> (32 - 2 * m);
+    const uint32_t rc = rc_mmer(fw, m);
+    return xxh64_8(min(fw, rc));
+}
+
+__global__ void __launch_bounds__(256)
+dense_rows_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int k, int m, uint64_t thr,
+                  uint32_t *__restrict__ nm_bits, uint32_t *__restrict__ sel_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_pos = n_bases >= (uint64_t)m ? n_bases - m + 1 : 0;
+    const uint64_t n_rows = (n_pos + 31) >> 5;
+    const uint64_t row0 = warp * DN_ROWS;
+    if (row0 >= n_rows) return;
+    const uint64_t row1 = min(row0 + (uint64_t)DN_ROWS, n_rows);
+    const int d = k - m;
+    int T = 0;
+    while ((2 << T) <= d) T++;                               // 2^T <= d < 2^(T+1)
+    const int sA = 1 + d - (1 << T), sB = sA + 1;            // second window of size d / d+1, seen from p-1
+    uint64_t prevA[6];                                       // previous row of every doubling level
+#pragma unroll
+    for (int t = 0; t < 6; t++) prevA[t] = ~0ULL;
+    for (long long row = (long long)row0 - DN_WARM; row < (long long)row1; row++) {
+        const long long p = row * 32 + lane;
+        const uint64_t h = mmer_hash_at(packed, p, n_pos, m);
+        // A_t[i] = min of the 2^t hashes ending at i
+        uint64_t A = h;
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            if (t < T) {
+                const uint64_t old = prevA[t];
+                prevA[t] = A;
+                A = umin64(A, shift_down(A, old, 1 << t, lane));
+            }
+        }
+        const uint64_t oldT = prevA[5];
+        prevA[5] = A;
+        const uint64_t e1 = shift_down(A, oldT, 1, lane);                  // window ending at p-1
+        const uint64_t md = umin64(e1, shift_down(A, oldT, sA, lane));     // min h[p-d .. p-1]
+        const uint64_t mw = umin64(e1, shift_down(A, oldT, sB, lane));     // min h[p-d-1 .. p-1]
+        const unsigned nm = __ballot_sync(0xffffffffu, h < mw);
+        const unsigned sl = __ballot_sync(0xffffffffu, umin64(h, md) <= thr);
+        if (row >= (long long)row0 && lane == 0) { nm_bits[row] = nm; sel_bits[row] = sl; }
+    }
+}
+
+// regular_minimizer_pos (SubSampler.cpp:81-169) on the k-mer that starts at global base `g`:
+// right-most m-mer first, strict '<' on the hash, position quirks kept (:88-93, :149-164).
+__device__ uint64_t dense_rescan(const uint32_t *__restrict__ packed, uint64_t g, int d, int m)
+{
+    uint64_t hbest = 0, pos = 0;
+    uint32_t best = 0;
+    bool rev = false;
+    for (int j = 0; j <= d; j++) {
+        const uint64_t p = g + (uint64_t)(d - j);
+        const uint64_t w = p >> 4;
+        const uint32_t fw = window16(__ldg(packed + w), __ldg(packed + w + 1), (int)(p & 15)) >> (32 - 2 * m);
+        const uint32_t rc = rc_mmer(fw, m);
+        const uint32_t cn = min(fw, rc);
+        const bool lrev = cn != fw;
+        const uint64_t h = xxh64_8(cn);
+        if (j == 0) {
+            best = cn; rev = lrev; hbest = h;
+            pos = lrev ? 0 : (uint64_t)d;
+        } else if (hbest > h) {
+            pos = (uint64_t)(d - j); best = cn; rev = lrev; hbest = h;
+        } else if (cn == best && lrev == rev) {
+            if (rev && pos > (uint64_t)j) pos = (uint64_t)j;
+            if (!rev && pos > (uint64_t)(d - j)) pos = (uint64_t)(d - j);
+        }
+    }
+    return pos;
+}
+
+// Relative position of the next "new minimum" iteration after bit `p_rel` of record [rb, re), or `limit` if none
+// (positions are m-mer starts relative to rb; valid iterations enter m-mers d+1 .. n-m).
+__device__ uint64_t next_flag(const uint32_t *__restrict__ nm_bits, uint64_t rb, uint64_t from_rel, uint64_t last_rel,
+                              uint64_t none)
+{
+    if (from_rel > last_rel) return none;
+    uint64_t g = rb + from_rel;
+    const uint64_t g_last = rb + last_rel;
+    uint64_t w = g >> 5;
+    uint32_t bits = nm_bits[w] & (0xFFFFFFFFu << (g & 31));
+    for (;;) {
+        if (bits) {
+            const uint64_t hit = (w << 5) + (uint64_t)(__ffs(bits) - 1);
+            return hit <= g_last ? hit - rb : none;
+        }
+        w++;
+        if ((w << 5) > g_last) return none;
+        bits = nm_bits[w];
+    }
+}
+
+// Rescans between a state with position_min = pm (relative k-mer index space) and iteration c_end (exclusive).
+__device__ uint32_t replay_rescans(const uint32_t *__restrict__ packed, uint64_t rb, uint64_t pm, uint64_t c_end, int d, int m)
+{
+    uint32_t n = 0;
+    for (uint64_t c = pm + 1; c < c_end; c = pm + 1) {       // iteration c rescans when c-1 >= position_min (:391)
+        pm = c + dense_rescan(packed, rb + c, d, m);          // position_min += i + 1 (:397)
+        n++;
+    }
+    return n;
+}
+
+__device__ __forceinline__ uint64_t first_rec_ending_after(const uint64_t *__restrict__ rec_end, uint64_t n_rec, uint64_t pos)
+{
+    uint64_t lo = 0, hi = n_rec;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (rec_end[mid] <= pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One thread per 32-position row: the segments that start at its "new minimum" bits, and the selected k-mers
+// among its positions.  totals[2*input] += super-k-mer boundaries, totals[2*input+1] += selected k-mers.
+__global__ void __launch_bounds__(256)
+dense_segments_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, const uint32_t *__restrict__ nm_bits,
+                      const uint32_t *__restrict__ sel_bits, const uint64_t *__restrict__ rec_begin,
+                      const uint64_t *__restrict__ rec_end, const uint32_t *__restrict__ rec_input, uint64_t n_rec,
+                      int k, int m, unsigned long long *__restrict__ totals)
+{
+    __shared__ unsigned long long s_acc[2];
+    __shared__ uint32_t s_input;
+    const uint64_t n_pos = n_bases >= (uint64_t)m ? n_bases - m + 1 : 0;
+    const uint64_t n_rows = (n_pos + 31) >> 5;
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = k - m;
+    if (threadIdx.x == 0) { s_acc[0] = 0; s_acc[1] = 0; s_input = 0xFFFFFFFFu; }
+    __syncthreads();
+    uint32_t my_input = 0xFFFFFFFFu;
+    unsigned long long my_bound = 0, my_sel = 0;
+    auto flush = [&](uint32_t input, unsigned long long b, unsigned long long s, bool direct) {
+        if (input == 0xFFFFFFFFu || (b | s) == 0) return;
+        if (direct) {
+            if (b) atomicAdd(totals + 2 * input, b);
+            if (s) atomicAdd(totals + 2 * input + 1, s);
+        } else {
+            if (b) atomicAdd(&s_acc[0], b);
+            if (s) atomicAdd(&s_acc[1], s);
+        }
+    };
+    // the block's common input = input of the first record that overlaps the block's first row
+    if (threadIdx.x == 0 && n_rec) {
+        const uint64_t r0 = first_rec_ending_after(rec_end, n_rec, (uint64_t)blockIdx.x * blockDim.x * 32);
+        if (r0 < n_rec) s_input = rec_input[r0];
+    }
+    __syncthreads();
+    const uint32_t block_input = s_input;
+    if (row < n_rows && n_rec) {
+        const uint64_t g0 = row << 5, g1 = g0 + 31;
+        const uint32_t nmw = nm_bits[row], slw = sel_bits[row];
+        for (uint64_t r = first_rec_ending_after(rec_end, n_rec, g0); r < n_rec && rec_begin[r] <= g1; r++) {
+            const uint64_t rb = rec_begin[r], n = rec_end[r] - rb;
+            if (n < (uint64_t)k) continue;
+            const uint32_t input = rec_input[r];
+            if (input != my_input) { flush(my_input, my_bound, my_sel, my_input != block_input); my_input = input; my_bound = my_sel = 0; }
+            const uint64_t K = n - k + 1;
+            // bits of this row inside [lo_rel, hi_rel] of the record
+            auto mask_range = [&](uint64_t lo_rel, uint64_t hi_rel) -> uint32_t {
+                const uint64_t lo = rb + lo_rel, hi = rb + hi_rel;
+                if (hi < g0 || lo > g1 || hi_rel < lo_rel) return 0u;
+                const uint32_t a = lo > g0 ? (uint32_t)(lo - g0) : 0u, b = hi < g1 ? (uint32_t)(hi - g0) : 31u;
+                return (0xFFFFFFFFu << a) & (0xFFFFFFFFu >> (31 - b));
+            };
+            // selected k-mers: the k-mer that starts at c ends its window at m-mer c + d
+            my_sel += __popc(slw & mask_range((uint64_t)d, n - m));
+            // new-minimum iterations c = 1 .. K-1 enter m-mer c + d
+            uint32_t bits = K > 1 ? (nmw & mask_range((uint64_t)d + 1, n - m)) : 0u;
+            while (bits) {
+                const uint32_t bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint64_t p_rel = g0 + bit - rb;                       // the entering m-mer; position_min = p_rel
+                my_bound++;                                                 // minimizer changed (:401)
+                const uint64_t nx = next_flag(nm_bits, rb, p_rel + 1, n - m, ~0ULL);
+                const uint64_t c_end = nx == ~0ULL ? K : nx - d;
+                my_bound += replay_rescans(packed, rb, p_rel, c_end, d, m);
+            }
+        }
+    }
+    flush(my_input, my_bound, my_sel, my_input != block_input);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_input != 0xFFFFFFFFu) {
+        if (s_acc[0]) atomicAdd(totals + 2 * block_input, s_acc[0]);
+        if (s_acc[1]) atomicAdd(totals + 2 * block_input + 1, s_acc[1]);
+    }
+}
+
+// One thread per record: its first k-mer's rescan (:359-365) and what follows until the first new minimum, plus
+// the record's last super-k-mer (:441-454).
+__global__ void dense_records_kernel(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ nm_bits,
+                                     const uint64_t *__restrict__ rec_begin, const uint64_t *__restrict__ rec_end,
+                                     const uint32_t *__restrict__ rec_input, uint64_t n_rec, int k, int m,
+                                     unsigned long long *__restrict__ totals)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t rb = rec_begin[r], n = rec_end[r] - rb;
+    if (n < (uint64_t)k) return;
+    const int d = k - m;
+    const uint64_t K = n - k + 1;
+    unsigned long long bound = 1;                                           // the tail super-k-mer
+    if (K > 1) {
+        const uint64_t pm = dense_rescan(packed, rb, d, m);                 // position_min of k-mer 0
+        const uint64_t nx = next_flag(nm_bits, rb, (uint64_t)d + 1, n - m, ~0ULL);
+        const uint64_t c_end = nx == ~0ULL ? K : nx - d;
+        bound += replay_rescans(packed, rb, pm, c_end, d, m);
+    }
+    atomicAdd(totals + 2 * rec_input[r], bound);
+}
+
+#define DN_CK(call)                                  \
+    do {                                             \
+        cudaError_t e_ = (call);                     \
+        if (e_ != cudaSuccess) return e_;            \
+    } while (0)
+
+cudaError_t dense_stats_run(DenseBuffers *b, const DenseIn &in, uint64_t *h_total_superkmers,
+                            uint64_t *h_selected_kmers, float *kernel_ms, uint32_t *launched, cudaStream_t st)
+{
+    const uint64_t n_pos = in.n_bases >= (uint64_t)in.m ? in.n_bases - in.m + 1 : 0;
+    const uint64_t n_rows = (n_pos + 31) >> 5;
+    const size_t nin = in.n_inputs ? in.n_inputs : 1;
+    if (!b->ev0) { DN_CK(cudaEventCreate(&b->ev0)); DN_CK(cudaEventCreate(&b->ev1)); }
+    DN_CK(b->nm.ensure((n_rows + 2) * 4)); DN_CK(b->sel.ensure((n_rows + 2) * 4)); DN_CK(b->totals.ensure(nin * 16));
+    DN_CK(cudaMemsetAsync(b->totals.p, 0, nin * 16, st));
+    DN_CK(cudaEventRecord(b->ev0, st));
+    uint32_t nl = 0;
+    if (n_rows && in.n_rec) {
+        const uint64_t warps = (n_rows + DN_ROWS - 1) / DN_ROWS;
+        dense_rows_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(in.d_packed, in.n_bases, in.k, in.m, in.thr,
+                                                                       b->nm.as<uint32_t>(), b->sel.as<uint32_t>());
+        dense_segments_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(in.d_packed, in.n_bases, b->nm.as<uint32_t>(),
+            b->sel.as<uint32_t>(), in.d_rec_begin, in.d_rec_end, in.d_rec_input, in.n_rec, in.k, in.m,
+            b->totals.as<unsigned long long>());
+        dense_records_kernel<<<(unsigned)((in.n_rec + 127) / 128), 128, 0, st>>>(in.d_packed, b->nm.as<uint32_t>(), in.d_rec_begin,
+            in.d_rec_end, in.d_rec_input, in.n_rec, in.k, in.m, b->totals.as<unsigned long long>());
+        nl = 3;
+    }
+    DN_CK(cudaEventRecord(b->ev1, st));
+    std::vector<unsigned long long> h(nin * 2);
+    DN_CK(cudaMemcpyAsync(h.data(), b->totals.p, nin * 16, cudaMemcpyDeviceToHost, st));
+    DN_CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < in.n_inputs; i++) {
+        if (h_total_superkmers) h_total_superkmers[i] = h[2 * i];
+        if (h_selected_kmers) h_selected_kmers[i] = h[2 * i + 1];
+    }
+    if (kernel_ms) DN_CK(cudaEventElapsedTime(kernel_ms, b->ev0, b->ev1));
+    if (launched) *launched = nl;
+    return cudaGetLastError();
+}
+
+}  // namespace spsp

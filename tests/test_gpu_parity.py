@@ -388,3 +388,77 @@ def test_pipeline_k63(oracle):
         assert np.array_equal(sizes, o_sizes)
         assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
         pl.close()
+
+
+# ---------------------------------------------------------------- dense minimizer machine
+
+@pytest.mark.parametrize("k,m,s,inputs", [
+    (31, 11, 1000, ["c1", "nasty", "tiny", "empty", "reads", "multi"]),
+    (31, 11, 10, ["nasty", "multi", "noheader", "fam12_0"]),
+    (21, 9, 5, ["nasty21", "multi", "wrap257"]),
+    (15, 5, 3, ["nasty", "multi"]),
+    (63, 15, 10, ["nasty", "multi", "fam12_2"]),
+    (63, 3, 4, ["nasty", "multi"]),
+    (31, 13, 200, ["nasty", "reads"]),
+    (17, 15, 6, ["nasty", "multi"]),
+    (31, 11, 1, ["nasty", "multi"]),
+])
+def test_dense_machine_matches_oracle(k, m, s, inputs, oracle):
+    """Warp-shuffle sliding-window minimum + parallel replay of the minimizer state machine:
+    total_superkmer_number of every input equals the reference loop's (oracle: literal dense
+    restatement of SubSampler.cpp:352-454), and the number of k-mers whose window minimum is
+    <= T equals the selected k-mer count of the sketch header."""
+    words, nb, rb, re_, ri = _batch(inputs, k)
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+    info = {}
+    tot, sel = ctx.dense_stats(words, nb, rb, re_, ri, len(inputs), info=info)
+    for i, inp in enumerate(inputs):
+        sk, st = oracle.sketch(build_input(inp), k, m, s)
+        assert int(tot[i]) == st["total_superkmers"], (inp, int(tot[i]), st["total_superkmers"])
+        assert int(sel[i]) == st["selected_kmers"], (inp, int(sel[i]), st["selected_kmers"])
+        assert int(sel[i]) == int(sk.split(b"\n", 1)[0].split()[2])
+    ctx.close()
+
+
+def test_dense_machine_full_size_property():
+    """Size-independent cross-check at full genome size: the dense kernel's selected k-mer count
+    (window minimum <= T at every k-mer) equals the header field of the sketch built by the sparse
+    hit path + device post-pass, for every input of a 16 x 5 Mbp batch."""
+    fam = synth.Family(5_000_000, 42)
+    k, m, s = 31, 11, 1000
+    ws, ros = [], []
+    for i in range(16):
+        w, nb, ro = S.pack_fasta(fam.fasta(i), k)
+        ws.append(w); ros.append(ro)
+    words, n_total, rb, re_, ri = S.batch_layout(ws, ros)
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+    sks = ctx.sketch_batch(words, n_total, rb, re_, ri, 16, s)
+    tot, sel = ctx.dense_stats(words, n_total, rb, re_, ri, 16)
+    for i in range(16):
+        assert int(sel[i]) == int(sks[i].split(b"\n", 1)[0].split()[2])
+        # every record has at least one super-k-mer per w+1 k-mers and at most one per k-mer
+        kmers = 5_000_000 - k + 1
+        assert kmers // (k - m + 2) <= int(tot[i]) <= kmers
+    ctx.close()
+
+
+def test_dense_machine_matches_reference_print_stat():
+    """total_superkmer_number / selected k-mers of the dense kernels against the numbers the reference
+    binary printed (tests/golden/stats.json), one single-input batch per golden sketch case."""
+    import json
+    from tests.conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "stats.json")) as f:
+        stats = json.load(f)
+    checked = 0
+    for name, want in sorted(stats.items()):
+        inp, k, m, s, a = SKETCH_CASES[name]
+        if want.get("none_selected"):
+            continue
+        words, nb, rb, re_, ri = _batch([inp], k)
+        ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+        tot, sel = ctx.dense_stats(words, nb, rb, re_, ri, 1)
+        ctx.close()
+        assert int(tot[0]) == want["total_superkmers"], (name, int(tot[0]), want["total_superkmers"])
+        assert int(sel[0]) == want["selected_kmers"], (name, int(sel[0]), want["selected_kmers"])
+        checked += 1
+    assert checked >= 25

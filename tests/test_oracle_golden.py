@@ -88,3 +88,22 @@ def test_closed_form_selection(oracle):
         got = sorted((int(a), int(b)) for a, b in sel)
         assert got == sorted(want)
         assert st["selected_kmers"] == len(want)
+
+
+def test_oracle_stats_match_reference_print_stat(oracle):
+    """The restatement's dense state machine reproduces the totals the reference binary prints
+    (print_stat, SubSampler.cpp:633-665; tests/golden/stats.json from tools/make_golden_stats.py)."""
+    import json
+    with open(os.path.join(GOLDEN_DIR, "stats.json")) as f:
+        stats = json.load(f)
+    checked = 0
+    for name, want in sorted(stats.items()):
+        inp, k, m, s, a = SKETCH_CASES[name]
+        _, st = oracle.sketch(build_input(inp), k, m, s, a)
+        if want.get("none_selected"):
+            assert st["selected_kmers"] == 0
+            continue
+        for key in ("total_kmers", "total_superkmers", "selected_kmers", "selected_superkmers"):
+            assert st[key] == want[key], (name, key, st[key], want[key])
+        checked += 1
+    assert checked >= 25
