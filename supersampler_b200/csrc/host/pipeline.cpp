@@ -77,6 +77,9 @@ void BatchSketcher::run(const std::vector<BatchSource> &src, std::vector<std::ve
     sketches.assign(n, std::vector<uint8_t>());
     ok.assign(n, 1);
     selected.assign(n, 0);
+    total_kmers.assign(n, 0);
+    total_superkmers.assign(n, 0);
+    dense_ms = 0;
     elem_off_.assign(1, 0);
     h_minim_.clear(); h_klo_.clear(); h_khi_.clear();
     elems_on_device_ = false;
@@ -209,6 +212,21 @@ void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<P
     if (spsp_sketch_batch_staged(ctx, 0, n_total, rb.data(), re.data(), ri.data(), rb.size(), (uint32_t)nb, abundance_,
                                  &res) != 0)
         throw_spsp("spsp_sketch_batch_staged");
+    if (dense_stats) {
+        std::vector<uint64_t> tot(nb ? nb : 1), sel(nb ? nb : 1);
+        float ms = 0;
+        if (spsp_dense_stats_staged(ctx, 0, n_total, rb.data(), re.data(), ri.data(), rb.size(), (uint32_t)nb, tot.data(),
+                                    sel.data(), &ms) != 0)
+            throw_spsp("spsp_dense_stats_staged");
+        dense_ms += ms;
+        for (size_t j = 0; j < nb; j++) {
+            const Prepared &p = prep[first + j];
+            total_superkmers[first + j] = tot[j];
+            for (size_t r = 0; r + 1 < p.rec_off.size(); r++) total_kmers[first + j] += p.rec_off[r + 1] - p.rec_off[r] - (uint64_t)k_ + 1;
+            if (sel[j] != res.selected[j])      // two independent device paths must agree on the selected k-mers
+                throw std::runtime_error("dense and sparse sketch paths disagree on the number of selected k-mers");
+        }
+    }
     auto t2 = clk::now();
     stats.device_s += secs(t1, t2);
     stats.scan_ms += res.scan_ms; stats.post_ms += res.post_ms;

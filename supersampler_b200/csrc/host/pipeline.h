@@ -56,6 +56,11 @@ public:
     BatchStats stats;                          // last run()
     uint64_t max_batch_bases = 1ull << 30;     // upper bound of one batch (bases incl. padding)
     std::vector<uint64_t> selected;            // header field 3 of every source, last run()
+    // print_stat totals that need every k-mer (SubSampler.cpp:633-665): filled by run() when dense_stats is
+    // set, by the dense minimizer machine on the batch still staged on the device (spsp_dense_stats_staged).
+    bool dense_stats = false;
+    std::vector<uint64_t> total_kmers, total_superkmers;
+    double dense_ms = 0;
 
 private:
     struct Prepared;

@@ -65,6 +65,19 @@ void Subsampler::sketch_packed(std::vector<uint8_t> &sketch)
     auto t2 = clk::now();
     t_scan = secs(t0, t1);
     t_post = secs(t1, t2);
+    total_superkmers = 0;
+    if (want_dense_stats) {
+        // print_stat's totals over every k-mer: dense minimizer machine on the buffer the scan left on the device
+        std::vector<uint64_t> rb(input_.rec_off.begin(), input_.rec_off.end() - 1), re(input_.rec_off.begin() + 1, input_.rec_off.end());
+        std::vector<uint32_t> ri(rb.size(), 0);
+        uint64_t tot = 0, sel = 0;
+        if (spsp_dense_stats_staged(ctx, slot_, input_.n_bases, rb.data(), re.data(), ri.data(), rb.size(), 1, &tot, &sel,
+                                    nullptr) != 0)
+            throw_spsp("spsp_dense_stats_staged");
+        if (sel != stats.selected_kmers)
+            throw std::runtime_error("dense and sparse sketch paths disagree on the number of selected k-mers");
+        total_superkmers = tot;
+    }
 }
 
 void Subsampler::sketch_buffer(const uint8_t *fasta, size_t n, std::vector<uint8_t> &sketch)
@@ -105,9 +118,8 @@ static std::string with_commas(uint64_t n)
 
 void Subsampler::print_stat()
 {
-    // The reference's totals that need the dense state machine (number of
-    // super-k-mers in the whole input, density) are not computed by the sparse
-    // path; stdout is not part of the parity contract.
+    // Totals over every k-mer (total_superkmer_number) come from the dense minimizer
+    // machine on the GPU (want_dense_stats); everything else from the exact post-pass.
     if (stats.selected_kmers == 0) {
         std::cout << "No kmer selected ***Crickets noise***" << std::endl;
         return;
@@ -120,7 +132,16 @@ void Subsampler::print_stat()
               << " with duplicates" << std::endl;
     std::cout << "This means a practical subsampling rate of " << (double)total_kmers / stats.distinct_kmers
               << " without duplicates" << std::endl;
-    std::cout << "I selected " << with_commas(stats.selected_superkmers) << " superkmers" << std::endl;
+    if (total_superkmers) {
+        std::cout << "I have seen " << with_commas(total_superkmers) << " superkmers and I selected "
+                  << with_commas(stats.selected_superkmers) << " superkmers" << std::endl;
+        std::cout << "This means a practical subsampling rate of " << (double)total_superkmers / stats.selected_superkmers
+                  << " with duplicates" << std::endl;
+        std::cout << "This means a mean superkmer size of " << (double)total_kmers / total_superkmers
+                  << " kmer per superkmer in the input" << std::endl;
+    } else {
+        std::cout << "I selected " << with_commas(stats.selected_superkmers) << " superkmers" << std::endl;
+    }
     std::cout << "After reconstruction and filtering with abundance, I have selected "
               << with_commas(stats.out_superkmers) << " superkmers" << std::endl;
     std::cout << "This means a mean superkmer size of " << (double)stats.selected_kmers / stats.selected_superkmers
@@ -199,6 +220,7 @@ int sub_sampler_main(int argc, char **argv)
         if (!input.empty()) {
             auto session = std::make_shared<DeviceSession>(0, (int)k, (int)m1, thr, 1);
             Subsampler ss(k, m1, s, c, type, abundance, session, 0);
+            ss.want_dense_stats = verbose;
             ss.parse_fasta_test(input, output);
             if (verbose) ss.print_stat();
             return 0;
@@ -235,6 +257,7 @@ int sub_sampler_main(int argc, char **argv)
                 if (mine.empty()) return;
                 auto session = std::make_shared<DeviceSession>((int)g, (int)k, (int)m1, thr, 1);
                 BatchSketcher bs(session, (int)k, (int)m1, s, abundance, (int)per_gpu);
+                bs.dense_stats = verbose;
                 std::vector<BatchSource> src(mine.size());
                 for (size_t j = 0; j < mine.size(); j++) src[j].path = files[mine[j]];
                 std::vector<std::vector<uint8_t>> sk;
@@ -255,15 +278,28 @@ int sub_sampler_main(int argc, char **argv)
                 });
                 if (verbose) {
                     std::lock_guard<std::mutex> lk(cout_mu);
-                    for (size_t j = 0; j < mine.size(); j++)
-                        if (ok[j])
-                            std::cout << files[mine[j]] << ": I selected " << with_commas(bs.selected[j]) << " kmers, sketch of "
-                                      << with_commas(sk[j].size()) << " bytes" << std::endl;
+                    for (size_t j = 0; j < mine.size(); j++) {
+                        if (!ok[j]) continue;
+                        std::cout << files[mine[j]] << ":" << std::endl;
+                        if (bs.selected[j] == 0) {
+                            std::cout << "No kmer selected ***Crickets noise***" << std::endl;
+                            continue;
+                        }
+                        std::cout << "I have seen " << with_commas(bs.total_kmers[j]) << " kmers and I selected "
+                                  << with_commas(bs.selected[j]) << " kmers" << std::endl;
+                        std::cout << "This means a practical subsampling rate of "
+                                  << (double)bs.total_kmers[j] / (double)bs.selected[j] << " with duplicates" << std::endl;
+                        std::cout << "I have seen " << with_commas(bs.total_superkmers[j]) << " superkmers" << std::endl;
+                        std::cout << "This means a mean superkmer size of "
+                                  << (double)bs.total_kmers[j] / (double)bs.total_superkmers[j] << " kmer per superkmer in the input"
+                                  << std::endl;
+                        std::cout << "Sketch of " << with_commas(sk[j].size()) << " bytes" << std::endl;
+                    }
                     const BatchStats &st = bs.stats;
                     std::cout << "GPU " << g << ": " << with_commas(st.bases) << " bases in " << st.batches << " batch(es), "
                               << with_commas(st.hits) << " selected m-mer positions; pack " << st.pack_s * 1e3 << " ms, device "
                               << st.device_s * 1e3 << " ms (scan kernel " << st.scan_ms << " ms, post-pass " << st.post_ms
-                              << " ms)" << std::endl;
+                              << " ms, dense totals " << bs.dense_ms << " ms)" << std::endl;
                 }
             } catch (const std::exception &e) {
                 errors[g] = e.what();

@@ -40,6 +40,8 @@ public:
     SketchStats stats;
     double t_pack = 0, t_scan = 0, t_post = 0, t_write = 0;   // seconds, last input
     int gzip_level = 6;
+    bool want_dense_stats = false;     // also compute print_stat's totals over every k-mer (dense kernels)
+    uint64_t total_superkmers = 0;     // total_superkmer_number of the last input (when want_dense_stats)
 
 private:
     void sketch_packed(std::vector<uint8_t> &sketch);

@@ -462,3 +462,34 @@ def test_dense_machine_matches_reference_print_stat():
         assert int(sel[0]) == want["selected_kmers"], (name, int(sel[0]), want["selected_kmers"])
         checked += 1
     assert checked >= 25
+
+
+def test_cli_print_stat_totals(tmp_path):
+    """sub_sampler -v 1 prints the reference's totals (kmers / superkmers seen) for -i and -f."""
+    import json
+    from tests.conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "stats.json")) as f:
+        stats = json.load(f)
+    exe_s = os.path.join(capi.BIN_DIR, "sub_sampler")
+    name = "multi_k31_m11_s20"
+    inp, k, m, s, a = SKETCH_CASES[name]
+    p = tmp_path / (inp + ".fa")
+    p.write_bytes(build_input(inp))
+    want = stats[name]
+
+    def commas(n):
+        return f"{n:,}"
+    line_k = f"I have seen {commas(want['total_kmers'])} kmers and I selected {commas(want['selected_kmers'])} kmers"
+    r = subprocess.run([exe_s, "-i", str(p), "-k", str(k), "-m", str(m), "-s", str(s)], cwd=tmp_path,
+                       stdin=subprocess.DEVNULL, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert line_k in r.stdout
+    assert (f"I have seen {commas(want['total_superkmers'])} superkmers and I selected "
+            f"{commas(want['selected_superkmers'])} superkmers") in r.stdout
+    fof = tmp_path / "in.txt"
+    fof.write_text(str(p) + "\n")
+    r = subprocess.run([exe_s, "-f", str(fof), "-k", str(k), "-m", str(m), "-s", str(s), "-t", "2"], cwd=tmp_path,
+                       stdin=subprocess.DEVNULL, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert line_k in r.stdout
+    assert f"I have seen {commas(want['total_superkmers'])} superkmers" in r.stdout

@@ -24,6 +24,10 @@ def main():
         ctx.sketch_batch(None, n_total, rb, re_, ri, n, s, device_ptr=d.data_ptr(), info=info)
         ctx.cmp_load_batch()
         ctx.cmp_run((0, n), (0, n), True)
+    dinfo = {}
+    tot, sel = ctx.dense_stats(None, n_total, rb, re_, ri, n, device_ptr=d.data_ptr(), info=dinfo)
+    tot, sel = ctx.dense_stats(None, n_total, rb, re_, ri, n, device_ptr=d.data_ptr(), info=dinfo)
+    print("dense_ms", dinfo["dense_ms"], "total_superkmers[0]", int(tot[0]), "selected[0]", int(sel[0]))
     print("scan_ms", info["scan_ms"], "post_ms", info["post_ms"], "hits", info["n_hits"], "elems", info["n_elems"])
 
 if __name__ == "__main__":
