@@ -65,13 +65,12 @@ constexpr int DN_WARM = 2;            // warm-up rows: windows reach back at mos
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
-// Value of a row-distributed array `sh` (1..32) positions earlier: from this row or the previous one.
+// Value of a row-distributed array `sh` (1..32) positions earlier: from this row or the previous one.  The
+// sending lane knows which of the two its receiver wants, so one shuffle moves the right value.
 __device__ __forceinline__ uint64_t shift_down(uint64_t cur, uint64_t prev, int sh, int lane)
 {
-    const int src = (lane - sh) & 31;
-    const uint64_t a = __shfl_sync(0xffffffffu, cur, src);
-    const uint64_t b = __shfl_sync(0xffffffffu, prev, src);
-    return lane >= sh ? a : b;
+    const uint64_t send = lane + sh < 32 ? cur : prev;       // receiver (lane + sh) & 31 is in this row or wrapped
+    return __shfl_sync(0xffffffffu, send, (lane - sh) & 31);
 }
 
 // Canonical m-mer hash at global position p (positions past the end hash to +inf).
@@ -186,6 +185,52 @@ __device__ uint32_t replay_rescans(const uint32_t *__restrict__ packed, uint64_t
     return n;
 }
 
+// regular_minimizer_pos by a whole warp: lane l hashes m-mer j = l (and j = l + 32 when d >= 32) of the k-mer
+// at global base g; warp reductions pick the winner of the right-to-left strict-'<' scan (smallest j among the
+// minimal hashes) and apply the position quirks in closed form: with the winner at j0 in orientation r, start
+// from (j0 == 0 ? (r ? 0 : d) : d - j0) and, over the later m-mers j > j0 with the same canonical value and
+// orientation, forward takes d - max j, reverse takes min(start, min j)  (:88-93, :149-164).
+__device__ __forceinline__ uint64_t warp_rescan(const uint32_t *__restrict__ packed, uint64_t g, int d, int m, int lane)
+{
+    uint64_t h[2] = {~0ULL, ~0ULL};
+    uint32_t cn[2] = {0, 0};
+    bool rv[2] = {false, false};
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int j = lane + 32 * s;
+        if (j <= d && (s == 0 || d >= 32)) {
+            const uint64_t p = g + (uint64_t)(d - j);
+            const uint64_t w = p >> 4;
+            const uint32_t fw = window16(__ldg(packed + w), __ldg(packed + w + 1), (int)(p & 15)) >> (32 - 2 * m);
+            const uint32_t rc = rc_mmer(fw, m);
+            cn[s] = min(fw, rc);
+            rv[s] = cn[s] != fw;
+            h[s] = xxh64_8(cn[s]);
+        }
+    }
+    // minimal hash of the window (two 32-bit reductions)
+    const uint64_t hl = umin64(h[0], h[1]);
+    const uint32_t hi_min = __reduce_min_sync(0xffffffffu, (uint32_t)(hl >> 32));
+    const uint32_t lo_min = __reduce_min_sync(0xffffffffu, (uint32_t)(hl >> 32) == hi_min ? (uint32_t)hl : 0xFFFFFFFFu);
+    const uint64_t hmin = ((uint64_t)hi_min << 32) | lo_min;
+    const unsigned w0 = __ballot_sync(0xffffffffu, h[0] == hmin), w1 = __ballot_sync(0xffffffffu, h[1] == hmin && lane + 32 <= d);
+    const int j0 = w0 ? __ffs(w0) - 1 : 32 + __ffs(w1) - 1;
+    const int src = j0 & 31;
+    const uint32_t best = __shfl_sync(0xffffffffu, j0 < 32 ? cn[0] : cn[1], src);
+    const bool rev = __shfl_sync(0xffffffffu, (int)(j0 < 32 ? rv[0] : rv[1]), src) != 0;
+    const unsigned t0 = __ballot_sync(0xffffffffu, lane > j0 && lane <= d && cn[0] == best && rv[0] == rev);
+    const unsigned t1 = __ballot_sync(0xffffffffu, lane + 32 > j0 && lane + 32 <= d && cn[1] == best && rv[1] == rev);
+    int pos = j0 == 0 ? (rev ? 0 : d) : d - j0;
+    if (!rev) {
+        if (t1) pos = d - (32 + 31 - __clz(t1));
+        else if (t0) pos = d - (31 - __clz(t0));
+    } else {
+        const int jm = t0 ? __ffs(t0) - 1 : (t1 ? 32 + __ffs(t1) - 1 : 0x7fffffff);
+        if (jm < pos) pos = jm;
+    }
+    return (uint64_t)pos;
+}
+
 __device__ __forceinline__ uint64_t first_rec_ending_after(const uint64_t *__restrict__ rec_end, uint64_t n_rec, uint64_t pos)
 {
     uint64_t lo = 0, hi = n_rec;
@@ -196,8 +241,16 @@ __device__ __forceinline__ uint64_t first_rec_ending_after(const uint64_t *__res
     return lo;
 }
 
-// One thread per 32-position row: the segments that start at its "new minimum" bits, and the selected k-mers
-// among its positions.  totals[2*input] += super-k-mer boundaries, totals[2*input+1] += selected k-mers.
+// One thread per 32-position row finds the segments that start at its "new minimum" bits and counts the
+// selected k-mers among its positions; the segments are queued in shared memory and replayed by whole warps
+// (the rescans inside a segment are sequential, each one is a warp-wide reduction).
+// totals[2*input] += super-k-mer boundaries, totals[2*input+1] += selected k-mers.
+constexpr int DS_QCAP = 96;                 // queued segments per warp; a lane adds at most 32 per row
+
+struct DsItem {
+    uint64_t rb, pm, c_end;                 // record start, position_min (relative), first iteration not replayed
+};
+
 __global__ void __launch_bounds__(256)
 dense_segments_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, const uint32_t *__restrict__ nm_bits,
                       const uint32_t *__restrict__ sel_bits, const uint64_t *__restrict__ rec_begin,
@@ -206,63 +259,129 @@ dense_segments_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, con
 {
     __shared__ unsigned long long s_acc[2];
     __shared__ uint32_t s_input;
+    __shared__ DsItem s_q[8][DS_QCAP];
+    __shared__ uint32_t s_qin[8][DS_QCAP];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const uint64_t n_pos = n_bases >= (uint64_t)m ? n_bases - m + 1 : 0;
     const uint64_t n_rows = (n_pos + 31) >> 5;
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int d = k - m;
-    if (threadIdx.x == 0) { s_acc[0] = 0; s_acc[1] = 0; s_input = 0xFFFFFFFFu; }
-    __syncthreads();
-    uint32_t my_input = 0xFFFFFFFFu;
-    unsigned long long my_bound = 0, my_sel = 0;
-    auto flush = [&](uint32_t input, unsigned long long b, unsigned long long s, bool direct) {
-        if (input == 0xFFFFFFFFu || (b | s) == 0) return;
-        if (direct) {
-            if (b) atomicAdd(totals + 2 * input, b);
-            if (s) atomicAdd(totals + 2 * input + 1, s);
-        } else {
-            if (b) atomicAdd(&s_acc[0], b);
-            if (s) atomicAdd(&s_acc[1], s);
+    if (threadIdx.x == 0) {
+        s_acc[0] = 0; s_acc[1] = 0; s_input = 0xFFFFFFFFu;
+        // the block's common input = input of the first record that ends behind the block's first position
+        if (n_rec) {
+            const uint64_t r0 = first_rec_ending_after(rec_end, n_rec, (uint64_t)blockIdx.x * blockDim.x * 32);
+            if (r0 < n_rec) s_input = rec_input[r0];
         }
-    };
-    // the block's common input = input of the first record that overlaps the block's first row
-    if (threadIdx.x == 0 && n_rec) {
-        const uint64_t r0 = first_rec_ending_after(rec_end, n_rec, (uint64_t)blockIdx.x * blockDim.x * 32);
-        if (r0 < n_rec) s_input = rec_input[r0];
     }
     __syncthreads();
     const uint32_t block_input = s_input;
-    if (row < n_rows && n_rec) {
-        const uint64_t g0 = row << 5, g1 = g0 + 31;
-        const uint32_t nmw = nm_bits[row], slw = sel_bits[row];
-        for (uint64_t r = first_rec_ending_after(rec_end, n_rec, g0); r < n_rec && rec_begin[r] <= g1; r++) {
-            const uint64_t rb = rec_begin[r], n = rec_end[r] - rb;
-            if (n < (uint64_t)k) continue;
-            const uint32_t input = rec_input[r];
-            if (input != my_input) { flush(my_input, my_bound, my_sel, my_input != block_input); my_input = input; my_bound = my_sel = 0; }
-            const uint64_t K = n - k + 1;
-            // bits of this row inside [lo_rel, hi_rel] of the record
-            auto mask_range = [&](uint64_t lo_rel, uint64_t hi_rel) -> uint32_t {
-                const uint64_t lo = rb + lo_rel, hi = rb + hi_rel;
-                if (hi < g0 || lo > g1 || hi_rel < lo_rel) return 0u;
-                const uint32_t a = lo > g0 ? (uint32_t)(lo - g0) : 0u, b = hi < g1 ? (uint32_t)(hi - g0) : 31u;
-                return (0xFFFFFFFFu << a) & (0xFFFFFFFFu >> (31 - b));
-            };
-            // selected k-mers: the k-mer that starts at c ends its window at m-mer c + d
-            my_sel += __popc(slw & mask_range((uint64_t)d, n - m));
-            // new-minimum iterations c = 1 .. K-1 enter m-mer c + d
-            uint32_t bits = K > 1 ? (nmw & mask_range((uint64_t)d + 1, n - m)) : 0u;
-            while (bits) {
-                const uint32_t bit = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const uint64_t p_rel = g0 + bit - rb;                       // the entering m-mer; position_min = p_rel
-                my_bound++;                                                 // minimizer changed (:401)
-                const uint64_t nx = next_flag(nm_bits, rb, p_rel + 1, n - m, ~0ULL);
-                const uint64_t c_end = nx == ~0ULL ? K : nx - d;
-                my_bound += replay_rescans(packed, rb, p_rel, c_end, d, m);
+    auto add = [&](uint32_t input, unsigned long long bnd, unsigned long long sel) {
+        if (input == 0xFFFFFFFFu || (bnd | sel) == 0) return;
+        if (input != block_input) {
+            if (bnd) atomicAdd(totals + 2 * input, bnd);
+            if (sel) atomicAdd(totals + 2 * input + 1, sel);
+        } else {
+            if (bnd) atomicAdd(&s_acc[0], bnd);
+            if (sel) atomicAdd(&s_acc[1], sel);
+        }
+    };
+    uint32_t qn = 0;                                             // queued segments of this warp (warp-uniform)
+    // replay every queued segment with the whole warp
+    auto drain = [&]() {
+        __syncwarp();
+        uint32_t cur_in = 0xFFFFFFFFu;
+        unsigned long long cnt = 0;
+        for (uint32_t i = 0; i < qn; i++) {
+            const DsItem it = s_q[wi][i];
+            const uint32_t in_i = s_qin[wi][i];
+            if (in_i != cur_in) { if (lane == 0) add(cur_in, cnt, 0); cur_in = in_i; cnt = 0; }
+            uint64_t pm = it.pm;
+            for (uint64_t c = pm + 1; c < it.c_end; c = pm + 1) {   // iteration c rescans when c-1 >= position_min (:391)
+                pm = c + warp_rescan(packed, it.rb + c, d, m, lane); // position_min += i + 1 (:397)
+                cnt++;                                              // dump: the super-k-mer ends (:401)
             }
         }
+        if (lane == 0) add(cur_in, cnt, 0);
+        __syncwarp();
+        qn = 0;
+    };
+
+    // per-lane state while walking the row
+    uint32_t my_input = 0xFFFFFFFFu;
+    unsigned long long my_bound = 0, my_sel = 0;
+    uint64_t r = 0, r_stop = 0;
+    uint32_t nmw = 0, slw = 0;
+    const uint64_t g0 = row << 5, g1 = g0 + 31;
+    if (row < n_rows && n_rec) {
+        nmw = nm_bits[row]; slw = sel_bits[row];
+        r = first_rec_ending_after(rec_end, n_rec, g0);
+        r_stop = r;
+        while (r_stop < n_rec && rec_begin[r_stop] <= g1) r_stop++;
     }
-    flush(my_input, my_bound, my_sel, my_input != block_input);
+    // the warp walks in rounds: every lane contributes the segments of ONE record overlap per round
+    for (;;) {
+        const bool have = r < r_stop;
+        if (!__any_sync(0xffffffffu, have)) break;
+        uint32_t bits = 0;
+        uint64_t rb = 0, n = 0, K = 0;
+        uint32_t input = 0;
+        if (have) {
+            rb = rec_begin[r]; n = rec_end[r] - rb; input = rec_input[r];
+            if (n >= (uint64_t)k) {
+                K = n - k + 1;
+                auto mask_range = [&](uint64_t lo_rel, uint64_t hi_rel) -> uint32_t {
+                    const uint64_t lo = rb + lo_rel, hi = rb + hi_rel;
+                    if (hi_rel < lo_rel || hi < g0 || lo > g1) return 0u;
+                    const uint32_t a = lo > g0 ? (uint32_t)(lo - g0) : 0u, b = hi < g1 ? (uint32_t)(hi - g0) : 31u;
+                    return (0xFFFFFFFFu << a) & (0xFFFFFFFFu >> (31 - b));
+                };
+                if (input != my_input) { add(my_input, my_bound, my_sel); my_input = input; my_bound = my_sel = 0; }
+                // selected k-mers: the k-mer that starts at c ends its window at m-mer c + d
+                my_sel += __popc(slw & mask_range((uint64_t)d, n - m));
+                // new-minimum iterations c = 1 .. K-1 enter m-mer c + d
+                if (K > 1) bits = nmw & mask_range((uint64_t)d + 1, n - m);
+                my_bound += __popc(bits);                        // the minimizer changes there (:374-388, :401)
+            }
+            r++;
+        }
+        // queue the segments of this round (at most 32 per lane); drain first if they might not fit
+        const uint32_t mine = __popc(bits);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t done_before = 0;                                // items of this round already queued (over all lanes)
+        while (done_before < total) {
+            if (qn == DS_QCAP) drain();
+            const uint32_t room = DS_QCAP - qn;
+            // lanes write the items whose round-index falls into [done_before, done_before + room)
+            uint32_t idx = incl - mine;                          // round-index of my first item
+            uint32_t b2 = bits;
+            while (b2) {
+                const uint32_t bit = __ffs(b2) - 1;
+                b2 &= b2 - 1;
+                if (idx >= done_before && idx < done_before + room) {
+                    const uint64_t p_rel = g0 + bit - rb;        // the entering m-mer; position_min = p_rel
+                    const uint64_t nx = next_flag(nm_bits, rb, p_rel + 1, n - m, ~0ULL);
+                    DsItem it;
+                    it.rb = rb; it.pm = p_rel; it.c_end = nx == ~0ULL ? K : nx - d;
+                    const uint32_t slot = qn + (idx - done_before);
+                    s_q[wi][slot] = it;
+                    s_qin[wi][slot] = input;
+                }
+                idx++;
+            }
+            const uint32_t put = min(room, total - done_before);
+            qn += put;
+            done_before += put;
+        }
+    }
+    drain();
+    add(my_input, my_bound, my_sel);
     __syncthreads();
     if (threadIdx.x == 0 && block_input != 0xFFFFFFFFu) {
         if (s_acc[0]) atomicAdd(totals + 2 * block_input, s_acc[0]);
