@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -45,6 +46,84 @@ void parallel_for(int threads, size_t n, const std::function<void(size_t)> &fn)
     if (!error.empty()) throw std::runtime_error(error);
 }
 
+struct WorkerPool::Impl {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> threads;
+    const std::function<void(size_t)> *fn = nullptr;
+    size_t n = 0;
+    std::atomic<size_t> next{0};
+    uint64_t generation = 0;
+    int active = 0;
+    bool stop = false;
+    std::string error;
+
+    void drain()
+    {
+        try {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                (*fn)(i);
+            }
+        } catch (const std::exception &e) {
+            std::lock_guard<std::mutex> g(mu);
+            if (error.empty()) error = e.what();
+            next.store(n);
+        }
+    }
+    void worker()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            drain();
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if (--active == 0) cv_done.notify_all();
+            }
+        }
+    }
+};
+
+WorkerPool::WorkerPool(int threads) : impl_(new Impl()), n_threads_(threads < 1 ? 1 : threads)
+{
+    for (int t = 1; t < n_threads_; t++) impl_->threads.emplace_back([this] { impl_->worker(); });
+}
+
+WorkerPool::~WorkerPool()
+{
+    {
+        std::lock_guard<std::mutex> g(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv_work.notify_all();
+    for (auto &t : impl_->threads) t.join();
+    delete impl_;
+}
+
+void WorkerPool::run(size_t n, const std::function<void(size_t)> &fn)
+{
+    if (n == 0) return;
+    Impl &p = *impl_;
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        p.fn = &fn; p.n = n; p.next.store(0); p.error.clear();
+        p.active = (int)p.threads.size();
+        p.generation++;
+    }
+    p.cv_work.notify_all();
+    p.drain();
+    std::unique_lock<std::mutex> lk(p.mu);
+    p.cv_done.wait(lk, [&] { return p.active == 0; });
+    if (!p.error.empty()) throw std::runtime_error(p.error);
+}
+
 struct BatchSketcher::Prepared {
     uint64_t len = 0;                  // upper bound of the number of bases (= text bytes)
     bool ok = true, from_file = false;
@@ -55,7 +134,8 @@ struct BatchSketcher::Prepared {
 };
 
 BatchSketcher::BatchSketcher(std::shared_ptr<DeviceSession> session, int k, int m, double s, unsigned abundance, int threads)
-    : session_(std::move(session)), k_(k), m_(m), threads_(threads < 1 ? 1 : threads), s_(s), abundance_(abundance)
+    : session_(std::move(session)), pool_(threads), k_(k), m_(m), threads_(threads < 1 ? 1 : threads), s_(s),
+      abundance_(abundance)
 {
 }
 
@@ -89,7 +169,7 @@ void BatchSketcher::run(const std::vector<BatchSource> &src, std::vector<std::ve
     // ---- prepare: sizes; gzip inputs are inflated here (their size is unknown before)
     auto t0 = clk::now();
     std::vector<Prepared> prep(n);
-    parallel_for(threads_, n, [&](size_t i) {
+    pool_.run(n, [&](size_t i) {
         Prepared &p = prep[i];
         if (src[i].data) { p.len = src[i].len; return; }
         p.from_file = true;
@@ -157,28 +237,41 @@ void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<P
     if (spsp_batch_reserve(ctx, 0, need_words) != 0) throw_spsp("spsp_batch_reserve");
 
     // ---- pack: every worker cleans + packs whole inputs into their regions and queues the copy
-    parallel_for(threads_, nb, [&](size_t j) {
+    pool_.run(nb, [&](size_t j) {
         Prepared &p = prep[first + j];
         const BatchSource &sc = src[first + j];
         PackedInput in(false);
         in.words.attach(stage_ + p.word_off, spsp_packed_words(p.ok ? p.len : 0));
+        uint64_t uploaded = 0;                              // words of this region already queued for the copy
+        auto upload_to = [&](uint64_t words) {
+            if (words <= uploaded) return;
+            if (spsp_batch_upload(ctx, 0, p.word_off + uploaded, stage_ + p.word_off + uploaded, words - uploaded) != 0)
+                throw_spsp("spsp_batch_upload");
+            uploaded = words;
+        };
         {
+            // feed in slices: what is final after a slice goes to the device while the next one is packed
+            const size_t SLICE = 1u << 20;
             FastaPacker pk(in, (uint32_t)k_);
             if (!p.ok) {
             } else if (!p.from_file) {
                 const uint8_t *d = sc.data ? sc.data : p.text.data();
                 const size_t len = sc.data ? sc.len : p.text.size();
-                pk.feed(d, len);
+                for (size_t off = 0; off < len; off += SLICE) {
+                    pk.feed(d + off, std::min(SLICE, len - off));
+                    if (off + SLICE < len) upload_to(pk.commit());
+                }
             } else {
                 int fd = open(sc.path.c_str(), O_RDONLY);
                 if (fd < 0) throw std::runtime_error("cannot reopen " + sc.path);
-                std::vector<uint8_t> buf(1u << 20);
+                std::vector<uint8_t> buf(SLICE);
                 uint64_t got = 0;
                 while (got < p.len) {                        // never more than the size the region was cut for
                     ssize_t r = read(fd, buf.data(), (size_t)std::min<uint64_t>(buf.size(), p.len - got));
                     if (r <= 0) break;
                     pk.feed(buf.data(), (size_t)r);
                     got += (uint64_t)r;
+                    if (got < p.len) upload_to(pk.commit());
                 }
                 close(fd);
             }
@@ -186,8 +279,7 @@ void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<P
         }
         p.n_bases = in.n_bases;
         p.rec_off.swap(in.rec_off);
-        const uint64_t words = spsp_packed_words(p.n_bases);
-        if (spsp_batch_upload(ctx, 0, p.word_off, stage_ + p.word_off, words) != 0) throw_spsp("spsp_batch_upload");
+        upload_to(spsp_packed_words(p.n_bases));
         in.words.detach();
         std::vector<uint8_t>().swap(p.text);
     });

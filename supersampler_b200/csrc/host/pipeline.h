@@ -31,6 +31,23 @@ struct BatchStats {
     uint64_t hits = 0, elems = 0, bases = 0, batches = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
+// Persistent worker threads (the pack phase runs every few milliseconds: no thread start-up per batch).
+class WorkerPool {
+public:
+    explicit WorkerPool(int threads);
+    ~WorkerPool();
+    WorkerPool(const WorkerPool &) = delete;
+    WorkerPool &operator=(const WorkerPool &) = delete;
+    // Runs fn(i) for i in [0, n); the caller takes part; rethrows the first exception.
+    void run(size_t n, const std::function<void(size_t)> &fn);
+    int size() const { return n_threads_; }
+
+private:
+    struct Impl;
+    Impl *impl_;
+    int n_threads_;
+};
+
 class BatchSketcher {
 public:
     // Uses slot 0 of `session` (the compare stage's stream, so the hand-off needs no extra sync).
@@ -67,6 +84,7 @@ private:
     void run_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last,
                    std::vector<std::vector<uint8_t>> &sketches, bool keep_host_elems);
     std::shared_ptr<DeviceSession> session_;
+    WorkerPool pool_;
     int k_, m_, threads_;
     double s_;
     unsigned abundance_;

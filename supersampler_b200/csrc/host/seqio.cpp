@@ -226,6 +226,19 @@ void FastaPacker::feed(const uint8_t *p, size_t n)
     acc_ = acc; fill_ = fill; word_idx_ = widx; out_.n_bases = nb;
 }
 
+uint64_t FastaPacker::commit()
+{
+    // a record shorter than min_len is taken back when it ends (end_record): everything older than the
+    // current record's start is final, and so is everything once the record is long enough to stay
+    uint64_t stable = (out_.n_bases - rec_start_ >= min_len_) ? word_idx_ : ck_word_idx_;
+    stable &= ~(uint64_t)1;                                     // whole 64-bit units
+    if (stable > converted_) {
+        words_to_msb_first(out_.words.data() + converted_, stable - converted_);
+        converted_ = stable;
+    }
+    return converted_;
+}
+
 void FastaPacker::finish()
 {
     end_record();
@@ -234,7 +247,8 @@ void FastaPacker::finish()
     uint32_t *w = out_.words.data();
     uint64_t widx = word_idx_;
     if (fill_) emit64(w, widx, acc_);                 // bits above fill_ are zero: left-aligned after the sweep
-    words_to_msb_first(w, widx);
+    if (widx > converted_) words_to_msb_first(w + converted_, widx - converted_);
+    converted_ = widx;
     widx = (out_.n_bases + 15) / 16;                  // zero padding for the kernels
     for (; widx < need; widx++) w[widx] = 0;
 }

@@ -50,6 +50,9 @@ public:
     FastaPacker(PackedInput &out, uint32_t min_len);
     void feed(const uint8_t *p, size_t n);
     void finish();
+    // Number of leading output words that are final already (in output bit order, never rewritten):
+    // lets a caller copy a long input to the device while the rest is still being packed.
+    uint64_t commit();
 
 private:
     void end_record();
@@ -62,6 +65,7 @@ private:
     uint64_t acc_ = 0;
     int fill_ = 0;                     // bits in acc_ (< 64, even); bits above are zero
     uint64_t word_idx_ = 0;            // next u32 word to write (even until finish())
+    uint64_t converted_ = 0;           // words already swept into output bit order
     uint64_t rec_start_ = 0;           // base offset where the current record began
     // checkpoint of the pending bases at rec_start_, to drop short records
     uint64_t ck_acc_ = 0;
