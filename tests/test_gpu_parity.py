@@ -493,3 +493,54 @@ def test_cli_print_stat_totals(tmp_path):
     assert r.returncode == 0, r.stderr
     assert line_k in r.stdout
     assert f"I have seen {commas(want['total_superkmers'])} superkmers" in r.stdout
+
+
+# ---------------------------------------------------------------- BASELINE config shapes (scaled down)
+
+def test_config5_query_mode_m13_s200(oracle):
+    """C5 shape: N-vs-All query mode at k31 m13 s200 -- 6 queries against 70 references (3 column tiles),
+    sketches from the batch pipeline, compare from the device-resident elements; CSV text at -p 6."""
+    fas = [synth.fasta_bytes([(nm, g)]) for nm, g in synth.genome_family(76, 120_000, seed=21)]
+    k, m, s = 31, 13, 200
+    pl = S.Pipeline(k, m, s, threads=8)
+    sks = pl.sketch(fas)
+    for i in (0, 5, 40, 75):
+        assert sks[i] == oracle.sketch(fas[i], k, m, s)[0]
+    q = 6
+    inter, sizes, full = pl.compare(q)
+    assert full and inter.shape == (q, len(fas))
+    o_inter, o_sizes, _, _ = oracle.compare(sks, q)
+    assert np.array_equal(sizes, o_sizes)
+    # the reference fills pairs that involve a query; row i of the query block
+    sym = o_inter + o_inter.T
+    got = inter.copy()
+    np.fill_diagonal(got[:, :q], 0)
+    assert np.array_equal(got, sym[:q])
+    names = [f"g{i}.gz" for i in range(len(fas))]
+    for jac in (False, True):
+        assert S.format_csv(names, q, inter, full, sizes, jac, 6, 0.0) == oracle.csv(names, q, o_inter, o_sizes, jac, 6, 0.0)
+    pl.close()
+
+
+def test_config4_read_sets(oracle):
+    """C4 shape: 150 bp reads (one record each, both strands), several read sets in one batch: short-record
+    boundaries everywhere, uint8 counts well above 1, dense totals per read set."""
+    g = synth.random_genome(120_000, 77)
+    sets = [synth.reads_fasta_bytes(synth.read_set(8_000, 150, g, 100 + i)) for i in range(4)]
+    sets.append(synth.reads_fasta_bytes(synth.read_set(300, 40, g, 9)))          # reads of k+9 bases
+    k, m, s = 31, 11, 100
+    pl = S.Pipeline(k, m, s, threads=4)
+    sks = pl.sketch(sets)
+    want = [oracle.sketch(x, k, m, s) for x in sets]
+    assert sks == [w[0] for w in want]
+    inter, sizes, _ = pl.compare()
+    o_inter, o_sizes, _, _ = oracle.compare(sks)
+    assert np.array_equal(sizes, o_sizes) and np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    pl.close()
+    ws, ros = zip(*[(lambda r: (r[0], r[2]))(S.pack_fasta(x, k)) for x in sets])
+    words, nb, rb, re_, ri = S.batch_layout(list(ws), list(ros))
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+    tot, sel = ctx.dense_stats(words, nb, rb, re_, ri, len(sets))
+    for i, (_, st) in enumerate(want):
+        assert int(tot[i]) == st["total_superkmers"] and int(sel[i]) == st["selected_kmers"]
+    ctx.close()

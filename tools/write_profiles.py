@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""gpurun_out/ev_* (tools/collect_evidence.sh) -> profiles/ (tracked, judged)."""
+import io, json, os, shutil, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+def run(*a):
+    return subprocess.run(list(a), capture_output=True, text=True).stdout
+
+def main():
+    os.makedirs(P, exist_ok=True)
+    for src, dst in (("ev_bench_n1.json", f"{R}_bench_n1.json"), ("ev_bench_ref.json", f"{R}_bench_reference_arm.json"),
+                     ("ev_launches.csv", f"{R}_bench_launches.csv"), ("ev_pipeline_probe.txt", f"{R}_pipeline_probe.txt"),
+                     ("ev_gpu.txt", f"{R}_box.txt")):
+        if os.path.exists(os.path.join(G, src)):
+            shutil.copy(os.path.join(G, src), os.path.join(P, dst))
+    with open(os.path.join(P, f"{R}_bench_launch_summary.md"), "w") as f:
+        f.write("# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (per-launch times are cold and serialised: compare shares)\n\n")
+        f.write(run(sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(G, "ev_launches.csv")))
+    for rep, name, title in (("ev_prof_scan", "scan_ncu", "scan_filter_kernel, bench workload"),
+                             ("ev_prof_post", "postpass_compare_ncu", "pp_chain_kernel / pp_emit_kernel / hashjoin_kernel, bench workload"),
+                             ("ev_prof_dense", "dense_ncu", "dense_rows_kernel / dense_segments_kernel, bench workload")):
+        path = os.path.join(G, rep + ".ncu-rep")
+        if os.path.exists(path):
+            with open(os.path.join(P, f"{R}_{name}.md"), "w") as f:
+                f.write(f"# ncu --set full --clock-control none: {title}\n\n")
+                f.write(run(sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), path))
+    # traffic of the dominant streaming kernel for bench.py's roofline.traffic
+    path = os.path.join(G, "ev_prof_scan.ncu-rep")
+    if os.path.exists(path):
+        import csv
+        rows = list(csv.reader(io.StringIO(run("ncu", "-i", path, "--page", "raw", "--csv"))))
+        hdr, units = rows[0], rows[1]
+        def val(name, row):
+            i = hdr.index(name); v = float(row[i]); u = units[i].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        rd, wr = val("dram__bytes_read.sum", rows[2]), val("dram__bytes_write.sum", rows[2])
+        with open(os.path.join(P, f"{R}_traffic.json"), "w") as f:
+            json.dump({"kernel": rows[2][hdr.index("Kernel Name")][:60], "workload": "C2 batch: 320012288 bases, k31 m11 s1000",
+                       "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "traffic_bytes_per_launch": int(rd + wr),
+                       "source": f"ncu --set full --clock-control none, profiles/{R}_scan_ncu.md launch 0"}, f, indent=1)
+    for t in ("ev_batch_s1000.txt", "ev_batch_s100.txt"):
+        if os.path.exists(os.path.join(G, t)):
+            shutil.copy(os.path.join(G, t), os.path.join(P, f"{R}_{t[3:]}"))
+    print("profiles/ updated")
+
+if __name__ == "__main__":
+    main()
