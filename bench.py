@@ -243,7 +243,12 @@ def b200_arm(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dist = None
+    saved_stdout = None
     if world > 1:
+        # libraries (NCCL's version banner) write to fd 1: keep stdout clean for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -415,6 +420,9 @@ def b200_arm(args, rank, world, local_rank):
                                           f"({a:.2f} s) + comparator ({b:.2f} s, single-threaded by construction)",
                                 "sketch_gbp_per_s": total_bases / a / 1e9,
                                 "compare_pairs_per_s": pairs / (c if c else b)}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -79,33 +79,49 @@ class _DevArray:
 
 
 def exchange_device_elements(sizes: np.ndarray, d_mn: int, d_lo: int, d_hi: Optional[int], device):
-    """All-gather of element arrays that already live on this rank's GPU (device
-    pointers from spsp_batch_elements): sizes first, then padded payloads, NCCL
-    over NVLink.  Same return value as exchange_elements."""
+    """exchange_tensors on raw device pointers (spsp_batch_elements)."""
+    import torch
+    e = int(np.asarray(sizes).sum())
+    wrap = lambda ptr, ts: torch.as_tensor(_DevArray(ptr, e, ts), device=device) if e else None
+    return exchange_tensors(sizes, wrap(d_mn, "<i4"), wrap(d_lo, "<i8"), wrap(d_hi, "<i8") if d_hi else None,
+                            d_hi is not None and d_hi != 0, device)
+
+
+def exchange_tensors(sizes: np.ndarray, t_mn, t_lo, t_hi, has_hi: bool, device):
+    """All-gather of the element arrays of this rank's sketches (tensors on
+    `device`: int32 minimizers, int64 k-mer words; None when the rank has no
+    element): sizes first, then ONE collective for the payload (klo | khi |
+    minimizer packed into one padded byte buffer per rank) -- NCCL over NVLink on
+    GPUs, gloo in the CPU tests.  Same return value as exchange_elements."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
     t_sizes = torch.from_numpy(np.ascontiguousarray(sizes, np.int64)).to(device)
-    all_sizes = [torch.empty_like(t_sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, t_sizes)
-    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    all_sizes = torch.empty(world * t_sizes.numel(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_sizes, t_sizes)
+    all_sizes = all_sizes.cpu().numpy().reshape(world, -1)
     e_rank = [int(x.sum()) for x in all_sizes]
     e_mine = int(np.asarray(sizes).sum())
-    e_max = max(max(e_rank), 1)
+    e_max = (max(max(e_rank), 1) + 1) & ~1                    # even: the 4-byte section stays 8-byte aligned
+    n64 = 2 if has_hi else 1
+    stride = e_max * (8 * n64 + 4)                            # bytes per rank: [klo][khi][minimizer]
+    buf = torch.zeros(stride, dtype=torch.uint8, device=device)
+    if e_mine:
+        buf[: e_mine * 8].view(torch.int64).copy_(t_lo)
+        if has_hi:
+            buf[e_max * 8: e_max * 8 + e_mine * 8].view(torch.int64).copy_(t_hi)
+        o = e_max * 8 * n64
+        buf[o: o + e_mine * 4].view(torch.int32).copy_(t_mn)
+    out = torch.empty(world * stride, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, buf)
 
-    def gather(ptr, typestr, t_dtype):
-        buf = torch.zeros(e_max, dtype=t_dtype, device=device)
-        if e_mine:
-            buf[:e_mine] = torch.as_tensor(_DevArray(ptr, e_mine, typestr), device=device)
-        out = torch.empty(world * e_max, dtype=t_dtype, device=device)
-        dist.all_gather_into_tensor(out, buf)
-        if all(e == e_max for e in e_rank):
-            return out
-        return torch.cat([out[r * e_max: r * e_max + e_rank[r]] for r in range(world)]).contiguous()
+    def section(byte_off, width, t_dtype):
+        parts = [out[r * stride + byte_off: r * stride + byte_off + e_rank[r] * width].view(t_dtype) for r in range(world)]
+        return torch.cat(parts).contiguous()
 
-    g_mn = gather(d_mn, "<i4", torch.int32)
-    g_lo = gather(d_lo, "<i8", torch.int64)
-    g_hi = gather(d_hi, "<i8", torch.int64) if d_hi else None
+    g_lo = section(0, 8, torch.int64)
+    g_hi = section(e_max * 8, 8, torch.int64) if has_hi else None
+    g_mn = section(e_max * 8 * n64, 4, torch.int32)
     return all_sizes.reshape(-1), g_mn, g_lo, g_hi
 
 

@@ -44,6 +44,10 @@ def main():
         sks.append(cache[nm])
     kk, mm, sizes, mn, lo, hi = D.local_elements(sks)
     all_sizes, d_mn, d_lo, d_hi = D.exchange_elements(sizes, mn, lo, hi, torch.device("cpu"))
+    # the fused single-collective exchange used on the GPUs gives the same arrays
+    t = lambda a, v: torch.from_numpy(a.view(v).copy()) if a.size else None
+    s2, f_mn, f_lo, f_hi = D.exchange_tensors(sizes, t(mn, np.int32), t(lo, np.int64), None, False, torch.device("cpu"))
+    assert np.array_equal(s2, all_sizes) and torch.equal(f_mn, d_mn) and torch.equal(f_lo, d_lo) and f_hi is None
     n = all_sizes.size
     off = np.concatenate([[0], np.cumsum(all_sizes)])
     el = np.zeros(int(off[-1]), dtype=[("m", "<u4"), ("l", "<u8")])
