@@ -27,6 +27,8 @@ void spsph_free(void *p);
  * Comparator.cpp:464-521): same flags, defaults, outputs in the CWD. */
 int spsph_sub_sampler_main(int argc, char **argv);
 int spsph_comparator_main(int argc, char **argv);
+/* [cpu] The reference's sortCSV helper (sort_csv.cpp:26-122): argv = {prog, matrix.csv[.gz], out.csv, names.txt}. */
+int spsph_sort_csv_main(int argc, char **argv);
 
 /* [cpu] compute_threshold (SubSampler.cpp:622-631); s is the float-parsed -s. */
 uint64_t spsph_threshold(int k, int m, double s);

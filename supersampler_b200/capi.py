@@ -117,6 +117,7 @@ def host_lib():
         L.spsph_threshold.argtypes = [C.c_int, C.c_int, C.c_double]
         L.spsph_sub_sampler_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
         L.spsph_comparator_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.spsph_sort_csv_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
         L.spsph_pack_fasta.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.spsph_postpass.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
@@ -475,6 +476,11 @@ def _run_main(fn, argv: Sequence[str]) -> int:
 def run_sub_sampler(args: Sequence[str]) -> int:
     """In-process `sub_sampler <args>` (writes into the CWD like the reference)."""
     return _run_main(host_lib().spsph_sub_sampler_main, ["sub_sampler", *args])
+
+
+def run_sort_csv(args: Sequence[str]) -> int:
+    """[cpu] In-process `sortCSV matrix.csv[.gz] out.csv names.txt`."""
+    return _run_main(host_lib().spsph_sort_csv_main, ["sortCSV", *args])
 
 
 def run_comparator(args: Sequence[str]) -> int:

@@ -33,6 +33,7 @@ extern "C" const char *spsph_last_error(void) { return g_herr.c_str(); }
 extern "C" void spsph_free(void *p) { free(p); }
 extern "C" int spsph_sub_sampler_main(int argc, char **argv) { return sub_sampler_main(argc, argv); }
 extern "C" int spsph_comparator_main(int argc, char **argv) { return comparator_main(argc, argv); }
+extern "C" int spsph_sort_csv_main(int argc, char **argv) { return sort_csv_main(argc, argv); }
 extern "C" uint64_t spsph_threshold(int k, int m, double s) { return compute_threshold(k, m, s); }
 
 extern "C" int spsph_pack_fasta(const uint8_t *fasta, size_t n, uint32_t min_len, uint32_t **words, uint64_t *n_bases,

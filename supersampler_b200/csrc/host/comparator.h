@@ -44,5 +44,6 @@ private:
 };
 
 int comparator_main(int argc, char **argv);          // Comparator.cpp:464-521
+int sort_csv_main(int argc, char **argv);            // sort_csv.cpp:115-122 (host-only helper)
 
 }  // namespace spsp_host

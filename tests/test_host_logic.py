@@ -157,3 +157,20 @@ def test_postpass_batch_one_scan_many_inputs(oracle):
     out = S.postpass_batch(packed, np.array(bo), np.array(nbs), np.concatenate(ro), rec_first, hits, k, m, s, threads=3)
     for i, sk in zip(inputs, out):
         assert sk == oracle.sketch(build_input(i), k, m, s)[0], i
+
+
+def test_sort_csv_matches_reference(tmp_path):
+    """sortCSV mirror (sort_csv.cpp:26-122) against the reference binary's output
+    (tests/golden/fam12_s100.jaccard.sorted.csv, generated with oracle/_ref/sortCSV)."""
+    import gzip
+    jac = open(os.path.join(GOLDEN_DIR, "fam12_s100.jaccard.csv"), "rb").read()
+    want = open(os.path.join(GOLDEN_DIR, "fam12_s100.jaccard.sorted.csv"), "rb").read()
+    order = open(os.path.join(GOLDEN_DIR, "fam12_s100.sort_order.txt"), "rb").read()
+    (tmp_path / "names.txt").write_bytes(order)
+    with gzip.open(tmp_path / "j.csv.gz", "wb") as f:
+        f.write(jac)
+    (tmp_path / "j.csv").write_bytes(jac)
+    for src in ("j.csv.gz", "j.csv"):
+        out = tmp_path / ("sorted_" + src + ".csv")
+        assert S.run_sort_csv([str(tmp_path / src), str(out), str(tmp_path / "names.txt")]) == 0
+        assert out.read_bytes() == want
