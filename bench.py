@@ -284,8 +284,15 @@ def b200_arm(args, rank, world, local_rank):
     stats = {"scan_ms": [], "post_ms": [], "cmp_ms": [], "hits": 0, "launches": 0, "sketch_s": [], "compare_s": [],
              "d2h": 0, "e2e": []}
 
+    if dist is not None:
+        D.join_contexts(dctx, rank, world)
+        D.join_contexts(pctx, rank, world)
+    use_native = os.environ.get("SPSP_BENCH_TORCH_EXCHANGE", "0") != "1"
+
     def compare_device(ctx, elem_off, cinfo):
         """Compare stage from the elements the batch left on `ctx`'s device."""
+        if dist is not None and use_native:
+            return D.native_exchange_compare(ctx, n_in, rank, world, cinfo)
         if dist is None:
             l0 = ctx.launches()
             ctx.cmp_load_batch()
@@ -310,7 +317,7 @@ def b200_arm(args, rank, world, local_rank):
             stats["hits"] = info["n_hits"]
             stats["launches"] += nl + cinfo.get("launches", 0)
             stats["sketch_s"].append(t1 - t0); stats["compare_s"].append(t2 - t1)
-            stats["d2h"] = sum(len(x) for x in sks) + res[0].size * 4
+            stats["d2h"] = sum(len(x) for x in sks) + (res[0].size * 4 if res[0] is not None else 0)
         return sks, res
 
     def e2e_step(i, record):
@@ -321,10 +328,10 @@ def b200_arm(args, rank, world, local_rank):
         else:
             off, on_dev = pipe.elem_off()
             assert on_dev
-            res = D.allgather_compare_device(off, pctx, rank, world, cinfo)
+            res = compare_device(pctx, off, cinfo)
         if record:
             info["cmp_kernel_ms"] = cinfo.get("kernel_ms"); info["launches"] += cinfo.get("launches", 0)
-            info["d2h_bytes"] += res[0].size * 4
+            info["d2h_bytes"] += res[0].size * 4 if res[0] is not None else 0
             stats["e2e"].append(info)
         return sks, res
 
@@ -361,7 +368,15 @@ def b200_arm(args, rank, world, local_rank):
 
     # both paths must produce the same bytes / counts
     assert sks_res == sks_e2e, "device-resident and host-buffer paths disagree"
-    assert np.array_equal(cmp_res[0], cmp_e2e[0]) and np.array_equal(cmp_res[1], cmp_e2e[1])
+    assert np.array_equal(cmp_res[1], cmp_e2e[1])
+    if rank == 0:
+        assert np.array_equal(cmp_res[0], cmp_e2e[0])
+    if dist is not None and use_native:
+        # the exchange inside the C ABI must give what the torch.distributed exchange gives
+        chk = D.allgather_compare_device(pipe.elem_off()[0], pctx, rank, world, {})
+        assert np.array_equal(chk[1], cmp_res[1])
+        if rank == 0:
+            assert np.array_equal(np.triu(chk[0], 1), np.triu(cmp_res[0], 1)), "native and torch exchange disagree"
 
     if rank != 0:
         if dist is not None:

@@ -209,6 +209,27 @@ int spsp_dense_stats_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const uin
                             const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
                             uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms);
 
+/* ---- multi-GPU compare (one process per GPU) --------------------------------
+ * The compare stage's only exchange step, on NCCL over NVLink (libnccl.so.2 is
+ * loaded at run time; single-GPU callers never need it).  Rank 0 creates an id
+ * (spsp_nccl_unique_id, 128 bytes), hands it to every rank by any side channel
+ * (torch.distributed broadcast, MPI, a file), every rank calls spsp_nccl_init.
+ *
+ * spsp_cmp_exchange_batch: all-vs-all compare of the union of the sketches the
+ * last batch left on every rank's device (rank-major order): all-gather of
+ * counts, then of the sizes and element arrays (one NCCL group, in place),
+ * sketch ranges built on the device, the 32x32 tiles dealt round-robin to the
+ * ranks, hash join, sum-reduce of the disjoint tiles to rank 0.  On rank 0
+ * inter_out (row-major, ld >= N, zeroed by the call's semantics: overwritten)
+ * receives the N x N counts (entries i < j valid); every rank receives
+ * sizes_out[N] (|K_i|) and *n_total = N.  cap_sketches = capacity of the output
+ * arrays in sketches (-2 with *n_total set when too small).  Collective: every
+ * rank must call it. */
+int spsp_nccl_unique_id(uint8_t *id128);
+int spsp_nccl_init(spsp_ctx *ctx, const uint8_t *id128, int rank, int world);
+int spsp_cmp_exchange_batch(spsp_ctx *ctx, int slot, uint32_t *inter_out, uint64_t ld, uint64_t *sizes_out,
+                            uint32_t cap_sketches, uint32_t *n_total, float *kernel_ms);
+
 /* Number of kernels this library launched on the context since creation. */
 int spsp_launch_count(spsp_ctx *ctx, uint64_t *n);
 

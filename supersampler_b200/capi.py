@@ -96,6 +96,10 @@ def device_lib():
         L.spsp_dense_stats_device.argtypes = L.spsp_dense_stats.argtypes
         L.spsp_dense_stats_staged.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.spsp_nccl_unique_id.argtypes = [C.c_void_p]
+        L.spsp_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.spsp_cmp_exchange_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.spsp_batch_reserve.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
         L.spsp_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
         L.spsp_sketch_batch_staged.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -617,6 +621,31 @@ class DeviceContext:
         _dcheck(self.L.spsp_batch_elements(self.h, slot, None, None, None, C.byref(a), C.byref(b), C.byref(c)),
                 "spsp_batch_elements")
         return a.value, b.value, c.value
+
+    def nccl_init(self, rank: int, world: int, broadcast):
+        """Join the ranks' contexts into one NCCL communicator.  `broadcast(buf: np.ndarray[128] uint8) ->
+        np.ndarray` must return rank 0's buffer on every rank (any side channel, e.g. torch.distributed)."""
+        buf = np.zeros(128, np.uint8)
+        if rank == 0:
+            _dcheck(self.L.spsp_nccl_unique_id(buf.ctypes.data), "spsp_nccl_unique_id")
+        buf = np.ascontiguousarray(broadcast(buf), np.uint8)
+        _dcheck(self.L.spsp_nccl_init(self.h, buf.ctypes.data, rank, world), "spsp_nccl_init")
+        self._world = world
+
+    def cmp_exchange_batch(self, cap_sketches: int, rank: int, slot: int = 0, info: Optional[dict] = None):
+        """All-vs-all compare of the union of every rank's last batch (collective).
+        -> (inter[N, N] uint32 (complete on rank 0, None elsewhere), sizes[N] uint64)."""
+        inter = np.zeros((cap_sketches, cap_sketches), np.uint32) if rank == 0 else None
+        sizes = np.zeros(cap_sketches, np.uint64)
+        n, ms = C.c_uint32(), C.c_float()
+        l0 = self.launches()
+        _dcheck(self.L.spsp_cmp_exchange_batch(self.h, slot, inter.ctypes.data if inter is not None else None, cap_sketches,
+                                               sizes.ctypes.data, cap_sketches, C.byref(n), C.byref(ms)),
+                "spsp_cmp_exchange_batch")
+        if info is not None:
+            info.update(kernel_ms=float(ms.value), launches=self.launches() - l0)
+        nt = int(n.value)
+        return (inter[:nt, :nt] if inter is not None else None), sizes[:nt]
 
     def cmp_load_batch(self, slot: int = 0):
         _dcheck(self.L.spsp_cmp_load_batch(self.h, slot), "spsp_cmp_load_batch")

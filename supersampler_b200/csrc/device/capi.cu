@@ -1,6 +1,9 @@
 // C ABI of the device layer (include/spsp.h): contexts, slots (streams),
 // buffers and kernel launches.  No algorithmic work happens on the host here
 // and there is no CPU fallback: every entry point needs a CUDA device.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +108,11 @@ struct spsp_ctx {
     PinBuf p_stage, p_out;
     cudaEvent_t cev0 = nullptr, cev1 = nullptr;
     bool cmp_timed = false;
+    // multi-GPU exchange (one process per GPU)
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    DevBuf x_hdr, x_sizes, x_klo, x_khi, x_min, x_begin, x_end, x_compact, x_out;
+    PinBuf xp_hdr, xp_sizes, xp_out;
     uint64_t launches = 0;
     std::mutex mu;
 };
@@ -244,6 +252,8 @@ static void free_cmp(spsp_ctx *c)
     c->n_sketches = 0;
 }
 
+static void nccl_release(spsp_ctx *c);
+
 extern "C" int spsp_destroy(spsp_ctx *c)
 {
     if (!c) return 0;
@@ -261,6 +271,7 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     free_cmp(c);
+    nccl_release(c);
     cudaFree(c->d_table);
     cudaFree(c->d_exact);
     if (c->cev0) cudaEventDestroy(c->cev0);
@@ -421,6 +432,7 @@ static int finish_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *ske
     c->n_chunks = (uint32_t)chunks;
     CK(c->b_chunk_off.ensure((size_t)n_sketches * (chunks + 1) * sizeof(uint64_t)));
     c->cmp.sk_off = static_cast<const uint64_t *>(c->b_sk_off.p);
+    c->cmp.sk_end = nullptr;
     c->cmp.chunk_off = static_cast<uint64_t *>(c->b_chunk_off.p);
     CK(launch_chunk_offsets(c->cmp, n_sketches, c->n_chunks, c->m, st));
     c->launches++;
@@ -798,6 +810,176 @@ extern "C" int spsp_batch_elements(spsp_ctx *c, int slot, uint32_t *minimizer, u
     if (d_minimizer) *d_minimizer = s.last_batch.d_minim;
     if (d_kmer_lo) *d_kmer_lo = s.last_batch.d_klo;
     if (d_kmer_hi) *d_kmer_hi = s.last_batch.d_khi;
+    return 0;
+}
+
+// ------------------------------------------------------- multi-GPU exchange
+//
+// One process per GPU.  NCCL is loaded at run time (dlopen of libnccl.so.2: the copy the process already has,
+// e.g. PyTorch's, or the system one), so single-GPU users never touch it.
+
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.h = h;
+#define SPSP_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+        SPSP_SYM(GetUniqueId, "ncclGetUniqueId"); SPSP_SYM(CommInitRank, "ncclCommInitRank");
+        SPSP_SYM(CommDestroy, "ncclCommDestroy"); SPSP_SYM(AllGather, "ncclAllGather"); SPSP_SYM(Reduce, "ncclReduce");
+        SPSP_SYM(GroupStart, "ncclGroupStart"); SPSP_SYM(GroupEnd, "ncclGroupEnd"); SPSP_SYM(GetErrorString, "ncclGetErrorString");
+#undef SPSP_SYM
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Reduce || !api.GroupStart ||
+            !api.GroupEnd || !api.GetErrorString)
+            api.h = nullptr;
+    });
+    return api.h ? &api : nullptr;
+}
+}  // namespace
+
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) return fail(-1, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
+    } while (0)
+
+static void nccl_release(spsp_ctx *c)
+{
+    if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    c->comm = nullptr;
+    c->x_hdr.release(); c->x_sizes.release(); c->x_klo.release(); c->x_khi.release(); c->x_min.release();
+    c->x_begin.release(); c->x_end.release(); c->x_compact.release(); c->x_out.release();
+    c->xp_hdr.release(); c->xp_sizes.release(); c->xp_out.release();
+}
+
+extern "C" int spsp_nccl_unique_id(uint8_t *id128)
+{
+    if (!id128) return fail(-3, "spsp_nccl_unique_id: null buffer");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(-1, "spsp_nccl_unique_id: libnccl.so.2 not found");
+    ncclUniqueId id;
+    NK(n->GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int spsp_nccl_init(spsp_ctx *c, const uint8_t *id128, int rank, int world)
+{
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(-3, "spsp_nccl_init: bad args");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(-1, "spsp_nccl_init: libnccl.so.2 not found");
+    CK(cudaSetDevice(c->device));
+    if (c->comm) { n->CommDestroy(c->comm); c->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NK(n->CommInitRank(&c->comm, world, id, rank));
+    c->rank = rank; c->world = world;
+    return 0;
+}
+
+extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_out, uint64_t ld, uint64_t *sizes_out,
+                                       uint32_t cap_sketches, uint32_t *n_total, float *kernel_ms)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !n_total) return fail(-3, "spsp_cmp_exchange_batch: bad args");
+    NcclApi *n = nccl_api();
+    if (!n || !c->comm) return fail(-3, "spsp_cmp_exchange_batch: call spsp_nccl_init first");
+    Slot &s = c->slots[slot];
+    if (!s.has_batch) return fail(-3, "spsp_cmp_exchange_batch: no batch on this slot");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->slots[0].stream;
+    if (slot != 0) CK(cudaStreamSynchronize(s.stream));
+    const uint32_t W = (uint32_t)c->world, R = (uint32_t)c->rank;
+    const bool hi = c->k > 32;
+    const uint64_t n_local = s.last_batch_inputs, e_local = s.last_batch.n_elems;
+    // ---- stage A: how many sketches / elements every rank brings
+    CK(c->x_hdr.ensure(2 * W * 8)); CK(c->xp_hdr.ensure(2 * W * 8));
+    uint64_t *h_hdr = static_cast<uint64_t *>(c->xp_hdr.p);
+    uint64_t *d_hdr = static_cast<uint64_t *>(c->x_hdr.p);
+    h_hdr[2 * R] = n_local; h_hdr[2 * R + 1] = e_local;
+    CK(cudaMemcpyAsync(d_hdr + 2 * R, h_hdr + 2 * R, 16, cudaMemcpyHostToDevice, st));
+    NK(n->AllGather(d_hdr + 2 * R, d_hdr, 2, ncclUint64, c->comm, st));
+    CK(cudaMemcpyAsync(h_hdr, d_hdr, 2 * W * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t N = 0, E = 0, n_max = 1, e_max = 1;
+    for (uint32_t r = 0; r < W; r++) {
+        N += h_hdr[2 * r]; E += h_hdr[2 * r + 1];
+        n_max = std::max(n_max, h_hdr[2 * r]); e_max = std::max(e_max, h_hdr[2 * r + 1]);
+    }
+    *n_total = (uint32_t)N;
+    if (N > cap_sketches) return fail(-2, "spsp_cmp_exchange_batch: output arrays too small");
+    if (R == 0 && N && (!inter_out || ld < N)) return fail(-3, "spsp_cmp_exchange_batch: bad output matrix");
+    if (N == 0) return 0;
+    // ---- stage B: sizes and elements of every rank, in place, one group
+    CK(c->x_sizes.ensure(W * n_max * 8)); CK(c->xp_sizes.ensure(n_max * 8));
+    CK(c->x_klo.ensure(W * e_max * 8)); CK(c->x_min.ensure(W * e_max * 4));
+    if (hi) CK(c->x_khi.ensure(W * e_max * 8));
+    uint64_t *h_sz = static_cast<uint64_t *>(c->xp_sizes.p);
+    for (uint64_t i = 0; i < n_max; i++) h_sz[i] = i < n_local ? s.last_batch.h_elem_off[i + 1] - s.last_batch.h_elem_off[i] : 0;
+    uint64_t *d_sz = static_cast<uint64_t *>(c->x_sizes.p);
+    uint64_t *d_klo = static_cast<uint64_t *>(c->x_klo.p), *d_khi = static_cast<uint64_t *>(c->x_khi.p);
+    uint32_t *d_min = static_cast<uint32_t *>(c->x_min.p);
+    CK(cudaMemcpyAsync(d_sz + R * n_max, h_sz, n_max * 8, cudaMemcpyHostToDevice, st));
+    if (e_local) {
+        CK(cudaMemcpyAsync(d_klo + R * e_max, s.last_batch.d_klo, e_local * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(d_min + R * e_max, s.last_batch.d_minim, e_local * 4, cudaMemcpyDeviceToDevice, st));
+        if (hi) CK(cudaMemcpyAsync(d_khi + R * e_max, s.last_batch.d_khi, e_local * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    NK(n->GroupStart());
+    NK(n->AllGather(d_sz + R * n_max, d_sz, n_max, ncclUint64, c->comm, st));
+    NK(n->AllGather(d_klo + R * e_max, d_klo, e_max, ncclUint64, c->comm, st));
+    NK(n->AllGather(d_min + R * e_max, d_min, e_max, ncclUint32, c->comm, st));
+    if (hi) NK(n->AllGather(d_khi + R * e_max, d_khi, e_max, ncclUint64, c->comm, st));
+    NK(n->GroupEnd());
+    // ---- sketch ranges of the union (rank-major), chunk offsets, this rank's tiles
+    CK(c->x_begin.ensure(N * 8)); CK(c->x_end.ensure(N * 8)); CK(c->x_compact.ensure(N * 8));
+    CK(launch_gathered_ranges(d_hdr, d_sz, W, n_max, e_max, static_cast<uint64_t *>(c->x_begin.p),
+                              static_cast<uint64_t *>(c->x_end.p), static_cast<uint64_t *>(c->x_compact.p), st));
+    c->owns_cmp = false;
+    c->has_hi = hi;
+    c->n_sketches = (uint32_t)N;
+    c->n_elems = E;
+    c->cmp.minim = d_min; c->cmp.klo = d_klo; c->cmp.khi = hi ? d_khi : nullptr;
+    c->cmp.sk_off = static_cast<const uint64_t *>(c->x_begin.p);
+    c->cmp.sk_end = static_cast<const uint64_t *>(c->x_end.p);
+    const double avg = (double)E / (double)N;
+    uint64_t chunks = (uint64_t)std::ceil(32.0 * avg / (0.7 * CMP_CAP));
+    chunks = std::min<uint64_t>(std::max<uint64_t>(chunks, 1), 8192);
+    c->n_chunks = (uint32_t)chunks;
+    CK(c->b_chunk_off.ensure((size_t)N * (chunks + 1) * sizeof(uint64_t)));
+    c->cmp.chunk_off = static_cast<uint64_t *>(c->b_chunk_off.p);
+    CK(launch_chunk_offsets(c->cmp, (uint32_t)N, c->n_chunks, c->m, st));
+    c->launches += 2;
+    CK(c->x_out.ensure(N * N * 4)); CK(c->xp_out.ensure(N * N * 4 + N * 8));
+    uint32_t *d_out = static_cast<uint32_t *>(c->x_out.p);
+    CK(cudaMemsetAsync(d_out, 0, N * N * 4, st));
+    int rc = cmp_run_impl(c, 0, (uint32_t)N, 0, (uint32_t)N, 1, R, W, d_out, N);     // synchronises the stream
+    if (rc) return rc;
+    if (kernel_ms) spsp_cmp_last_kernel_ms(c, kernel_ms);
+    // ---- disjoint tiles: the sum over ranks is the gather to rank 0
+    NK(n->Reduce(d_out, d_out, N * N, ncclUint32, ncclSum, 0, c->comm, st));
+    uint8_t *h_out = static_cast<uint8_t *>(c->xp_out.p);
+    if (R == 0) CK(cudaMemcpyAsync(h_out, d_out, N * N * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_out + N * N * 4, c->x_compact.p, N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (R == 0)
+        for (uint64_t i = 0; i < N; i++) memcpy(inter_out + i * ld, h_out + i * N * 4, N * 4);
+    if (sizes_out) memcpy(sizes_out, h_out + N * N * 4, N * 8);
     return 0;
 }
 

@@ -24,14 +24,14 @@
 namespace spsp {
 
 __global__ void chunk_offsets_kernel(const uint32_t *__restrict__ minim, const uint64_t *__restrict__ sk_off,
-                                     uint32_t n_sketches, uint32_t n_chunks, uint64_t space,
+                                     const uint64_t *__restrict__ sk_end, uint32_t n_sketches, uint32_t n_chunks, uint64_t space,
                                      uint64_t *__restrict__ chunk_off)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t total = (uint64_t)n_sketches * (n_chunks + 1);
     if (t >= total) return;
     uint32_t s = (uint32_t)(t / (n_chunks + 1)), c = (uint32_t)(t % (n_chunks + 1));
-    uint64_t lo = sk_off[s], hi = sk_off[s + 1];
+    uint64_t lo = sk_off[s], hi = sk_end ? sk_end[s] : sk_off[s + 1];
     // first element with minimizer >= boundary(c)
     uint64_t bound = space * c / n_chunks;          // space <= 2^30, c <= 2^13
     if (c == n_chunks) { chunk_off[t] = hi; return; }
@@ -178,12 +178,41 @@ hashjoin_kernel(CmpData d, const uint2 *__restrict__ tiles, uint32_t n_chunks, u
     }
 }
 
+// One thread per rank: hdr_all[2r] = sketches of rank r, sizes_all[r * n_max + i] = elements of its sketch i,
+// which start at element r * e_max of the gathered arrays.
+__global__ void gathered_ranges_kernel(const uint64_t *__restrict__ hdr_all, const uint64_t *__restrict__ sizes_all,
+                                       uint32_t world, uint64_t n_max, uint64_t e_max, uint64_t *__restrict__ sk_begin,
+                                       uint64_t *__restrict__ sk_end, uint64_t *__restrict__ sizes_compact)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= world) return;
+    uint64_t first = 0;
+    for (uint32_t q = 0; q < r; q++) first += hdr_all[2 * q];
+    uint64_t acc = r * e_max;
+    const uint64_t n = hdr_all[2 * r];
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t sz = sizes_all[r * n_max + i];
+        sk_begin[first + i] = acc;
+        sk_end[first + i] = acc + sz;
+        sizes_compact[first + i] = sz;
+        acc += sz;
+    }
+}
+
+cudaError_t launch_gathered_ranges(const uint64_t *d_hdr_all, const uint64_t *d_sizes_all, uint32_t world, uint64_t n_max,
+                                   uint64_t e_max, uint64_t *sk_begin, uint64_t *sk_end, uint64_t *sizes_compact,
+                                   cudaStream_t st)
+{
+    gathered_ranges_kernel<<<1, 32, 0, st>>>(d_hdr_all, d_sizes_all, world, n_max, e_max, sk_begin, sk_end, sizes_compact);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chunk_offsets(const CmpData &d, uint32_t n_sketches, uint32_t n_chunks, int m, cudaStream_t st)
 {
     uint64_t total = (uint64_t)n_sketches * (n_chunks + 1);
     if (!total) return cudaSuccess;
     unsigned blocks = (unsigned)((total + 255) / 256);
-    chunk_offsets_kernel<<<blocks, 256, 0, st>>>(d.minim, d.sk_off, n_sketches, n_chunks, 1ULL << (2 * m),
+    chunk_offsets_kernel<<<blocks, 256, 0, st>>>(d.minim, d.sk_off, d.sk_end, n_sketches, n_chunks, 1ULL << (2 * m),
                                                  d.chunk_off);
     return cudaGetLastError();
 }

@@ -155,6 +155,30 @@ def allgather_compare_device(elem_off, dctx, rank: int, world: int, info: Option
     return compare_gathered(all_sizes, g_mn, g_lo, g_hi, rank, world, dctx, info)
 
 
+def join_contexts(dctx, rank: int, world: int):
+    """spsp_nccl_init on every rank: rank 0's NCCL id travels over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    def bcast(buf):
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.from_numpy(buf.copy())
+        if on_gpu:
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        return t.cpu().numpy()
+
+    dctx.nccl_init(rank, world, bcast)
+
+
+def native_exchange_compare(dctx, n_local: int, rank: int, world: int, info: Optional[dict] = None, slot: int = 0):
+    """The compare stage of a multi-GPU job entirely inside the C ABI (spsp_cmp_exchange_batch):
+    NCCL all-gather of the device-resident elements + tiles + reduce, no tensor library in between.
+    Same return value as allgather_compare_device (inter is None on ranks other than 0)."""
+    inter, sizes = dctx.cmp_exchange_batch(n_local * world, rank, slot, info)
+    return inter, sizes, False
+
+
 def allgather_compare(sketches: Sequence[bytes], k: int, m: int, rank: int, world: int, dctx, info: Optional[dict] = None):
     """All-vs-all compare of the union of all ranks' sketches (rank-major order).
     Returns (inter[N,N] uint32 -- complete on rank 0 --, sizes[N] uint64, False)."""
