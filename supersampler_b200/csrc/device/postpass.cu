@@ -66,7 +66,7 @@ struct PostpassBuffers {
     DBuf cnt, hkey, hval, hkey2, hval2, hhash, hrec, cflag, cid, cl_first, cl_np, cl_nk, cl_poff, cl_eoff;
     DBuf pc_first, pc_nk, pc_min, pc_meta, pc_eoff;
     DBuf eA, eklo, ekhi, epm, idx0, idx1, idx2, skey, skey2, head, uid;
-    DBuf uA, uklo, ukhi, ufirst, upm, ucnt, uhead, bflag, bidm, bstart, uidx0, uidx2, ins, seen;
+    DBuf uA, uklo, ukhi, upm, ucnt, bflag, bidm, bstart, uidx0, uidx2, uent, eslot, hfirst, hcount, huniq, seen;
     DBuf visit, bbytes, bnmax, boff, body, in_bytes, in_sel, in_elems, eflag, eoff, el_min, el_klo, el_khi, cubtmp;
     HBuf h_cnt, h_body, h_in, h_off;
 };
@@ -364,89 +364,138 @@ __global__ void pp_entries_kernel(const uint32_t *__restrict__ packed, const uin
     epm[t] = (uint8_t)pm;
 }
 
-__global__ void pp_gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n,
-                                     uint64_t *__restrict__ dst)
+// ------------------------------------------------------------ K5 unique k-mers
+//
+// handle_superkmer's `minimizer_map[min][kmer]` (SubSampler.cpp:243-302) as ONE global open-addressing table
+// keyed by (bucket, oriented k-mer): a slot remembers the smallest entry index that carries its key (the first
+// occurrence: its order is the insertion order of the reference's dense map) and how many entries do (the
+// uint8 count, SubSampler.h:24).  No k-mer sort is needed: first occurrences, compacted in entry order and
+// stably sorted by bucket only, ARE the buckets in insertion order.
+constexpr uint32_t H_EMPTY = 0xFFFFFFFFu;
+
+struct GHash {
+    uint32_t *first;             // [slots] smallest entry index with the slot's key, H_EMPTY if free
+    uint32_t *count;             // [slots] entries with the slot's key
+    uint32_t *uniq;              // [slots] index of the key in the unique (bucket-grouped) arrays
+    uint64_t mask;               // slots - 1
+    const uint64_t *eA, *eklo, *ekhi;   // entry arrays the keys live in
+};
+__device__ __forceinline__ uint64_t gh_hash(uint64_t A, uint64_t lo, uint64_t hi)
 {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) dst[t] = src[idx[t]];
+    uint64_t x = lo ^ (hi * 0xC2B2AE3D27D4EB4FULL) ^ (A * 0x9E3779B97F4A7C15ULL);
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 29;
+    return x;
+}
+// Slot of (A, lo, hi), or ~0 when the key is not in the table.
+__device__ __forceinline__ uint64_t gh_find(const GHash &h, uint64_t A, uint64_t lo, uint64_t hi)
+{
+    uint64_t s = gh_hash(A, lo, hi) & h.mask;
+    for (;;) {
+        const uint32_t e = h.first[s];
+        if (e == H_EMPTY) return ~0ULL;
+        if (h.eA[e] == A && h.eklo[e] == lo && (!h.ekhi || h.ekhi[e] == hi)) return s;
+        s = (s + 1) & h.mask;
+    }
 }
 
-// ------------------------------------------------------------ K5 runs / unique
+__global__ void pp_hash_insert_kernel(GHash h, uint32_t *__restrict__ eslot, const Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt->n_entries) return;
+    const uint64_t A = h.eA[t], lo = h.eklo[t], hi = h.ekhi ? h.ekhi[t] : 0;
+    uint64_t s = gh_hash(A, lo, hi) & h.mask;
+    for (;;) {
+        uint32_t e = *reinterpret_cast<volatile uint32_t *>(h.first + s);
+        if (e == H_EMPTY) {
+            e = atomicCAS(h.first + s, H_EMPTY, (uint32_t)t);
+            if (e == H_EMPTY) break;                          // claimed a free slot
+        }
+        // the slot belongs to the key of entry e (entries are immutable, so that key can be read)
+        if (h.eA[e] == A && h.eklo[e] == lo && (!h.ekhi || h.ekhi[e] == hi)) {
+            atomicMin(h.first + s, (uint32_t)t);
+            break;
+        }
+        s = (s + 1) & h.mask;
+    }
+    atomicAdd(h.count + s, 1u);
+    eslot[t] = (uint32_t)s;
+}
 
-__global__ void pp_head_kernel(const uint64_t *__restrict__ sA, const uint32_t *__restrict__ idx,
-                               const uint64_t *__restrict__ eklo, const uint64_t *__restrict__ ekhi, uint64_t bound,
-                               uint32_t *__restrict__ head, const Counters *cnt)
+__global__ void pp_first_flag_kernel(const uint32_t *__restrict__ hfirst, const uint32_t *__restrict__ eslot, uint64_t bound,
+                                     uint32_t *__restrict__ head, const Counters *cnt)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bound) return;
-    bool h = false;
-    if (t < cnt->n_entries) {
-        h = true;
-        if (t > 0) {
-            const uint32_t a = idx[t], b = idx[t - 1];
-            h = sA[t] != sA[t - 1] || eklo[a] != eklo[b] || (ekhi && ekhi[a] != ekhi[b]);
-        }
-    }
-    head[t] = h ? 1u : 0u;
+    head[t] = (t < cnt->n_entries && hfirst[eslot[t]] == (uint32_t)t) ? 1u : 0u;
 }
 
-__global__ void pp_unique_kernel(const uint64_t *__restrict__ sA, const uint32_t *__restrict__ idx,
-                                 const uint64_t *__restrict__ eklo, const uint64_t *__restrict__ ekhi,
-                                 const uint8_t *__restrict__ epm, const uint32_t *__restrict__ head,
-                                 const uint32_t *__restrict__ uid, uint64_t bound, uint64_t *__restrict__ uA,
-                                 uint64_t *__restrict__ uklo, uint64_t *__restrict__ ukhi, uint32_t *__restrict__ ufirst,
-                                 uint8_t *__restrict__ upm, uint32_t *__restrict__ uhead, Counters *cnt)
+// first occurrences in entry order: bucket key for the sort, entry index, identity permutation
+__global__ void pp_unique_list_kernel(const uint64_t *__restrict__ eA, const uint32_t *__restrict__ head,
+                                      const uint32_t *__restrict__ uid, uint64_t bound, uint64_t *__restrict__ ukey,
+                                      uint32_t *__restrict__ uent, uint32_t *__restrict__ uidx, Counters *cnt)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= bound || t >= cnt->n_entries) return;
-    if (head[t]) {
-        const uint32_t u = uid[t], e = idx[t];      // stable sorts: the run's first entry has the smallest order
-        uA[u] = sA[t]; uklo[u] = eklo[e];
-        if (ukhi) ukhi[u] = ekhi[e];
-        ufirst[u] = e; upm[u] = epm[e]; uhead[u] = (uint32_t)t;
-    }
-    if (t + 1 == cnt->n_entries) cnt->n_unique = uid[t] + head[t];
+    if (t >= bound) return;
+    uidx[t] = (uint32_t)t;
+    ukey[t] = ~0ULL;                                          // padding sorts last (real keys are written below)
+    if (t + 1 == bound) cnt->n_unique = uid[t] + head[t];
+}
+__global__ void pp_unique_list_fill_kernel(const uint64_t *__restrict__ eA, const uint32_t *__restrict__ head,
+                                           const uint32_t *__restrict__ uid, uint64_t *__restrict__ ukey,
+                                           uint32_t *__restrict__ uent, const Counters *cnt)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt->n_entries || !head[t]) return;
+    const uint32_t u = uid[t];
+    ukey[u] = eA[t];
+    uent[u] = (uint32_t)t;
 }
 
-// count (mod 256, SubSampler.h:24) + bucket heads
-__global__ void pp_unique_finish_kernel(const uint64_t *__restrict__ uA, const uint32_t *__restrict__ uhead, uint64_t bound,
-                                        uint8_t *__restrict__ ucnt, uint32_t *__restrict__ bflag,
-                                        uint32_t *__restrict__ uidx, uint8_t *__restrict__ seen, const Counters *cnt)
+// unique k-mers grouped by bucket (stable sort of the list above): key, leftmost minimizer position, count
+// mod 256, bucket heads; every slot learns where its key ended up.
+__global__ void pp_unique_finish_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ order,
+                                        const uint32_t *__restrict__ uent, const uint32_t *__restrict__ eslot, GHash h,
+                                        const uint8_t *__restrict__ epm, uint64_t bound, uint64_t *__restrict__ uA,
+                                        uint64_t *__restrict__ uklo, uint64_t *__restrict__ ukhi, uint8_t *__restrict__ upm,
+                                        uint8_t *__restrict__ ucnt, uint32_t *__restrict__ bflag, uint8_t *__restrict__ seen,
+                                        const Counters *cnt)
 {
-    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= bound) return;
-    uidx[u] = (uint32_t)u;
-    seen[u] = 0;
-    if (u >= cnt->n_unique) { bflag[u] = 0; return; }
-    const uint64_t next = (u + 1 < cnt->n_unique) ? uhead[u + 1] : cnt->n_entries;
-    ucnt[u] = (uint8_t)((next - uhead[u]) & 0xFF);
-    bflag[u] = (u == 0 || uA[u] != uA[u - 1]) ? 1u : 0u;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= bound) return;
+    seen[j] = 0;
+    if (j >= cnt->n_unique) { bflag[j] = 0; return; }
+    const uint32_t t = uent[order[j]], s = eslot[t];
+    uA[j] = skey[j];
+    uklo[j] = h.eklo[t];
+    if (ukhi) ukhi[j] = h.ekhi[t];
+    upm[j] = epm[t];
+    ucnt[j] = (uint8_t)(h.count[s] & 0xFFu);                  // uint8 counter of the reference wraps at 256
+    h.uniq[s] = (uint32_t)j;
+    bflag[j] = (j == 0 || skey[j] != skey[j - 1]) ? 1u : 0u;
 }
 
-// bucket starts + the key of the insertion-order sort: (bucket, order of the first occurrence)
-__global__ void pp_bucket_start_kernel(const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid,
-                                       const uint32_t *__restrict__ ufirst, uint64_t bound, int order_bits,
-                                       uint32_t *__restrict__ bstart, uint64_t *__restrict__ okey, Counters *cnt)
+__global__ void pp_bucket_start_kernel(const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid, uint64_t bound,
+                                       uint32_t *__restrict__ bstart, Counters *cnt)
 {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= bound) return;
-    if (u >= cnt->n_unique) { okey[u] = ~0ULL; return; }            // padding sorts last
-    const uint32_t b = bid[u] + bflag[u] - 1;                      // bid = exclusive scan of the head flags
-    okey[u] = ((uint64_t)b << order_bits) | ufirst[u];
-    if (bflag[u]) bstart[b] = (uint32_t)u;
+    if (u >= bound || u >= cnt->n_unique) return;
+    if (bflag[u]) bstart[bid[u]] = (uint32_t)u;               // bid = exclusive scan of the head flags
     if (u + 1 == cnt->n_unique) cnt->n_buckets = bid[u] + bflag[u];
 }
 
 // -------------------------------------------------------- K6 reconstruction
 
-// One bucket's unique k-mers, sorted by key; indices are bucket-relative.  The
-// arrays live in shared memory (small buckets, staged by the warp) or in global
-// memory (buckets larger than RC_CAP).
+// One bucket's unique k-mers in insertion order; indices are bucket-relative.  The arrays live in shared
+// memory (small buckets, staged by the warp) or in global memory (buckets larger than RC_CAP, looked up
+// through the global table).
 struct BucketView {
     const uint64_t *klo, *khi;     // khi null when k <= 32
     const uint8_t *cnt;
     uint8_t *seen;
-    uint32_t n;
+    uint32_t n, bs;                // size, first unique index of the bucket
+    uint64_t A;                    // bucket key
     unsigned abundance;
     int k;
 };
@@ -455,15 +504,11 @@ __device__ __forceinline__ K128 bv_key(const BucketView &v, uint32_t u)
 {
     return K128{v.klo[u], v.khi ? v.khi[u] : 0};
 }
-// binary search in the bucket's key-sorted unique list
-__device__ __forceinline__ int bv_find(const BucketView &v, const K128 &key)
+// bucket-relative index of `key` in bucket v, or -1
+__device__ __forceinline__ int bv_find(const GHash &h, const BucketView &v, const K128 &key)
 {
-    uint32_t lo = 0, hi = v.n;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (k_lt(bv_key(v, mid), key)) lo = mid + 1; else hi = mid;
-    }
-    return (lo < v.n && k_eq(bv_key(v, lo), key)) ? (int)lo : -1;
+    const uint64_t s = gh_find(h, v.A, key.lo, key.hi);
+    return s == ~0ULL ? -1 : (int)(h.uniq[s] - v.bs);
 }
 __device__ __forceinline__ K128 bv_neighbour(const K128 &cur, bool left, int t, int k)
 {
@@ -487,19 +532,18 @@ constexpr int RC_WARPS = 4;          // buckets in flight per CTA (one warp each
 constexpr int RC_SK = 192;           // 2-bit codes of a super-k-mer (2k-m <= 123, grows both ways from 64)
 constexpr uint32_t VISIT_START = 0u << 30, VISIT_LEFT = 1u << 30, VISIT_RIGHT = 2u << 30, VISIT_MASK = (1u << 30) - 1u;
 constexpr uint32_t VISIT_END = 0xFFFFFFFFu;
-constexpr uint16_t ADJ_NONE = 0xFFFF;
+constexpr uint16_t ADJ_NONE = RC_CAP;    // sentinel neighbour: seen[RC_CAP] is always set
 
 // Shared-memory slice of one warp of pp_chain_kernel.
 struct RcSmem {
     uint64_t *klo, *khi;
     uint32_t *slot;
     uint16_t *adj;               // [u][left 0..3, right 0..3] neighbour index in probe order A,T,C,G
-    uint16_t *ins;
-    uint8_t *cnt, *seen, *pm;
+    uint8_t *cnt, *seen, *pm;    // seen has RC_CAP + 16 entries
 };
 static size_t rc_smem_bytes(bool hi128)
 {
-    return (size_t)RC_WARPS * (RC_CAP * (8 + (hi128 ? 8 : 0) + 16 + 2 + 3) + RC_SLOTS * 4);
+    return (size_t)RC_WARPS * (RC_CAP * (8 + (hi128 ? 8 : 0) + 16 + 3) + 16 + RC_SLOTS * 4);
 }
 __device__ __forceinline__ RcSmem rc_carve(uint8_t *base, int wi, bool hi128)
 {
@@ -512,11 +556,9 @@ __device__ __forceinline__ RcSmem rc_carve(uint8_t *base, int wi, bool hi128)
     base += (size_t)RC_WARPS * RC_CAP * 16;
     r.slot = reinterpret_cast<uint32_t *>(base) + (size_t)wi * RC_SLOTS;
     base += (size_t)RC_WARPS * RC_SLOTS * 4;
-    r.ins = reinterpret_cast<uint16_t *>(base) + (size_t)wi * RC_CAP;
-    base += (size_t)RC_WARPS * RC_CAP * 2;
     r.cnt = base + (size_t)wi * RC_CAP;
-    r.seen = base + (size_t)(RC_WARPS + wi) * RC_CAP;
-    r.pm = base + (size_t)(2 * RC_WARPS + wi) * RC_CAP;
+    r.pm = base + (size_t)(RC_WARPS + wi) * RC_CAP;
+    r.seen = base + (size_t)2 * RC_WARPS * RC_CAP + (size_t)wi * (RC_CAP + 16);
     return r;
 }
 __device__ __forceinline__ uint32_t rc_hash(const K128 &key)
@@ -557,43 +599,35 @@ __device__ __forceinline__ void rc_walk_staged(const RcSmem &sm, uint32_t nb, in
     }
     __syncwarp();
     if (lane == 0) {
-        uint32_t nv = 0, cursor = 0;
-        for (;;) {
-            // find_first_kmer (:604-620): first unseen entry in insertion order
-            uint32_t start = 0;
-            for (; cursor < nb; cursor++) {
-                start = sm.ins[cursor];
-                if (!sm.seen[start] && sm.cnt[start] >= abundance) break;
-            }
-            if (cursor >= nb) break;
+        uint32_t nv = 0;
+        // find_first_kmer (:604-620): the k-mers are stored in insertion order
+        for (uint32_t start = 0; start < nb; start++) {
+            if (sm.seen[start] || sm.cnt[start] < abundance) continue;
             sm.seen[start] = 1;
             visit[nv++] = start | VISIT_START;
-            const uint8_t pms = sm.pm[start];
-            uint64_t n_left = (uint64_t)d - pms, n_right = pms;
+            const uint32_t pms = sm.pm[start];
+            // n_left = d - pos_min as uint64 in the reference: a k-mer without the minimizer text (pos 255)
+            // extends to the left for as long as it can
+            uint32_t n_left = pms == 255u ? 0x7fffffffu : (uint32_t)d - pms, n_right = pms;
             uint32_t cur = start, ext = 0;                   // ext = k-mers added to the start k-mer
             while (ext != (uint32_t)d) {                     // |sk| != 2k-m
                 const bool left = n_left != 0;
                 if (!left && n_right == 0) break;
                 // find_next (:566-602): first neighbour in probe order that is in the bucket and unseen
                 const uint2 pk = *reinterpret_cast<const uint2 *>(sm.adj + cur * 8 + (left ? 0 : 4));
-                int found = -1;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const uint32_t c = ((t < 2 ? pk.x : pk.y) >> (16 * (t & 1))) & 0xFFFFu;
-                    if (found < 0 && c != ADJ_NONE && !sm.seen[c]) found = (int)c;
-                }
-                if (found >= 0) sm.seen[found] = 1;
+                const uint32_t c0 = pk.x & 0xFFFFu, c1 = pk.x >> 16, c2 = pk.y & 0xFFFFu, c3 = pk.y >> 16;
+                const uint32_t s0 = sm.seen[c0], s1 = sm.seen[c1], s2 = sm.seen[c2], s3 = sm.seen[c3];
+                const uint32_t found = !s0 ? c0 : !s1 ? c1 : !s2 ? c2 : !s3 ? c3 : (uint32_t)ADJ_NONE;
+                const bool ok = found != ADJ_NONE;
+                sm.seen[found] = 1;                          // the sentinel's flag is set anyway
+                if (ok) { visit[nv++] = found | (left ? VISIT_LEFT : VISIT_RIGHT); ext++; }
                 if (left) {
-                    n_left--;
-                    if (found >= 0) { visit[nv++] = (uint32_t)found | VISIT_LEFT; ext++; }
-                    else n_left = 0;
-                    cur = (n_left == 0) ? start : (uint32_t)found;
+                    n_left = ok ? n_left - 1 : 0;
+                    cur = n_left == 0 ? start : found;
                 } else {
+                    if (!ok) break;
                     n_right--;
-                    if (found < 0) break;
-                    visit[nv++] = (uint32_t)found | VISIT_RIGHT;
-                    ext++;
-                    cur = (uint32_t)found;
+                    cur = found;
                 }
             }
         }
@@ -604,12 +638,12 @@ __device__ __forceinline__ void rc_walk_staged(const RcSmem &sm, uint32_t nb, in
 
 // Same walk for a bucket too large to stage: global memory, binary search, lanes
 // 0..3 probing the four neighbours at once.
-__device__ __forceinline__ int rc_step_global(const BucketView &v, const K128 &cur, bool left, K128 *out)
+__device__ __forceinline__ int rc_step_global(const GHash &h, const BucketView &v, const K128 &cur, bool left, K128 *out)
 {
     const int lane = threadIdx.x & 31;
     int u = -1;
     if (lane < 4) {
-        u = bv_find(v, bv_neighbour(cur, left, lane, v.k));
+        u = bv_find(h, v, bv_neighbour(cur, left, lane, v.k));
         if (u >= 0 && (v.seen[u] || v.cnt[u] < v.abundance)) u = -1;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, u >= 0);
@@ -621,21 +655,15 @@ __device__ __forceinline__ int rc_step_global(const BucketView &v, const K128 &c
     *out = bv_neighbour(cur, left, t, v.k);
     return u;
 }
-__device__ __forceinline__ void rc_walk_global(const BucketView &v, const uint8_t *__restrict__ pm,
-                                               const uint32_t *__restrict__ ins_g, uint32_t ins_base, int k, int m,
-                                               uint32_t *__restrict__ visit)
+__device__ __forceinline__ void rc_walk_global(const GHash &h, const BucketView &v, const uint8_t *__restrict__ pm, int k,
+                                               int m, uint32_t *__restrict__ visit)
 {
     const int lane = threadIdx.x & 31;
     const int d = k - m;
     const uint32_t nb = v.n;
-    uint32_t nv = 0, cursor = 0;
-    for (;;) {
-        uint32_t start = 0;
-        for (; cursor < nb; cursor++) {
-            start = ins_g[cursor] - ins_base;
-            if (!v.seen[start] && v.cnt[start] >= v.abundance) break;
-        }
-        if (cursor >= nb) break;
+    uint32_t nv = 0;
+    for (uint32_t start = 0; start < nb; start++) {
+        if (v.seen[start] || v.cnt[start] < v.abundance) continue;
         __syncwarp();
         if (lane == 0) { v.seen[start] = 1; visit[nv] = start | VISIT_START; }
         __syncwarp();
@@ -647,7 +675,7 @@ __device__ __forceinline__ void rc_walk_global(const BucketView &v, const uint8_
         while (ext != (uint32_t)d) {
             if (n_left != 0) {
                 K128 nx;
-                const int u = rc_step_global(v, cur, true, &nx);
+                const int u = rc_step_global(h, v, cur, true, &nx);
                 n_left--;
                 if (u >= 0) {
                     if (lane == 0) visit[nv] = (uint32_t)u | VISIT_LEFT;
@@ -658,7 +686,7 @@ __device__ __forceinline__ void rc_walk_global(const BucketView &v, const uint8_
                 cur = (n_left == 0) ? skey : nx;
             } else if (n_right != 0) {
                 K128 nx;
-                const int u = rc_step_global(v, cur, false, &nx);
+                const int u = rc_step_global(h, v, cur, false, &nx);
                 n_right--;
                 if (u < 0) break;
                 if (lane == 0) visit[nv] = (uint32_t)u | VISIT_RIGHT;
@@ -673,11 +701,11 @@ __device__ __forceinline__ void rc_walk_global(const BucketView &v, const uint8_
 }
 
 // One bucket per warp: the visit order of its k-mers (start / left extension /
-// right extension of each super-k-mer), everything pp_measure_kernel and
-// pp_emit_kernel need to size and write the bytes without another look-up.
+// right extension of each super-k-mer), everything pp_emit_kernel needs to size
+// and write the bytes without another look-up.
 __global__ void __launch_bounds__(RC_WARPS * 32)
-pp_chain_kernel(const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
-                const uint8_t *__restrict__ upm, uint8_t *__restrict__ seen_g, const uint32_t *__restrict__ ins,
+pp_chain_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ ukhi,
+                const uint8_t *__restrict__ ucnt, const uint8_t *__restrict__ upm, uint8_t *__restrict__ seen_g, GHash gh,
                 const uint32_t *__restrict__ bstart, int k, int m, unsigned abundance, uint32_t *__restrict__ visit,
                 const Counters *cnt)
 {
@@ -697,8 +725,8 @@ pp_chain_kernel(const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ 
                 sm.cnt[i] = ucnt[bs + i];
                 sm.pm[i] = upm[bs + i];
                 sm.seen[i] = 0;
-                sm.ins[i] = (uint16_t)(ins[bs + i] - bs);
             }
+            if (lane == 0) sm.seen[RC_CAP] = 1;                                 // the "no neighbour" sentinel
             __syncwarp();
             for (uint32_t i = lane; i < nb; i += 32) {                          // keys of a bucket are distinct
                 uint32_t s = rc_hash(K128{sm.klo[i], ukhi ? sm.khi[i] : 0});
@@ -707,8 +735,8 @@ pp_chain_kernel(const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ 
             __syncwarp();
             rc_walk_staged(sm, nb, k, m, abundance, visit + bs);
         } else {
-            BucketView v{uklo + bs, ukhi ? ukhi + bs : nullptr, ucnt + bs, seen_g + bs, nb, abundance, k};
-            rc_walk_global(v, upm + bs, ins + bs, bs, k, m, visit + bs);
+            BucketView v{uklo + bs, ukhi ? ukhi + bs : nullptr, ucnt + bs, seen_g + bs, nb, bs, uA[bs], abundance, k};
+            rc_walk_global(gh, v, upm + bs, k, m, visit + bs);
         }
     }
 }
@@ -834,11 +862,9 @@ pp_emit_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ ukl
 // distinct canonical k-mers of every bucket.  A unique oriented k-mer is in the
 // sketch iff count >= abundance; two orientations of one k-mer collapse.
 __global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo,
-                                       const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt,
-                                       const uint32_t *__restrict__ bflag, const uint32_t *__restrict__ bid,
-                                       const uint32_t *__restrict__ bstart, int k,
+                                       const uint64_t *__restrict__ ukhi, const uint8_t *__restrict__ ucnt, GHash gh, int k,
                                        unsigned abundance, uint64_t bound, uint32_t *__restrict__ eflag,
-                                       uint8_t *__restrict__ seen, const Counters *cnt)
+                                       const Counters *cnt)
 {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= bound) return;
@@ -849,11 +875,8 @@ __global__ void pp_element_flag_kernel(const uint64_t *__restrict__ uA, const ui
         const K128 rc = k_rc(key, k);
         if (k_lt(rc, key)) {
             // non-canonical orientation: drop it if the canonical one is in the bucket too
-            const uint32_t b = bid[u] + bflag[u] - 1;      // bid = exclusive scan of the bucket-head flags
-            const uint32_t bs = bstart[b], be = (b + 1 < cnt->n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
-            BucketView v{uklo + bs, ukhi ? ukhi + bs : nullptr, ucnt + bs, seen + bs, be - bs, abundance, k};
-            int o = bv_find(v, rc);
-            if (o >= 0 && v.cnt[o] >= abundance) keep = false;
+            const uint64_t s = gh_find(gh, uA[u], rc.lo, rc.hi);
+            if (s != ~0ULL && ucnt[gh.uniq[s]] >= abundance) keep = false;
         }
     }
     eflag[u] = keep ? 1u : 0u;
@@ -1024,43 +1047,40 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
         b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), b->pc_eoff.as<uint32_t>(), k, m, bound, input_shift,
         b->eA.as<uint64_t>(), b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(), b->idx0.as<uint32_t>(), cnt);
     launched++;
-    // stable LSD sorts: (bucket, key, order) with order = entry index
-    uint32_t *idx_cur = b->idx1.as<uint32_t>(), *idx_alt = b->idx2.as<uint32_t>();
-    PP_CK(sort_pairs(b, b->eklo.as<uint64_t>(), b->skey.as<uint64_t>(), b->idx0.as<uint32_t>(), idx_cur, bound, 0,
-                     hi128 ? 64 : 2 * k, st));
-    if (hi128) {
-        pp_gather_u64_kernel<<<nblk(bound), 256, 0, st>>>(ekhi, idx_cur, bound, b->skey.as<uint64_t>());
-        PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->skey2.as<uint64_t>(), idx_cur, idx_alt, bound, 0, 2 * k - 64, st));
-        std::swap(idx_cur, idx_alt);
-        launched++;
-    }
-    pp_gather_u64_kernel<<<nblk(bound), 256, 0, st>>>(b->eA.as<uint64_t>(), idx_cur, bound, b->skey.as<uint64_t>());
-    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->skey2.as<uint64_t>(), idx_cur, idx_alt, bound, 0, a_bits, st));
-    std::swap(idx_cur, idx_alt);
-    launched++;
-    const uint64_t *sA = b->skey2.as<uint64_t>();
-    // ---- unique k-mers
-    PP_CK(b->uA.ensure(bound * 8)); PP_CK(b->uklo.ensure(bound * 8)); if (hi128) PP_CK(b->ukhi.ensure(bound * 8));
-    PP_CK(b->ufirst.ensure(bound * 4)); PP_CK(b->upm.ensure(bound)); PP_CK(b->ucnt.ensure(bound)); PP_CK(b->uhead.ensure(bound * 4));
-    PP_CK(b->bflag.ensure(bound * 4)); PP_CK(b->bidm.ensure(bound * 4)); PP_CK(b->bstart.ensure(bound * 4));
-    PP_CK(b->uidx0.ensure(bound * 4)); PP_CK(b->uidx2.ensure(bound * 4)); PP_CK(b->seen.ensure(bound));
-    uint64_t *ukhi = hi128 ? b->ukhi.as<uint64_t>() : nullptr;
-    pp_head_kernel<<<nblk(bound), 256, 0, st>>>(sA, idx_cur, b->eklo.as<uint64_t>(), ekhi, bound, b->head.as<uint32_t>(), cnt);
+    // ---- unique k-mers: global hash table keyed by (bucket, k-mer), then ONE stable sort by bucket
+    uint64_t slots = 1024;
+    while (slots < 2 * bound) slots <<= 1;
+    if (slots > (1ULL << 31)) return cudaErrorInvalidValue;
+    PP_CK(b->hfirst.ensure(slots * 4)); PP_CK(b->hcount.ensure(slots * 4)); PP_CK(b->huniq.ensure(slots * 4));
+    PP_CK(b->eslot.ensure(bound * 4));
+    PP_CK(cudaMemsetAsync(b->hfirst.p, 0xFF, slots * 4, st));
+    PP_CK(cudaMemsetAsync(b->hcount.p, 0, slots * 4, st));
+    GHash gh{b->hfirst.as<uint32_t>(), b->hcount.as<uint32_t>(), b->huniq.as<uint32_t>(), slots - 1, b->eA.as<uint64_t>(),
+             b->eklo.as<uint64_t>(), ekhi};
+    pp_hash_insert_kernel<<<nblk(bound), 256, 0, st>>>(gh, b->eslot.as<uint32_t>(), cnt);
+    pp_first_flag_kernel<<<nblk(bound), 256, 0, st>>>(b->hfirst.as<uint32_t>(), b->eslot.as<uint32_t>(), bound,
+                                                      b->head.as<uint32_t>(), cnt);
     PP_CK(excl_sum(b, b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound, st));
-    pp_unique_kernel<<<nblk(bound), 256, 0, st>>>(sA, idx_cur, b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(),
-        b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound, b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
-        b->ufirst.as<uint32_t>(), b->upm.as<uint8_t>(), b->uhead.as<uint32_t>(), cnt);
-    pp_unique_finish_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uhead.as<uint32_t>(), bound,
-        b->ucnt.as<uint8_t>(), b->bflag.as<uint32_t>(), b->uidx0.as<uint32_t>(), b->seen.as<uint8_t>(), cnt);
+    PP_CK(b->uent.ensure(bound * 4)); PP_CK(b->uidx0.ensure(bound * 4)); PP_CK(b->uidx2.ensure(bound * 4));
+    pp_unique_list_kernel<<<nblk(bound), 256, 0, st>>>(b->eA.as<uint64_t>(), b->head.as<uint32_t>(), b->uid.as<uint32_t>(), bound,
+        b->skey.as<uint64_t>(), b->uent.as<uint32_t>(), b->uidx0.as<uint32_t>(), cnt);
+    pp_unique_list_fill_kernel<<<nblk(bound), 256, 0, st>>>(b->eA.as<uint64_t>(), b->head.as<uint32_t>(), b->uid.as<uint32_t>(),
+        b->skey.as<uint64_t>(), b->uent.as<uint32_t>(), cnt);
+    // first occurrences are in entry order: a stable sort by bucket leaves every bucket in insertion order
+    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->skey2.as<uint64_t>(), b->uidx0.as<uint32_t>(), b->uidx2.as<uint32_t>(), bound, 0,
+                     a_bits, st));
+    PP_CK(b->uA.ensure(bound * 8)); PP_CK(b->uklo.ensure(bound * 8)); if (hi128) PP_CK(b->ukhi.ensure(bound * 8));
+    PP_CK(b->upm.ensure(bound)); PP_CK(b->ucnt.ensure(bound));
+    PP_CK(b->bflag.ensure(bound * 4)); PP_CK(b->bidm.ensure(bound * 4)); PP_CK(b->bstart.ensure(bound * 4));
+    PP_CK(b->seen.ensure(bound));
+    uint64_t *ukhi = hi128 ? b->ukhi.as<uint64_t>() : nullptr;
+    pp_unique_finish_kernel<<<nblk(bound), 256, 0, st>>>(b->skey2.as<uint64_t>(), b->uidx2.as<uint32_t>(), b->uent.as<uint32_t>(),
+        b->eslot.as<uint32_t>(), gh, b->epm.as<uint8_t>(), bound, b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
+        b->upm.as<uint8_t>(), b->ucnt.as<uint8_t>(), b->bflag.as<uint32_t>(), b->seen.as<uint8_t>(), cnt);
     PP_CK(excl_sum(b, b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), bound, st));
-    const int order_bits = bits_for(bound);
-    pp_bucket_start_kernel<<<nblk(bound), 256, 0, st>>>(b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), b->ufirst.as<uint32_t>(),
-        bound, order_bits, b->bstart.as<uint32_t>(), b->skey.as<uint64_t>(), cnt);
-    launched += 4;
-    // insertion order inside each bucket: one sort by (bucket, first order); +1 bit so that the padding sorts last
-    PP_CK(sort_pairs(b, b->skey.as<uint64_t>(), b->eA.as<uint64_t>(), b->uidx0.as<uint32_t>(), b->uidx2.as<uint32_t>(), bound, 0,
-                     std::min(64, 2 * order_bits + 1), st));
-    const uint32_t *ins = b->uidx2.as<uint32_t>();
+    pp_bucket_start_kernel<<<nblk(bound), 256, 0, st>>>(b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), bound,
+                                                        b->bstart.as<uint32_t>(), cnt);
+    launched += 6;
     // ---- reconstruction: walk every bucket's chains once (visit order + byte sizes), offsets; bytes are emitted below
     const size_t rc_smem = rc_smem_bytes(hi128);
     {
@@ -1074,8 +1094,8 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->bbytes.ensure(bound * 4)); PP_CK(b->bnmax.ensure(bound * 4)); PP_CK(b->boff.ensure(bound * 8));
     PP_CK(b->visit.ensure(bound * 4));
     PP_CK(cudaMemsetAsync(b->bbytes.p, 0, bound * 4, st));
-    pp_chain_kernel<<<rc_grid, RC_WARPS * 32, rc_smem, st>>>(b->uklo.as<uint64_t>(), ukhi, b->ucnt.as<uint8_t>(),
-        b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), ins, b->bstart.as<uint32_t>(), k, m, in.abundance,
+    pp_chain_kernel<<<rc_grid, RC_WARPS * 32, rc_smem, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi,
+        b->ucnt.as<uint8_t>(), b->upm.as<uint8_t>(), b->seen.as<uint8_t>(), gh, b->bstart.as<uint32_t>(), k, m, in.abundance,
         b->visit.as<uint32_t>(), cnt);
     const unsigned em_grid = (unsigned)std::min<uint64_t>((bound + 7) / 8, 148 * 8);
     pp_emit_kernel<false><<<em_grid, 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->visit.as<uint32_t>(),
@@ -1088,8 +1108,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->eflag.ensure(bound * 4)); PP_CK(b->eoff.ensure(bound * 4));
     PP_CK(b->el_min.ensure(bound * 4)); PP_CK(b->el_klo.ensure(bound * 8)); if (hi128) PP_CK(b->el_khi.ensure(bound * 8));
     pp_element_flag_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->ucnt.as<uint8_t>(),
-        b->bflag.as<uint32_t>(), b->bidm.as<uint32_t>(), b->bstart.as<uint32_t>(), k, in.abundance, bound,
-        b->eflag.as<uint32_t>(), b->seen.as<uint8_t>(), cnt);
+        gh, k, in.abundance, bound, b->eflag.as<uint32_t>(), cnt);
     PP_CK(excl_sum(b, b->eflag.as<uint32_t>(), b->eoff.as<uint32_t>(), bound, st));
     pp_element_write_kernel<<<nblk(bound), 256, 0, st>>>(b->uA.as<uint64_t>(), b->uklo.as<uint64_t>(), ukhi, b->eflag.as<uint32_t>(),
         b->eoff.as<uint32_t>(), k, input_shift, bound, b->el_min.as<uint32_t>(), b->el_klo.as<uint64_t>(),
