@@ -60,6 +60,7 @@ struct HBuf {
 // counters kept on the device between kernels
 struct Counters {
     unsigned long long n_valid, n_clusters, n_pieces, n_entries, n_unique, n_buckets, n_elems, body_bytes;
+    unsigned long long chain_next;      // work queue of pp_chain_kernel (next bucket to walk)
 };
 
 struct PostpassBuffers {
@@ -707,13 +708,18 @@ __global__ void __launch_bounds__(RC_WARPS * 32)
 pp_chain_kernel(const uint64_t *__restrict__ uA, const uint64_t *__restrict__ uklo, const uint64_t *__restrict__ ukhi,
                 const uint8_t *__restrict__ ucnt, const uint8_t *__restrict__ upm, uint8_t *__restrict__ seen_g, GHash gh,
                 const uint32_t *__restrict__ bstart, int k, int m, unsigned abundance, uint32_t *__restrict__ visit,
-                const Counters *cnt)
+                Counters *cnt)
 {
     extern __shared__ __align__(16) uint8_t rc_smem[];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const RcSmem sm = rc_carve(rc_smem, wi, ukhi != nullptr);
     const uint64_t n_buckets = cnt->n_buckets;
-    for (uint64_t b = (uint64_t)blockIdx.x * RC_WARPS + wi; b < n_buckets; b += (uint64_t)gridDim.x * RC_WARPS) {
+    // persistent warps pull buckets from a queue: the makespan is the largest bucket, not a wave of them
+    for (;;) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&cnt->chain_next, 1ULL);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_buckets) break;
         const uint32_t bs = bstart[b], be = (b + 1 < n_buckets) ? bstart[b + 1] : (uint32_t)cnt->n_unique;
         const uint32_t nb = be - bs;
         __syncwarp();
@@ -1090,7 +1096,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
             attr_done = true;
         }
     }
-    const unsigned rc_grid = (unsigned)std::min<uint64_t>((bound + RC_WARPS - 1) / RC_WARPS, 148 * 16);
+    const unsigned rc_grid = (unsigned)std::min<uint64_t>((bound + RC_WARPS - 1) / RC_WARPS, 148 * 8);
     PP_CK(b->bbytes.ensure(bound * 4)); PP_CK(b->bnmax.ensure(bound * 4)); PP_CK(b->boff.ensure(bound * 8));
     PP_CK(b->visit.ensure(bound * 4));
     PP_CK(cudaMemsetAsync(b->bbytes.p, 0, bound * 4, st));
