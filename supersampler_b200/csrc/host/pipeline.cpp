@@ -7,6 +7,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <mutex>
@@ -217,6 +218,7 @@ void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<P
 {
     spsp_ctx *ctx = session_->ctx();
     const size_t nb = last - first;
+    dbg_no_upload_ = getenv("SPSP_PIPE_NO_UPLOAD") != nullptr;      // measurement aid: pack only (results are garbage)
     auto t0 = clk::now();
     uint64_t total_words = 0;
     for (size_t i = first; i < last; i++) {
@@ -245,6 +247,7 @@ void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<P
         uint64_t uploaded = 0;                              // words of this region already queued for the copy
         auto upload_to = [&](uint64_t words) {
             if (words <= uploaded) return;
+            if (dbg_no_upload_) { uploaded = words; return; }
             if (spsp_batch_upload(ctx, 0, p.word_off + uploaded, stage_ + p.word_off + uploaded, words - uploaded) != 0)
                 throw_spsp("spsp_batch_upload");
             uploaded = words;

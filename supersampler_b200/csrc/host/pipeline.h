@@ -88,6 +88,7 @@ private:
     int k_, m_, threads_;
     double s_;
     unsigned abundance_;
+    bool dbg_no_upload_ = false;
     uint32_t *stage_ = nullptr;                // pinned staging buffer (grow-only)
     uint64_t stage_words_ = 0;
     // elements of the last run

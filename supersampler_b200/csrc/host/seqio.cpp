@@ -130,6 +130,11 @@ static void words_to_msb_first(uint32_t *w, uint64_t n)
     }
 }
 
+// The block loops run ~50 uops per 32 bytes, so the out-of-order window only covers a few cache lines of
+// text: an explicit prefetch this far ahead keeps enough misses in flight (measured on the bench box: the
+// hardware streamer alone leaves the loop latency-bound at ~6 GB/s per thread).
+constexpr int PACK_PREFETCH = 2048;
+
 // Whole 32-byte blocks of sequence text that hold no '>' (a possible record
 // start, left to the byte-wise state machine): every byte that is not a base --
 // line ends, N, IUPAC codes, CR -- is deleted (clean_dna, utils.cpp:675-702)
@@ -148,9 +153,11 @@ static inline const uint8_t *pack_blocks(const uint8_t *p, const uint8_t *end, u
                                           0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
     while (end - p >= 32) {
         const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
-        if (_mm256_movemask_epi8(_mm256_cmpeq_epi8(c, gt))) break;
+        _mm_prefetch(reinterpret_cast<const char *>(p) + PACK_PREFETCH, _MM_HINT_T0);
         const uint32_t okm = (uint32_t)_mm256_movemask_epi8(
             _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), _mm256_and_si256(c, up)));
+        // '>' is not a base: only a block with a deleted byte can hold one
+        if (okm != 0xFFFFFFFFu && _mm256_movemask_epi8(_mm256_cmpeq_epi8(c, gt))) break;
         const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(c, 1), three);
         const __m256i b4 = _mm256_madd_epi16(_mm256_maddubs_epi16(codes, w14), w116);   // byte = c0 + 4 c1 + 16 c2 + 64 c3
         const __m256i pk = _mm256_shuffle_epi8(b4, pick);
@@ -174,6 +181,61 @@ static inline const uint8_t *pack_blocks(const uint8_t *p, const uint8_t *end, u
     return p;
 }
 
+#if defined(__x86_64__)
+// The same block loop with AVX-512 (VBMI2), chosen at run time: 64 bytes per step, validity and '>' as mask
+// registers, VPCOMPRESSB squeezes the deleted bytes out before the codes are formed (no PDEP/PEXT chain), so a
+// step costs about what the 32-byte AVX2 step costs.
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi,avx512vbmi2,bmi,bmi2,lzcnt,popcnt")))
+static const uint8_t *pack_blocks_avx512(const uint8_t *p, const uint8_t *end, uint32_t *w, uint64_t &widx, uint64_t &acc,
+                                         int &fill, uint64_t &nb)
+{
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1));
+    const __m512i up = _mm512_set1_epi8((char)0xDF), three = _mm512_set1_epi8(3), gt = _mm512_set1_epi8('>');
+    const __m512i w14 = _mm512_set1_epi16(0x0401), w116 = _mm512_set1_epi32(0x00100001);
+    while (end - p >= 64) {
+        const __m512i c = _mm512_loadu_si512(p);
+        _mm_prefetch(reinterpret_cast<const char *>(p) + PACK_PREFETCH, _MM_HINT_T0);
+        const uint64_t ok = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, c), _mm512_and_si512(c, up));
+        // '>' is not a base: only a block with a deleted byte can hold one
+        if (ok != ~0ULL && _mm512_cmpeq_epi8_mask(c, gt)) break;
+        const __m512i z = _mm512_maskz_compress_epi8(ok, c);                                // bases first, zeros behind
+        const __m512i codes = _mm512_and_si512(_mm512_srli_epi16(z, 1), three);
+        const __m512i b4 = _mm512_madd_epi16(_mm512_maddubs_epi16(codes, w14), w116);       // byte = c0 + 4 c1 + 16 c2 + 64 c3
+        const __m128i pk = _mm512_cvtepi32_epi8(b4);                                        // code of base j at bits 2j of 128
+        const uint64_t v0 = (uint64_t)_mm_cvtsi128_si64(pk), v1 = (uint64_t)_mm_extract_epi64(pk, 1);
+        const int n = __builtin_popcountll(ok);
+        const int n0 = n < 32 ? 2 * n : 64, n1 = 2 * n - n0;                                // bits taken from v0 / v1
+        acc |= v0 << fill;
+        if (fill + n0 >= 64) {
+            memcpy(w + widx, &acc, 8); widx += 2;
+            acc = fill ? v0 >> (64 - fill) : 0;
+            fill -= 64;
+        }
+        fill += n0;
+        acc |= v1 << fill;                                                                  // v1 == 0 when n1 == 0
+        if (fill + n1 >= 64) {
+            memcpy(w + widx, &acc, 8); widx += 2;
+            acc = fill ? v1 >> (64 - fill) : 0;
+            fill -= 64;
+        }
+        fill += n1;
+        nb += (uint64_t)n;
+        p += 64;
+    }
+    return p;
+}
+
+static bool have_avx512_packer()
+{
+    static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                           __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512vbmi") &&
+                           __builtin_cpu_supports("avx512vbmi2") && !getenv("SPSP_NO_AVX512");
+    return ok;
+}
+#else
+static bool have_avx512_packer() { return false; }
+#endif
+
 void FastaPacker::feed(const uint8_t *p, size_t n)
 {
     if (!n) return;
@@ -184,9 +246,15 @@ void FastaPacker::feed(const uint8_t *p, size_t n)
     uint64_t acc = acc_;
     int fill = fill_;
     uint64_t widx = word_idx_, nb = out_.n_bases;
+    const bool wide = have_avx512_packer();
+    (void)wide;
     while (p < end) {
         if (state_ == SEQ) {
-            const uint8_t *q = pack_blocks(p, end, w, widx, acc, fill, nb);
+            const uint8_t *q = p;
+#if defined(__x86_64__)
+            if (wide) q = pack_blocks_avx512(q, end, w, widx, acc, fill, nb);
+#endif
+            q = pack_blocks(q, end, w, widx, acc, fill, nb);
             if (q != p) {
                 p = q;
                 if (p[-1] == '\n') state_ = LINE_START;          // the blocks ended with a line
