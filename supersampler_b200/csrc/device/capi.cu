@@ -79,6 +79,9 @@ struct Slot {
     bool pending = false;
     bool timed = false;
     // whole-batch path
+    // staged uploads alternate between two copy streams: one copy engine moves ~27 GB/s on this platform, two 55
+    cudaStream_t up_stream[2] = {nullptr, nullptr};
+    cudaEvent_t up_event[2] = {nullptr, nullptr};
     PostpassBuffers *pp = nullptr;
     DenseBuffers *dn = nullptr;
     DevBuf b_rec_begin, b_rec_end, b_rec_input;
@@ -236,6 +239,10 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
         CK(cudaEventCreate(&s.ev0));
         CK(cudaEventCreate(&s.ev1));
         CK(cudaEventCreate(&s.ev2));
+        for (int u = 0; u < 2; u++) {
+            CK(cudaStreamCreateWithFlags(&s.up_stream[u], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s.up_event[u], cudaEventDisableTiming));
+        }
     }
     CK(cudaEventCreate(&c->cev0));
     CK(cudaEventCreate(&c->cev1));
@@ -265,6 +272,10 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
         if (s.ev2) cudaEventDestroy(s.ev2);
+        for (int u = 0; u < 2; u++) {
+            if (s.up_stream[u]) { cudaStreamSynchronize(s.up_stream[u]); cudaStreamDestroy(s.up_stream[u]); }
+            if (s.up_event[u]) cudaEventDestroy(s.up_event[u]);
+        }
         if (s.pp) postpass_buffers_destroy(s.pp);
         if (s.dn) dense_buffers_destroy(s.dn);
         s.b_rec_begin.release(); s.b_rec_end.release(); s.b_rec_input.release();
@@ -675,6 +686,7 @@ extern "C" int spsp_batch_reserve(spsp_ctx *c, int slot, uint64_t total_words)
     CK(cudaSetDevice(c->device));
     Slot &s = c->slots[slot];
     CK(cudaStreamSynchronize(s.stream));          // nothing may still read the old buffer
+    for (int u = 0; u < 2; u++) CK(cudaStreamSynchronize(s.up_stream[u]));
     return ensure_packed(s, total_words);
 }
 
@@ -686,7 +698,9 @@ extern "C" int spsp_batch_upload(spsp_ctx *c, int slot, uint64_t word_off, const
     if (!n_words) return 0;
     if (!host_words) return fail(-3, "spsp_batch_upload: null input");
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(s.d_packed + word_off, host_words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    // consecutive 256 KB pieces alternate between the two copy streams (no shared state: callable from any thread)
+    cudaStream_t up = s.up_stream[(word_off >> 16) & 1];
+    CK(cudaMemcpyAsync(s.d_packed + word_off, host_words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, up));
     return 0;
 }
 
@@ -698,6 +712,10 @@ extern "C" int spsp_sketch_batch_staged(spsp_ctx *c, int slot, uint64_t n_bases,
     Slot &s = c->slots[slot];
     if (spsp_packed_words(n_bases) > s.d_packed_words) return fail(-3, "spsp_sketch_batch_staged: reserve the buffer first");
     CK(cudaSetDevice(c->device));
+    for (int u = 0; u < 2; u++) {                 // the scan waits for every upload queued so far
+        CK(cudaEventRecord(s.up_event[u], s.up_stream[u]));
+        CK(cudaStreamWaitEvent(s.stream, s.up_event[u], 0));
+    }
     return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
 }
 
