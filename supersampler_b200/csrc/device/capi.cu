@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -925,6 +926,10 @@ extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_ou
     const uint32_t W = (uint32_t)c->world, R = (uint32_t)c->rank;
     const bool hi = c->k > 32;
     const uint64_t n_local = s.last_batch_inputs, e_local = s.last_batch.n_elems;
+    static const bool timing = getenv("SPSP_XCHG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp[6] = {0, 0, 0, 0, 0, 0};
+    tp[0] = now();
     // ---- stage A: how many sketches / elements every rank brings
     CK(c->x_hdr.ensure(2 * W * 8)); CK(c->xp_hdr.ensure(2 * W * 8));
     uint64_t *h_hdr = static_cast<uint64_t *>(c->xp_hdr.p);
@@ -934,6 +939,7 @@ extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_ou
     NK(n->AllGather(d_hdr + 2 * R, d_hdr, 2, ncclUint64, c->comm, st));
     CK(cudaMemcpyAsync(h_hdr, d_hdr, 2 * W * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    tp[1] = now();
     uint64_t N = 0, E = 0, n_max = 1, e_max = 1;
     for (uint32_t r = 0; r < W; r++) {
         N += h_hdr[2 * r]; E += h_hdr[2 * r + 1];
@@ -964,6 +970,8 @@ extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_ou
     NK(n->AllGather(d_min + R * e_max, d_min, e_max, ncclUint32, c->comm, st));
     if (hi) NK(n->AllGather(d_khi + R * e_max, d_khi, e_max, ncclUint64, c->comm, st));
     NK(n->GroupEnd());
+    if (timing) { CK(cudaStreamSynchronize(st)); }
+    tp[2] = now();
     // ---- sketch ranges of the union (rank-major), chunk offsets, this rank's tiles
     CK(c->x_begin.ensure(N * 8)); CK(c->x_end.ensure(N * 8)); CK(c->x_compact.ensure(N * 8));
     CK(launch_gathered_ranges(d_hdr, d_sz, W, n_max, e_max, static_cast<uint64_t *>(c->x_begin.p),
@@ -988,6 +996,7 @@ extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_ou
     CK(cudaMemsetAsync(d_out, 0, N * N * 4, st));
     int rc = cmp_run_impl(c, 0, (uint32_t)N, 0, (uint32_t)N, 1, R, W, d_out, N);     // synchronises the stream
     if (rc) return rc;
+    tp[3] = now();
     if (kernel_ms) spsp_cmp_last_kernel_ms(c, kernel_ms);
     // ---- disjoint tiles: the sum over ranks is the gather to rank 0
     NK(n->Reduce(d_out, d_out, N * N, ncclUint32, ncclSum, 0, c->comm, st));
@@ -995,9 +1004,14 @@ extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_ou
     if (R == 0) CK(cudaMemcpyAsync(h_out, d_out, N * N * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_out + N * N * 4, c->x_compact.p, N * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    tp[4] = now();
     if (R == 0)
         for (uint64_t i = 0; i < N; i++) memcpy(inter_out + i * ld, h_out + i * N * 4, N * 4);
     if (sizes_out) memcpy(sizes_out, h_out + N * N * 4, N * 8);
+    tp[5] = now();
+    if (timing && R == 0)
+        fprintf(stderr, "[xchg] counts+sync %.0f us | gather %.0f | ranges+chunks+join %.0f | reduce+D2H %.0f | copy out %.0f\n",
+                tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
     return 0;
 }
 
