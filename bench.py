@@ -185,6 +185,26 @@ def run_reference_step(paths, args, wd, cores):
     return t1 - t0, t2 - t1, t2 - t1, "port"
 
 
+def reference_parity(wd, names, sketches, cmp_res, S):
+    """Byte parity of this step's outputs with the files the unmodified reference just wrote for the same
+    inputs: every gunzipped sketch, and both CSV matrices (`-p 6`).  Checker only, outside any timed region."""
+    import gzip
+    out = {"sketches_identical": 0, "sketches": len(names)}
+    for nm, sk in zip(names, sketches):
+        with gzip.open(os.path.join(wd, "subsampled_" + nm + ".gz"), "rb") as f:
+            out["sketches_identical"] += int(f.read() == sk)
+    inter, sizes, full = cmp_res
+    csv_names = [os.path.join(wd, "subsampled_" + nm + ".gz") for nm in names]
+    for tag, jac in (("containment", False), ("jaccard", True)):
+        with gzip.open(os.path.join(wd, f"res_{tag}.csv.gz"), "rb") as f:
+            ref = f.read()
+        ours = S.format_csv(csv_names, len(names), inter, full, sizes, jac, 6, 0.0)
+        out[f"{tag}_csv_identical"] = bool(ours == ref)
+    out["ok"] = bool(out["sketches_identical"] == out["sketches"] and out["containment_csv_identical"]
+                     and out["jaccard_csv_identical"])
+    return out
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -425,11 +445,21 @@ def b200_arm(args, rank, world, local_rank):
     # CPU baseline on this box's host cores (rank 0, N=1 only): the reference binaries on the same workload
     if world == 1 and not args.no_cpu_baseline:
         wd = scratch_dir()
+        wd_keep = wd
         try:
             paths = write_files(fastas, names, wd)
             a, b, c, kind = run_reference_step(paths, args, wd, cores)
-        finally:
+            for p_ in paths:
+                os.remove(p_)
+        except Exception:
             shutil.rmtree(wd, ignore_errors=True)
+            raise
+        # the same run is the parity check at full size: the reference's files against this step's results
+        parity = None
+        if kind == "reference":
+            parity = reference_parity(wd_keep, names, sks_res, cmp_res, S)
+        line["parity_vs_reference"] = parity
+        shutil.rmtree(wd, ignore_errors=True)
         line["cpu_baseline"] = {"value": total_bases / (a + b) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"full workload once: {args.genomes} x {args.bases} bp, sub_sampler -f -t {cores} "
                                           f"({a:.2f} s) + comparator ({b:.2f} s, single-threaded by construction)",
