@@ -544,3 +544,71 @@ def test_config4_read_sets(oracle):
     for i, (_, st) in enumerate(want):
         assert int(tot[i]) == st["total_superkmers"] and int(sel[i]) == st["selected_kmers"]
     ctx.close()
+
+
+# ---------------------------------------------------------------- randomized inputs
+
+def _random_fasta(rng, n_records):
+    """Adversarial-ish FASTA: random line widths, CRLF, N runs, lower case, tandem repeats, palindromes,
+    short records, empty lines, records without a trailing newline."""
+    out = bytearray()
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for r in range(n_records):
+        kind = int(rng.integers(0, 6))
+        L = int(rng.integers(0, 1500))
+        seq = bytes(rng.choice(list(b"ACGT"), size=L).astype(np.uint8))
+        if kind == 1 and L > 20:                         # tandem repeat
+            u = seq[: int(rng.integers(1, 12))]
+            seq = (u * (L // len(u) + 1))[:L]
+        elif kind == 2 and L > 20:                       # u rc(u) u rc(u)
+            u = seq[: L // 4]
+            seq = (u + u.translate(comp)[::-1]) * 2
+        elif kind == 3:                                  # junk characters that clean_dna deletes
+            seq = bytearray(seq)
+            for _ in range(int(rng.integers(0, 8))):
+                p = int(rng.integers(0, max(1, len(seq))))
+                seq[p:p] = bytes(rng.choice(list(b"NnRYKM-*>x "), size=int(rng.integers(1, 15))).astype(np.uint8))
+            seq = bytes(seq)
+        elif kind == 4:
+            seq = seq.lower()
+        width = int(rng.integers(1, 120))
+        nl = b"\r\n" if rng.integers(0, 4) == 0 else b"\n"
+        out += b">rec%d some text ACGT\n" % r if rng.integers(0, 10) else b">\n"
+        for i in range(0, len(seq), width):
+            line = seq[i:i + width]
+            if line.startswith(b">"):                    # a sequence line must not look like a header
+                line = b"N" + line
+            out += line + nl
+        if rng.integers(0, 6) == 0:
+            out += nl
+    if rng.integers(0, 2):
+        out = out.rstrip(b"\r\n")
+    return bytes(out)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_inputs_all_routes_agree(seed, oracle):
+    """Random (k, m, s, a) and random messy inputs: batch pipeline == per-file route == oracle (bytes),
+    compare counts == oracle, dense totals == oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    m = int(rng.choice([3, 5, 7, 9, 11, 13, 15]))
+    k = int(rng.choice([x for x in (15, 17, 21, 27, 31, 33, 41, 63) if x > m + 1]))
+    s = float(rng.choice([1, 1.5, 2, 3, 5, 10, 30, 100]))
+    a = int(rng.choice([1, 1, 1, 2]))
+    fas = [_random_fasta(rng, int(rng.integers(1, 40))) for _ in range(int(rng.integers(1, 7)))]
+    want = [oracle.sketch(f, k, m, s, a) for f in fas]
+    pl = S.Pipeline(k, m, s, a, threads=3)
+    got = pl.sketch(fas)
+    assert got == [w[0] for w in want], (k, m, s, a)
+    assert S.sketch_buffers(fas, k, m, s, a, threads=2) == got
+    inter, sizes, _ = pl.compare()
+    o_inter, o_sizes, _, _ = oracle.compare(got)
+    assert np.array_equal(sizes, o_sizes)
+    assert np.array_equal(np.triu(inter, 1), np.triu(o_inter, 1))
+    ws, ros = zip(*[(lambda r: (r[0], r[2]))(S.pack_fasta(f, k)) for f in fas])
+    words, nb, rb, re_, ri = S.batch_layout(list(ws), list(ros))
+    tot, sel = pl.device_context().dense_stats(words, nb, rb, re_, ri, len(fas))
+    for i, (_, st) in enumerate(want):
+        assert int(tot[i]) == st["total_superkmers"], (k, m, s, i)
+        assert int(sel[i]) == st["selected_kmers"]
+    pl.close()

@@ -174,3 +174,40 @@ def test_sort_csv_matches_reference(tmp_path):
         out = tmp_path / ("sorted_" + src + ".csv")
         assert S.run_sort_csv([str(tmp_path / src), str(out), str(tmp_path / "names.txt")]) == 0
         assert out.read_bytes() == want
+
+
+def test_packer_random_messy_inputs(oracle):
+    """Random line widths, CRLF, junk bytes, '>' inside lines, empty records: packer == clean_dna restatement,
+    for the AVX-512 and the AVX2 block loops and for sliced feeding."""
+    import subprocess, sys
+    from tests.test_gpu_parity import _random_fasta
+    for seed in range(25):
+        rng = np.random.default_rng(seed)
+        fa = _random_fasta(rng, int(rng.integers(1, 40)))
+        for k in (1, 31):
+            words, nb, offs = S.pack_fasta(fa, k)
+            bases, o = oracle.clean(fa)
+            keep = [(int(o[i]), int(o[i + 1])) for i in range(len(o) - 1) if int(o[i + 1]) - int(o[i]) >= k]
+            want = np.concatenate([bases[a:b] for a, b in keep]) if keep else np.zeros(0, np.uint8)
+            assert nb == want.size, (seed, k)
+            assert np.array_equal(unpack(words, nb), want), (seed, k)
+            assert list(np.diff(offs.astype(np.int64))) == [b - a for a, b in keep]
+    # the same check with the AVX-512 loop disabled (run-time dispatch is decided once per process)
+    code = ("import numpy as np, supersampler_b200 as S\n"
+            "from tests.test_gpu_parity import _random_fasta\n"
+            "import hashlib\n"
+            "h = hashlib.sha256()\n"
+            "for seed in range(25):\n"
+            "    rng = np.random.default_rng(seed)\n"
+            "    fa = _random_fasta(rng, int(rng.integers(1, 40)))\n"
+            "    w, nb, o = S.pack_fasta(fa, 31)\n"
+            "    h.update(w.tobytes()); h.update(o.tobytes())\n"
+            "print(h.hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env_extra in ({}, {"SPSP_NO_AVX512": "1"}):
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1]
