@@ -284,11 +284,17 @@ def b200_arm(args, rank, world, local_rank):
     total_bases_rank = sum(args.bases for _ in fastas)
     n_in = len(fastas)
 
+    # Both paths run the batches of consecutive steps one-deep pipelined, as a long job would: two device
+    # contexts on the GPU; while one sketches batch i+1 the other finishes the compare stage of batch i on a
+    # background thread (BatchStream).  Every step still is one full pass (sketch + compare) over its batch; the
+    # last compare is drained inside the timed region.  --no-pipelining runs the stages back to back.
+    from concurrent.futures import ThreadPoolExecutor
+    depth = 1 if args.no_pipelining else 2
     # host-buffer path: the public pipeline (pack on host threads -> pinned -> H2D -> scan -> post-pass -> compare)
-    pipe = S.Pipeline(k, m, s, device=local_rank, threads=threads)
-    pctx = pipe.device_context()
-    # device-resident path: a context of its own; all genomes packed back to back, R replicas in HBM
-    dctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
+    pipes = [S.Pipeline(k, m, s, device=local_rank, threads=threads) for _ in range(depth)]
+    pctxs = [p_.device_context() for p_ in pipes]
+    # device-resident path: contexts of their own; all genomes packed back to back, R replicas in HBM
+    dctxs = [S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank) for _ in range(depth)]
     ws, ros = [], []
     for fa in fastas:
         w, nb, offs = S.pack_fasta(fa, k)
@@ -305,69 +311,113 @@ def b200_arm(args, rank, world, local_rank):
              "d2h": 0, "e2e": []}
 
     if dist is not None:
-        D.join_contexts(dctx, rank, world)
-        D.join_contexts(pctx, rank, world)
+        for c_ in dctxs + pctxs:
+            D.join_contexts(c_, rank, world)
     use_native = os.environ.get("SPSP_BENCH_TORCH_EXCHANGE", "0") != "1"
 
     def compare_device(ctx, elem_off, cinfo):
         """Compare stage from the elements the batch left on `ctx`'s device."""
+        t0 = time.perf_counter()
         if dist is not None and use_native:
-            return D.native_exchange_compare(ctx, n_in, rank, world, cinfo)
-        if dist is None:
+            res = D.native_exchange_compare(ctx, n_in, rank, world, cinfo)
+        elif dist is None:
             l0 = ctx.launches()
             ctx.cmp_load_batch()
             inter = ctx.cmp_run((0, n_in), (0, n_in), True)
             cinfo.update(kernel_ms=ctx.cmp_kernel_ms(), launches=ctx.launches() - l0)
-            return inter, np.diff(np.asarray(elem_off, np.uint64)), False
-        return D.allgather_compare_device(elem_off, ctx, rank, world, cinfo)
-
-    def resident_step(i, record):
-        t0 = time.perf_counter()
-        info, cinfo = {}, {}
-        l0 = dctx.launches()
-        sks = dctx.sketch_batch(None, n_total, rec_begin, rec_end, rec_input, n_in, s,
-                                device_ptr=d_packed[i % replicas].data_ptr(), info=info)
-        nl = dctx.launches() - l0
-        t1 = time.perf_counter()
-        res = compare_device(dctx, info["elem_off"], cinfo)
-        t2 = time.perf_counter()
-        if record:
-            stats["scan_ms"].append(info["scan_ms"]); stats["post_ms"].append(info["post_ms"])
-            stats["cmp_ms"].append(cinfo.get("kernel_ms", 0.0))
-            stats["hits"] = info["n_hits"]
-            stats["launches"] += nl + cinfo.get("launches", 0)
-            stats["sketch_s"].append(t1 - t0); stats["compare_s"].append(t2 - t1)
-            stats["d2h"] = sum(len(x) for x in sks) + (res[0].size * 4 if res[0] is not None else 0)
-        return sks, res
-
-    def e2e_step(i, record):
-        info, cinfo = {}, {}
-        sks = pipe.sketch(fastas, info=info)
-        if dist is None:
-            res = pipe.compare(info=cinfo)
+            res = inter, np.diff(np.asarray(elem_off, np.uint64)), False
         else:
-            off, on_dev = pipe.elem_off()
-            assert on_dev
-            res = compare_device(pctx, off, cinfo)
-        if record:
-            info["cmp_kernel_ms"] = cinfo.get("kernel_ms"); info["launches"] += cinfo.get("launches", 0)
-            info["d2h_bytes"] += res[0].size * 4 if res[0] is not None else 0
-            stats["e2e"].append(info)
-        return sks, res
+            res = D.allgather_compare_device(elem_off, ctx, rank, world, cinfo)
+        cinfo["seconds"] = time.perf_counter() - t0
+        return res
 
-    def timed(fn, steps, warmup, ctx):
-        """K steps bracketed by barrier + synchronize; CUDA events on the stream the kernels are launched on;
-        every step ends with a device->host read of its result, so wall time >= device time."""
+    class Resident:
+        """Device-resident steps: sketch of batch i on context i % depth, its compare on the background thread."""
+
+        def __init__(self):
+            self.pool = ThreadPoolExecutor(1)
+            self.pending = None
+
+        def finish(self, record):
+            if self.pending is None:
+                return None
+            sks, fut, info, cinfo, nl, t_sk = self.pending
+            self.pending = None
+            res = fut.result()
+            if record:
+                stats["scan_ms"].append(info["scan_ms"]); stats["post_ms"].append(info["post_ms"])
+                stats["cmp_ms"].append(cinfo.get("kernel_ms", 0.0))
+                stats["hits"] = info["n_hits"]
+                stats["launches"] += nl + cinfo.get("launches", 0)
+                stats["sketch_s"].append(t_sk); stats["compare_s"].append(cinfo["seconds"])
+                stats["d2h"] = sum(len(x) for x in sks) + (res[0].size * 4 if res[0] is not None else 0)
+            return sks, res
+
+        def step(self, i, record):
+            ctx = dctxs[i % depth]
+            t0 = time.perf_counter()
+            info, cinfo = {}, {}
+            l0 = ctx.launches()
+            sks = ctx.sketch_batch(None, n_total, rec_begin, rec_end, rec_input, n_in, s,
+                                   device_ptr=d_packed[i % replicas].data_ptr(), info=info)
+            nl = ctx.launches() - l0
+            t_sk = time.perf_counter() - t0
+            out = self.finish(record)                       # compare of the previous batch ran meanwhile
+            fut = self.pool.submit(compare_device, ctx, info["elem_off"], cinfo)
+            self.pending = (sks, fut, info, cinfo, nl, t_sk)
+            if depth == 1:
+                out = self.finish(record)
+            return out
+
+    class HostBuffers:
+        """e2e steps through the public API: BatchStream over the two pipelines."""
+
+        def __init__(self):
+            def cmp_fn(pl, cinfo):
+                if dist is None:
+                    return pl.compare(info=cinfo)
+                off, on_dev = pl.elem_off()
+                assert on_dev
+                return compare_device(pctxs[pipes.index(pl)], off, cinfo)
+            self.stream = S.BatchStream(k, m, s, compare_fn=cmp_fn, pipelines=pipes + (pipes if depth == 1 else []))
+
+        @staticmethod
+        def _note(done, record):
+            if done is None:
+                return None
+            sks, res, info, cinfo = done
+            if record:
+                info["cmp_kernel_ms"] = cinfo.get("kernel_ms"); info["launches"] += cinfo.get("launches", 0)
+                info["d2h_bytes"] += res[0].size * 4 if res[0] is not None else 0
+                stats["e2e"].append(info)
+            return sks, res
+
+        def step(self, i, record):
+            out = self._note(self.stream.submit(fastas), record)
+            if depth == 1:
+                out = self._note(self.stream.drain(), record)
+            return out
+
+        def finish(self, record):
+            return self._note(self.stream.drain(), record)
+
+    def timed(runner, steps, warmup, ctx):
+        """K steps bracketed by barrier + synchronize; CUDA events on a stream the kernels are launched on;
+        the pipeline is drained inside the timed region (every step's results have reached the host)."""
         ext = torch.cuda.ExternalStream(ctx.stream(0))
         for i in range(warmup):
-            fn(i, False)
+            runner.step(i, False)
+        runner.finish(False)
         barrier(); torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record(ext)
         out = None
         for i in range(steps):
-            out = fn(warmup + i, True)
+            o = runner.step(warmup + i, True)
+            out = o if o is not None else out
+        o = runner.finish(True)
+        out = o if o is not None else out
         ev1.record(ext)
         torch.cuda.synchronize(); barrier()
         wall = time.perf_counter() - t0
@@ -382,8 +432,8 @@ def b200_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    t_res, (sks_res, cmp_res) = timed(resident_step, args.steps, args.warmup, dctx)
-    t_e2e, (sks_e2e, cmp_e2e) = timed(e2e_step, args.steps, args.warmup, pctx)
+    t_res, (sks_res, cmp_res) = timed(Resident(), args.steps, args.warmup, dctxs[0])
+    t_e2e, (sks_e2e, cmp_e2e) = timed(HostBuffers(), args.steps, args.warmup, pctxs[0])
     clocks = sampler.stop() if rank == 0 else None
 
     # both paths must produce the same bytes / counts
@@ -393,7 +443,8 @@ def b200_arm(args, rank, world, local_rank):
         assert np.array_equal(cmp_res[0], cmp_e2e[0])
     if dist is not None and use_native:
         # the exchange inside the C ABI must give what the torch.distributed exchange gives
-        chk = D.allgather_compare_device(pipe.elem_off()[0], pctx, rank, world, {})
+        last = pipes[(args.warmup + args.steps - 1) % depth]
+        chk = D.allgather_compare_device(last.elem_off()[0], pctxs[pipes.index(last)], rank, world, {})
         assert np.array_equal(chk[1], cmp_res[1])
         if rank == 0:
             assert np.array_equal(np.triu(chk[0], 1), np.triu(cmp_res[0], 1)), "native and torch exchange disagree"
@@ -426,7 +477,9 @@ def b200_arm(args, rank, world, local_rank):
                               "assemble": mean("assemble_s") * 1e3, "scan_kernel": mean("scan_ms"),
                               "postpass_device": mean("post_ms"), "compare_kernel": mean("cmp_kernel_ms")},
                 "gpu_launches": int(sum(x["launches"] for x in e2)),
-                "api": "supersampler_b200.Pipeline.sketch(FASTA bytes in host memory) + .compare()"},
+                "api": "supersampler_b200.BatchStream.submit(FASTA bytes in host memory) over two Pipelines "
+                       "(.sketch() + .compare(), the compare of batch i overlapping the sketch of batch i+1)"},
+        "pipelining": "off" if depth == 1 else "one batch deep: compare(i) on a background thread / second context while sketch(i+1) runs",
         "gpu_launches": stats["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(n_total)[0], "traffic_source": measured_traffic(n_total)[1],
@@ -485,6 +538,7 @@ def main():
     ap.add_argument("-m", type=int, default=11)
     ap.add_argument("-s", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipelining", action="store_true", help="run sketch and compare of a step back to back")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

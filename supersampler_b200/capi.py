@@ -392,6 +392,54 @@ class Pipeline:
         return DeviceContext._borrow(self.L.spsph_pipeline_ctx(self.h), self.k, self.m)
 
 
+class BatchStream:
+    """A stream of batches through two `Pipeline`s (two device contexts on one GPU): the compare stage of
+    batch i runs on a background thread while batch i+1 is being packed, copied and sketched, so a long job
+    pays for the compare stage only once, at the end.  `submit(inputs)` returns the finished result of the
+    PREVIOUS batch (None for the first), `drain()` the last one.  A result is
+    (sketches, (inter, sizes, full_rows), sketch_info, compare_info).
+
+    compare_fn(pipeline, info) -> (inter, sizes, full_rows) replaces the single-GPU `pipeline.compare` (the
+    multi-GPU exchange is plugged in here)."""
+
+    def __init__(self, k: int = 31, m: int = 11, s: float = 1000.0, abundance: int = 1, device: int = 0,
+                 threads: int = 8, compare_fn=None, pipelines: Optional[Sequence["Pipeline"]] = None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.pipes = list(pipelines) if pipelines else [Pipeline(k, m, s, abundance, device, threads) for _ in range(2)]
+        self._own = not pipelines
+        self.compare_fn = compare_fn or (lambda pl, info: pl.compare(info=info))
+        self.pool = ThreadPoolExecutor(1)
+        self.pending = None
+        self.n = 0
+
+    def submit(self, inputs: Sequence):
+        pl = self.pipes[self.n % 2]
+        self.n += 1
+        info, cinfo = {}, {}
+        sks = pl.sketch(inputs, info=info)               # overlaps the compare of the previous batch
+        prev = self._finish()
+        fut = self.pool.submit(self.compare_fn, pl, cinfo)
+        self.pending = (sks, fut, info, cinfo)
+        return prev
+
+    def _finish(self):
+        if self.pending is None:
+            return None
+        sks, fut, info, cinfo = self.pending
+        self.pending = None
+        return sks, fut.result(), info, cinfo
+
+    def drain(self):
+        return self._finish()
+
+    def close(self):
+        self._finish()
+        self.pool.shutdown()
+        if self._own:
+            for pl in self.pipes:
+                pl.close()
+
+
 def postpass_batch(packed: np.ndarray, base_off: np.ndarray, n_bases: np.ndarray, rec_off: np.ndarray,
                    rec_first: np.ndarray, hits: np.ndarray, k: int, m: int, s: float, abundance: int = 1,
                    threads: int = 8) -> List[bytes]:
