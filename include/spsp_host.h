@@ -117,6 +117,13 @@ int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t bases);
 int spsph_pipeline_sketch(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
                           const char *const *paths, uint8_t **out, size_t *out_len, int *ok, double *stats,
                           uint64_t *launches);
+/* spsph_pipeline_sketch in two halves, to overlap jobs on two pipelines: _pack prepares, packs and queues the
+ * H2D copies (returns when the host work is done; the inputs may be released then); _finish runs the device
+ * phase and delivers the results of that job (same n). */
+int spsph_pipeline_pack(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
+                        const char *const *paths);
+int spsph_pipeline_finish(spsph_pipeline *p, uint32_t n, uint8_t **out, size_t *out_len, int *ok, double *stats,
+                          uint64_t *launches);
 /* Element offsets (n + 1 entries) of the last spsph_pipeline_sketch call; *on_device = 1 when the
  * elements are still resident on the GPU (single batch: spsp_batch_elements on slot 0 of spsph_pipeline_ctx). */
 int spsph_pipeline_elem_off(spsph_pipeline *p, uint64_t *off, int *on_device);

@@ -163,6 +163,10 @@ def host_lib():
         L.spsph_pipeline_sketch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
                                             C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                             C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.spsph_pipeline_pack.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                          C.POINTER(C.c_char_p)]
+        L.spsph_pipeline_finish.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                            C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.spsph_pipeline_elem_off.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.spsph_pipeline_compare.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                              C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
@@ -344,19 +348,15 @@ class Pipeline:
         except Exception:
             pass
 
-    def sketch(self, inputs: Sequence, info: Optional[dict] = None) -> List[Optional[bytes]]:
-        """-> sketch bytes (before gzip) per input; None for a file that cannot be opened."""
+    @staticmethod
+    def _marshal(inputs):
         n = len(inputs)
         data = (C.c_char_p * n)(*[x if isinstance(x, (bytes, bytearray)) else None for x in inputs])
         lens = (C.c_size_t * n)(*[len(x) if isinstance(x, (bytes, bytearray)) else 0 for x in inputs])
         paths = (C.c_char_p * n)(*[os.fsencode(x) if not isinstance(x, (bytes, bytearray)) else None for x in inputs])
-        outs = (C.c_void_p * n)()
-        olens = (C.c_size_t * n)()
-        ok = (C.c_int * n)()
-        st = (C.c_double * 12)()
-        nl = C.c_uint64()
-        _hcheck(self.L.spsph_pipeline_sketch(self.h, n, data, lens, paths, outs, olens, ok, st, C.byref(nl)),
-                "pipeline_sketch")
+        return n, data, lens, paths
+
+    def _collect(self, n, outs, olens, ok, st, nl, info):
         res = []
         for i in range(n):
             res.append((C.string_at(outs[i], olens[i]) if olens[i] else b"") if ok[i] else None)
@@ -366,6 +366,29 @@ class Pipeline:
             info.update({k_: float(st[i]) for i, k_ in enumerate(self.STAT_NAMES)})
             info["launches"] = int(nl.value)
         return res
+
+    def sketch(self, inputs: Sequence, info: Optional[dict] = None) -> List[Optional[bytes]]:
+        """-> sketch bytes (before gzip) per input; None for a file that cannot be opened."""
+        n, data, lens, paths = self._marshal(inputs)
+        outs, olens, ok = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        st, nl = (C.c_double * 12)(), C.c_uint64()
+        _hcheck(self.L.spsph_pipeline_sketch(self.h, n, data, lens, paths, outs, olens, ok, st, C.byref(nl)),
+                "pipeline_sketch")
+        return self._collect(n, outs, olens, ok, st, nl, info)
+
+    def pack(self, inputs: Sequence) -> None:
+        """First half of sketch(): prepare, pack, queue the copies.  Returns when the host work is done."""
+        n, data, lens, paths = self._marshal(inputs)
+        _hcheck(self.L.spsph_pipeline_pack(self.h, n, data, lens, paths), "pipeline_pack")
+        self._n_packed = n
+
+    def finish(self, info: Optional[dict] = None) -> List[Optional[bytes]]:
+        """Second half of sketch(): device phase of the job pack() started."""
+        n = self._n_packed
+        outs, olens, ok = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        st, nl = (C.c_double * 12)(), C.c_uint64()
+        _hcheck(self.L.spsph_pipeline_finish(self.h, n, outs, olens, ok, st, C.byref(nl)), "pipeline_finish")
+        return self._collect(n, outs, olens, ok, st, nl, info)
 
     def compare(self, query_size: Optional[int] = None, info: Optional[dict] = None):
         """Compare the sketches of the last sketch() call -> (inter[rows, n], sizes[n], full_rows)."""
@@ -393,9 +416,9 @@ class Pipeline:
 
 
 class BatchStream:
-    """A stream of batches through two `Pipeline`s (two device contexts on one GPU): the compare stage of
-    batch i runs on a background thread while batch i+1 is being packed, copied and sketched, so a long job
-    pays for the compare stage only once, at the end.  `submit(inputs)` returns the finished result of the
+    """A stream of batches through two `Pipeline`s (two device contexts on one GPU): the device phase (scan +
+    post-pass) and the compare stage of batch i run on a background thread while the host threads clean, pack
+    and copy batch i+1, so a long job is bound by its slower half instead of their sum.  `submit(inputs)` returns the finished result of the
     PREVIOUS batch (None for the first), `drain()` the last one.  A result is
     (sketches, (inter, sizes, full_rows), sketch_info, compare_info).
 
@@ -415,19 +438,22 @@ class BatchStream:
     def submit(self, inputs: Sequence):
         pl = self.pipes[self.n % 2]
         self.n += 1
-        info, cinfo = {}, {}
-        sks = pl.sketch(inputs, info=info)               # overlaps the compare of the previous batch
+        pl.pack(inputs)                                  # host half; the previous batch's device half + compare run meanwhile
         prev = self._finish()
-        fut = self.pool.submit(self.compare_fn, pl, cinfo)
-        self.pending = (sks, fut, info, cinfo)
+        self.pending = self.pool.submit(self._back_half, pl)
         return prev
+
+    def _back_half(self, pl):
+        info, cinfo = {}, {}
+        sks = pl.finish(info=info)
+        res = self.compare_fn(pl, cinfo)
+        return sks, res, info, cinfo
 
     def _finish(self):
         if self.pending is None:
             return None
-        sks, fut, info, cinfo = self.pending
-        self.pending = None
-        return sks, fut.result(), info, cinfo
+        fut, self.pending = self.pending, None
+        return fut.result()
 
     def drain(self):
         return self._finish()

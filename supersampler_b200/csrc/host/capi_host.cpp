@@ -293,6 +293,8 @@ extern "C" int spsph_compare_buffers(int n_gpus, uint32_t n, uint32_t query_size
 struct spsph_pipeline {
     std::shared_ptr<DeviceSession> session;
     std::unique_ptr<BatchSketcher> bs;
+    uint64_t l0 = 0;
+    uint32_t n_pending = 0;
 };
 
 extern "C" int spsph_pipeline_create(int device, int k, int m, double s, unsigned abundance, int threads,
@@ -322,35 +324,78 @@ extern "C" int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t ba
     return 0;
 }
 
+static int pipeline_sources(uint32_t n, const uint8_t *const *fasta, const size_t *len, const char *const *paths,
+                            std::vector<BatchSource> &src)
+{
+    src.assign(n, BatchSource());
+    for (uint32_t i = 0; i < n; i++) {
+        if (fasta && fasta[i]) { src[i].data = fasta[i]; src[i].len = len[i]; }
+        else if (paths && paths[i]) src[i].path = paths[i];
+        else return hfail("input without data and without path");
+    }
+    return 0;
+}
+
+static void pipeline_deliver(spsph_pipeline *p, uint32_t n, std::vector<std::vector<uint8_t>> &sk, std::vector<char> &okv,
+                             uint8_t **out, size_t *out_len, int *ok, double *stats)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        out[i] = dup_vec(sk[i].data(), sk[i].size());
+        out_len[i] = sk[i].size();
+        if (ok) ok[i] = okv[i];
+    }
+    if (stats) {
+        const BatchStats &st = p->bs->stats;
+        stats[0] = st.prep_s; stats[1] = st.pack_s; stats[2] = st.device_s; stats[3] = st.assemble_s;
+        stats[4] = st.scan_ms; stats[5] = st.post_ms; stats[6] = (double)st.hits; stats[7] = (double)st.elems;
+        stats[8] = (double)st.h2d_bytes; stats[9] = (double)st.d2h_bytes; stats[10] = (double)st.batches;
+        stats[11] = (double)st.bases;
+    }
+}
+
 extern "C" int spsph_pipeline_sketch(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
                                      const char *const *paths, uint8_t **out, size_t *out_len, int *ok, double *stats,
                                      uint64_t *launches)
 {
     try {
         if (!p) return hfail("null pipeline");
-        std::vector<BatchSource> src(n);
-        for (uint32_t i = 0; i < n; i++) {
-            if (fasta && fasta[i]) { src[i].data = fasta[i]; src[i].len = len[i]; }
-            else if (paths && paths[i]) src[i].path = paths[i];
-            else return hfail("input without data and without path");
-        }
+        std::vector<BatchSource> src;
+        if (pipeline_sources(n, fasta, len, paths, src)) return -1;
         const uint64_t l0 = p->session->launches();
         std::vector<std::vector<uint8_t>> sk;
         std::vector<char> okv;
         p->bs->run(src, sk, okv);
-        for (uint32_t i = 0; i < n; i++) {
-            out[i] = dup_vec(sk[i].data(), sk[i].size());
-            out_len[i] = sk[i].size();
-            if (ok) ok[i] = okv[i];
-        }
-        if (stats) {
-            const BatchStats &st = p->bs->stats;
-            stats[0] = st.prep_s; stats[1] = st.pack_s; stats[2] = st.device_s; stats[3] = st.assemble_s;
-            stats[4] = st.scan_ms; stats[5] = st.post_ms; stats[6] = (double)st.hits; stats[7] = (double)st.elems;
-            stats[8] = (double)st.h2d_bytes; stats[9] = (double)st.d2h_bytes; stats[10] = (double)st.batches;
-            stats[11] = (double)st.bases;
-        }
+        pipeline_deliver(p, n, sk, okv, out, out_len, ok, stats);
         if (launches) *launches = p->session->launches() - l0;
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_pipeline_pack(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
+                                   const char *const *paths)
+{
+    try {
+        if (!p) return hfail("null pipeline");
+        std::vector<BatchSource> src;
+        if (pipeline_sources(n, fasta, len, paths, src)) return -1;
+        p->l0 = p->session->launches();
+        p->n_pending = n;
+        p->bs->begin(src);
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
+extern "C" int spsph_pipeline_finish(spsph_pipeline *p, uint32_t n, uint8_t **out, size_t *out_len, int *ok, double *stats,
+                                     uint64_t *launches)
+{
+    try {
+        if (!p) return hfail("null pipeline");
+        if (n != p->n_pending) return hfail("spsph_pipeline_finish: n differs from the packed job");
+        std::vector<std::vector<uint8_t>> sk;
+        std::vector<char> okv;
+        p->bs->finish(sk, okv);
+        pipeline_deliver(p, n, sk, okv, out, out_len, ok, stats);
+        if (launches) *launches = p->session->launches() - p->l0;
         return 0;
     } catch (const std::exception &e) { return hfail(e.what()); }
 }

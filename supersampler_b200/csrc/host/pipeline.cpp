@@ -134,6 +134,16 @@ struct BatchSketcher::Prepared {
     std::vector<uint64_t> rec_off;
 };
 
+struct BatchSketcher::Job {
+    std::vector<Prepared> prep;
+    std::vector<std::vector<uint8_t>> sketches;
+    std::vector<char> ok;
+    size_t first = 0, last = 0;
+    bool device_pending = false;
+    uint64_t total_words = 0;
+    std::chrono::steady_clock::time_point t_packed;
+};
+
 BatchSketcher::BatchSketcher(std::shared_ptr<DeviceSession> session, int k, int m, double s, unsigned abundance, int threads)
     : session_(std::move(session)), pool_(threads), k_(k), m_(m), threads_(threads < 1 ? 1 : threads), s_(s),
       abundance_(abundance)
@@ -153,6 +163,16 @@ static bool file_is_gzip(int fd)
 
 void BatchSketcher::run(const std::vector<BatchSource> &src, std::vector<std::vector<uint8_t>> &sketches, std::vector<char> &ok)
 {
+    begin(src);
+    finish(sketches, ok);
+}
+
+void BatchSketcher::begin(const std::vector<BatchSource> &src)
+{
+    job_.reset(new Job());
+    std::vector<std::vector<uint8_t>> &sketches = job_->sketches;
+    std::vector<char> &ok = job_->ok;
+    std::vector<Prepared> &prep = job_->prep;
     stats = BatchStats();
     const size_t n = src.size();
     sketches.assign(n, std::vector<uint8_t>());
@@ -169,7 +189,7 @@ void BatchSketcher::run(const std::vector<BatchSource> &src, std::vector<std::ve
 
     // ---- prepare: sizes; gzip inputs are inflated here (their size is unknown before)
     auto t0 = clk::now();
-    std::vector<Prepared> prep(n);
+    prep.assign(n, Prepared());
     pool_.run(n, [&](size_t i) {
         Prepared &p = prep[i];
         if (src[i].data) { p.len = src[i].len; return; }
@@ -207,14 +227,33 @@ void BatchSketcher::run(const std::vector<BatchSource> &src, std::vector<std::ve
         acc += need;
     }
     batches.emplace_back(first, n);
-    const bool multi = batches.size() > 1;
-    for (auto &b : batches) run_batch(src, prep, b.first, b.second, sketches, multi);
-    elems_on_device_ = !multi;
     stats.batches = batches.size();
+    if (batches.size() == 1) {
+        // the usual case: host half now, device half in finish()
+        pack_batch(src, prep, 0, n);
+        job_->first = 0; job_->last = n;
+        job_->device_pending = true;
+        return;
+    }
+    for (auto &b : batches) {
+        pack_batch(src, prep, b.first, b.second);
+        device_batch(prep, b.first, b.second, sketches, true);
+    }
 }
 
-void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last,
-                              std::vector<std::vector<uint8_t>> &sketches, bool keep_host_elems)
+void BatchSketcher::finish(std::vector<std::vector<uint8_t>> &sketches, std::vector<char> &ok)
+{
+    if (!job_) throw std::runtime_error("BatchSketcher::finish without begin");
+    if (job_->device_pending) {
+        device_batch(job_->prep, job_->first, job_->last, job_->sketches, false);
+        elems_on_device_ = true;
+    }
+    sketches.swap(job_->sketches);
+    ok.swap(job_->ok);
+    job_.reset();
+}
+
+void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last)
 {
     spsp_ctx *ctx = session_->ctx();
     const size_t nb = last - first;
@@ -288,6 +327,17 @@ void BatchSketcher::run_batch(const std::vector<BatchSource> &src, std::vector<P
     });
     auto t1 = clk::now();
     stats.pack_s += secs(t0, t1);
+    job_->total_words = total_words;
+    job_->t_packed = t1;
+}
+
+void BatchSketcher::device_batch(std::vector<Prepared> &prep, size_t first, size_t last,
+                                 std::vector<std::vector<uint8_t>> &sketches, bool keep_host_elems)
+{
+    spsp_ctx *ctx = session_->ctx();
+    const size_t nb = last - first;
+    const uint64_t total_words = job_->total_words, n_total = 16 * total_words;
+    auto t1 = clk::now();                                 // (not t_packed: the caller may have waited in between)
 
     // ---- records of the batch, ascending
     std::vector<uint64_t> rb, re;

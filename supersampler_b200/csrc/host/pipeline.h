@@ -59,6 +59,12 @@ public:
     // Sketch bytes (before gzip) of every source, in order.  ok[i] = 0 for a file that
     // cannot be opened (its sketch stays empty), like SubSampler.cpp:313-322.
     void run(const std::vector<BatchSource> &src, std::vector<std::vector<uint8_t>> &sketches, std::vector<char> &ok);
+    // The same in two halves, so that a caller can overlap them across jobs (another BatchSketcher can pack the
+    // next job while this one's device phase runs): begin() prepares, packs and queues the copies and returns
+    // as soon as the host work is done; finish() runs the device phase and delivers what run() delivers.
+    // `src` must stay valid until begin() returns.  A job that needs several batches is run entirely by begin().
+    void begin(const std::vector<BatchSource> &src);
+    void finish(std::vector<std::vector<uint8_t>> &sketches, std::vector<char> &ok);
 
     // All-vs-all (query_size >= n) or query-vs-all compare of the sketches of the last
     // run(), starting from the elements the batch left on the device (several batches:
@@ -81,8 +87,11 @@ public:
 
 private:
     struct Prepared;
-    void run_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last,
-                   std::vector<std::vector<uint8_t>> &sketches, bool keep_host_elems);
+    struct Job;
+    void pack_batch(const std::vector<BatchSource> &src, std::vector<Prepared> &prep, size_t first, size_t last);
+    void device_batch(std::vector<Prepared> &prep, size_t first, size_t last, std::vector<std::vector<uint8_t>> &sketches,
+                      bool keep_host_elems);
+    std::unique_ptr<Job> job_;                 // between begin() and finish()
     std::shared_ptr<DeviceSession> session_;
     WorkerPool pool_;
     int k_, m_, threads_;

@@ -612,3 +612,33 @@ def test_random_inputs_all_routes_agree(seed, oracle):
         assert int(tot[i]) == st["total_superkmers"], (k, m, s, i)
         assert int(sel[i]) == st["selected_kmers"]
     pl.close()
+
+
+def test_batch_stream_overlapped_jobs(oracle):
+    """BatchStream: pack of job i+1 overlaps the device phase + compare of job i on a second pipeline; every
+    job's sketches and counts equal the plain Pipeline's (and the oracle's)."""
+    k, m, s = 31, 11, 50
+    jobs = []
+    for j in range(5):
+        fam = [synth.fasta_bytes([(nm, g)]) for nm, g in synth.genome_family(5 + j, 40_000 + 7_000 * j, seed=30 + j)]
+        if j == 2:
+            fam.append(build_input("nasty"))
+        jobs.append(fam)
+    stream = S.BatchStream(k, m, s, threads=4)
+    results = []
+    for job in jobs:
+        done = stream.submit(job)
+        if done is not None:
+            results.append(done)
+    results.append(stream.drain())
+    assert stream.drain() is None
+    stream.close()
+    assert len(results) == len(jobs)
+    pl = S.Pipeline(k, m, s, threads=2)
+    for job, (sks, (inter, sizes, full), info, cinfo) in zip(jobs, results):
+        assert sks == pl.sketch(job)
+        assert sks[0] == oracle.sketch(job[0], k, m, s)[0]
+        i2, s2, f2 = pl.compare()
+        assert np.array_equal(inter, i2) and np.array_equal(sizes, s2) and full == f2
+        assert info["launches"] > 0 and cinfo["launches"] > 0
+    pl.close()
