@@ -137,12 +137,24 @@ hashjoin_kernel(CmpData d, const uint2 *__restrict__ tiles, uint32_t n_chunks, u
                 if (i_sk >= row_end) continue;
                 const uint64_t ib = d.chunk_off[(uint64_t)i_sk * (n_chunks + 1) + c];
                 const uint64_t ie = d.chunk_off[(uint64_t)i_sk * (n_chunks + 1) + c + 1];
+                // software pipeline: the next 32 row elements are requested before the current ones are probed
+                uint64_t n_lo = 0, n_hi = 0;
+                uint32_t n_mn = 0;
+                if (ib + lane < ie) {
+                    n_lo = d.klo[ib + lane]; n_mn = d.minim[ib + lane];
+                    if (HAS_HI) n_hi = d.khi[ib + lane];
+                }
                 for (uint64_t e0 = ib; e0 < ie; e0 += 32) {
+                    const uint64_t lo = n_lo, hi = n_hi;
+                    const uint32_t mn = n_mn;
+                    const bool have = e0 + lane < ie;
+                    const uint64_t en = e0 + 32 + lane;
+                    if (en < ie) {
+                        n_lo = d.klo[en]; n_mn = d.minim[en];
+                        if (HAS_HI) n_hi = d.khi[en];
+                    }
                     uint32_t mask = 0;
-                    const uint64_t e = e0 + lane;
-                    if (e < ie) {
-                        const uint64_t lo = d.klo[e], hi = HAS_HI ? d.khi[e] : 0;
-                        const uint32_t mn = d.minim[e];
+                    if (have) {
                         uint32_t h = elem_hash(lo, hi, mn);
                         for (;;) {
                             uint32_t o = s_slot[h];
@@ -157,11 +169,24 @@ hashjoin_kernel(CmpData d, const uint2 *__restrict__ tiles, uint32_t n_chunks, u
                     }
                     // 32 lane masks -> per-column counts (lane jj keeps column jj)
                     uint32_t any = __reduce_or_sync(0xffffffffu, mask);
-                    while (any) {
-                        int jj = __ffs(any) - 1;
-                        any &= any - 1;
-                        uint32_t b = __ballot_sync(0xffffffffu, (mask >> jj) & 1u);
-                        if (lane == jj) acc[r] += __popc(b);
+                    if (__popc(any) > 8) {
+                        // many columns hit (related sketches): transpose the 32x32 bit matrix with five
+                        // butterfly shuffles; lane jj ends up with bit jj of every lane's mask
+                        uint32_t v = __brev(mask);
+#pragma unroll
+                        for (int j = 16, m = 0x0000FFFF; j; j >>= 1, m ^= m << j) {
+                            const uint32_t x = __shfl_xor_sync(0xffffffffu, v, j);
+                            if (lane & j) v ^= ((x ^ (v >> j)) & (uint32_t)m) << j;
+                            else v ^= (v ^ (x >> j)) & (uint32_t)m;
+                        }
+                        acc[r] += __popc(v);
+                    } else {
+                        while (any) {
+                            int jj = __ffs(any) - 1;
+                            any &= any - 1;
+                            uint32_t bb = __ballot_sync(0xffffffffu, (mask >> jj) & 1u);
+                            if (lane == jj) acc[r] += __popc(bb);
+                        }
                     }
                 }
             }
