@@ -2,9 +2,9 @@
 // one stream, no host round trip until the sizes of the results are known:
 //
 //   hits ──K1 classify──▶ CUB sort by position ──K2 clusters──▶ K3 replay (count, write)
-//        ──▶ pieces ──K4 k-mer entries──▶ CUB stable sorts (key, bucket) ──K5 runs──▶
-//        unique k-mers (count mod 256, first order, pos_min) ──▶ buckets
-//        ──K6 greedy reconstruction (size, write)──▶ sketch bytes
+//        ──▶ pieces ──K4 k-mer entries──▶ K5 global hash table keyed (bucket, k-mer): first
+//        occurrence, count mod 256 ──▶ unique k-mers, ONE stable CUB sort by bucket ──▶ buckets
+//        in insertion order ──K6 chain walk (visit order) ──▶ measure / emit ──▶ sketch bytes
 //        ──K7 canonical elements──▶ compare stage (device resident)
 //
 // The generic steps (radix sort, prefix sum) are CUB library calls; everything
@@ -13,12 +13,9 @@
 #include "postpass.cuh"
 
 #include <algorithm>
-#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace spsp {
 
@@ -66,7 +63,7 @@ struct Counters {
 struct PostpassBuffers {
     DBuf cnt, hkey, hval, hkey2, hval2, hhash, hrec, cflag, cid, cl_first, cl_np, cl_nk, cl_poff, cl_eoff;
     DBuf pc_first, pc_nk, pc_min, pc_meta, pc_eoff;
-    DBuf eA, eklo, ekhi, epm, idx0, idx1, idx2, skey, skey2, head, uid;
+    DBuf eA, eklo, ekhi, epm, skey, skey2, head, uid;
     DBuf uA, uklo, ukhi, upm, ucnt, bflag, bidm, bstart, uidx0, uidx2, uent, eslot, hfirst, hcount, huniq, seen;
     DBuf visit, bbytes, bnmax, boff, body, in_bytes, in_sel, in_elems, eflag, eoff, el_min, el_klo, el_khi, cubtmp;
     HBuf h_cnt, h_body, h_in, h_off;
@@ -118,11 +115,6 @@ __device__ __forceinline__ K128 kmer_at(const uint32_t *__restrict__ w, uint64_t
     K128 top{((uint64_t)T[2] << 32) | T[3], ((uint64_t)T[0] << 32) | T[1]};
     return k_shr(top, 128 - 2 * k);
 }
-__device__ __forceinline__ uint32_t base_of(const uint32_t *__restrict__ w, uint64_t pos)
-{
-    return (__ldg(w + (pos >> 4)) >> (30 - 2 * (pos & 15))) & 3u;
-}
-
 // last record r with rec_begin[r] <= pos (n_rec >= 1, rec_begin[0] <= pos assumed checked by caller)
 __device__ __forceinline__ long long find_rec(const uint64_t *__restrict__ rec_begin, uint64_t n_rec, uint64_t pos)
 {
@@ -325,18 +317,10 @@ __global__ void pp_entries_kernel(const uint32_t *__restrict__ packed, const uin
                                   const uint32_t *__restrict__ pc_nk, const uint32_t *__restrict__ pc_min,
                                   const uint32_t *__restrict__ pc_meta, const uint32_t *__restrict__ pc_eoff, int k, int m,
                                   uint64_t bound, int input_shift, uint64_t *__restrict__ eA, uint64_t *__restrict__ eklo,
-                                  uint64_t *__restrict__ ekhi, uint8_t *__restrict__ epm, uint32_t *__restrict__ idx,
-                                  const Counters *cnt)
+                                  uint64_t *__restrict__ ekhi, uint8_t *__restrict__ epm, const Counters *cnt)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= bound) return;
-    idx[t] = (uint32_t)t;
-    if (t >= cnt->n_entries) {
-        eA[t] = ~0ULL; eklo[t] = ~0ULL;
-        if (ekhi) ekhi[t] = ~0ULL;
-        epm[t] = 0;
-        return;
-    }
+    if (t >= bound || t >= cnt->n_entries) return;
     // piece = last one whose first entry is <= t
     uint64_t lo = 0, hi = cnt->n_pieces;
     while (lo < hi) {
@@ -1039,7 +1023,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     }
     // ---- entries
     PP_CK(b->eA.ensure(bound * 8)); PP_CK(b->eklo.ensure(bound * 8)); if (hi128) PP_CK(b->ekhi.ensure(bound * 8));
-    PP_CK(b->epm.ensure(bound)); PP_CK(b->idx0.ensure(bound * 4)); PP_CK(b->idx1.ensure(bound * 4)); PP_CK(b->idx2.ensure(bound * 4));
+    PP_CK(b->epm.ensure(bound));
     PP_CK(b->skey.ensure(bound * 8)); PP_CK(b->skey2.ensure(bound * 8)); PP_CK(b->head.ensure(bound * 4)); PP_CK(b->uid.ensure(bound * 4));
     {
         // entry offset of every piece (exclusive scan of piece sizes)
@@ -1051,7 +1035,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     uint64_t *ekhi = hi128 ? b->ekhi.as<uint64_t>() : nullptr;
     pp_entries_kernel<<<nblk(bound), 256, 0, st>>>(in.d_packed, b->pc_first.as<uint64_t>(), b->pc_nk.as<uint32_t>(),
         b->pc_min.as<uint32_t>(), b->pc_meta.as<uint32_t>(), b->pc_eoff.as<uint32_t>(), k, m, bound, input_shift,
-        b->eA.as<uint64_t>(), b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(), b->idx0.as<uint32_t>(), cnt);
+        b->eA.as<uint64_t>(), b->eklo.as<uint64_t>(), ekhi, b->epm.as<uint8_t>(), cnt);
     launched++;
     // ---- unique k-mers: global hash table keyed by (bucket, k-mer), then ONE stable sort by bucket
     uint64_t slots = 1024;
