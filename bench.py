@@ -56,10 +56,10 @@ def measured_traffic(bases_per_launch):
         with open(p) as f:
             t = json.load(f)
         if abs(bases_per_launch - 320012288) < 1e6:
-            return t["traffic_bytes_per_launch"], t["source"]
+            return t["traffic_bytes_per_launch"], t["source"], t.get("pipes_pct_of_peak")
     except Exception:
         pass
-    return None, None
+    return None, None, None
 
 
 def measured_peaks():
@@ -485,7 +485,11 @@ def b200_arm(args, rank, world, local_rank):
                      "traffic": measured_traffic(n_total)[0], "traffic_source": measured_traffic(n_total)[1],
                      "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src, "kernel": "scan (q-gram filter or dense, see DESIGN.md)",
                      "kernel_ms": scan_ms, "bases_per_launch": int(n_total), "hits_per_launch": int(stats["hits"]),
-                     "kernel_tbp_per_s": n_total / (scan_ms * 1e-3) / 1e12},
+                     "kernel_tbp_per_s": n_total / (scan_ms * 1e-3) / 1e12,
+                     "kernel_share_of_step": scan_ms / (step_s * 1e3),
+                     "ncu_pipes_pct_of_peak": measured_traffic(n_total)[2],
+                     "note": "the kernel that streams every input byte; the rest of the step works on n/s-sized data "
+                             "(latency-bound post-pass, INT/LSU-bound compare), see DESIGN.md section 6"},
         "phases_ms": {"sketch": statistics.mean(stats["sketch_s"]) * 1e3,
                       "compare": statistics.mean(stats["compare_s"]) * 1e3,
                       "scan_kernel": scan_ms, "postpass_device": statistics.mean(stats["post_ms"]),

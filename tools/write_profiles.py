@@ -37,8 +37,15 @@ def main():
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         rd, wr = val("dram__bytes_read.sum", rows[2]), val("dram__bytes_write.sum", rows[2])
         with open(os.path.join(P, f"{R}_traffic.json"), "w") as f:
+            def pct(name):
+                return round(float(rows[2][hdr.index(name)]), 1) if name in hdr else None
             json.dump({"kernel": rows[2][hdr.index("Kernel Name")][:60], "workload": "C2 batch: 320012288 bases, k31 m11 s1000",
                        "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "traffic_bytes_per_launch": int(rd + wr),
+                       "pipes_pct_of_peak": {
+                           "lsu_wavefronts": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                           "issue_active": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                           "alu": pct("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                           "dram": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")},
                        "source": f"ncu --set full --clock-control none, profiles/{R}_scan_ncu.md launch 0"}, f, indent=1)
     for t in ("ev_batch_s1000.txt", "ev_batch_s100.txt"):
         if os.path.exists(os.path.join(G, t)):
