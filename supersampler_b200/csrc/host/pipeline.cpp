@@ -1,5 +1,7 @@
 #include "pipeline.h"
 
+#include "postpass.h"
+
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -214,13 +216,19 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
     stats.prep_s = secs(t0, clk::now());
     for (size_t i = 0; i < n; i++) ok[i] = prep[i].ok ? 1 : 0;
 
-    // ---- batches of consecutive inputs
+    // ---- batches of consecutive inputs: bounded by bases and by the expected number of selected k-mer
+    // occurrences (the device post-pass keeps ~150 bytes per occurrence: dense sampling, -s close to 1, must
+    // not turn a big batch into an allocation the GPU cannot serve)
+    const double p_hit = (double)compute_threshold(k_, m_, s_) / 18446744073709551616.0;
+    const double occ_per_base = std::min(1.0, 1.5 * (double)(k_ - m_ + 1) * p_hit);
+    const uint64_t occ_limit_bases = (uint64_t)std::min(9.0e18, (double)max_batch_occurrences / std::max(occ_per_base, 1e-12));
+    const uint64_t batch_limit = std::max<uint64_t>(4096, std::min(max_batch_bases, occ_limit_bases));
     std::vector<std::pair<size_t, size_t>> batches;
     size_t first = 0;
     uint64_t acc = 0;
     for (size_t i = 0; i < n; i++) {
         const uint64_t need = 16 * spsp_packed_words(prep[i].len);
-        if (i > first && acc + need > max_batch_bases) {
+        if (i > first && acc + need > batch_limit) {
             batches.emplace_back(first, i);
             first = i; acc = 0;
         }

@@ -78,6 +78,7 @@ public:
 
     BatchStats stats;                          // last run()
     uint64_t max_batch_bases = 1ull << 30;     // upper bound of one batch (bases incl. padding)
+    uint64_t max_batch_occurrences = 1ull << 27;   // ... and of its expected selected k-mer occurrences
     std::vector<uint64_t> selected;            // header field 3 of every source, last run()
     // print_stat totals that need every k-mer (SubSampler.cpp:633-665): filled by run() when dense_stats is
     // set, by the dense minimizer machine on the batch still staged on the device (spsp_dense_stats_staged).
