@@ -72,6 +72,12 @@ int spsp_host_free(void *p);
 int spsp_create(int device, int k, int m, uint64_t threshold, int n_slots, spsp_ctx **ctx);
 int spsp_destroy(spsp_ctx *ctx);
 int spsp_scan_config(spsp_ctx *ctx, int mode);
+/* Which filter table the context built for its (m, T): kind 0 = bit table,
+ * 1 = byte table of phase masks, 2 = bank-private bit table + exact hash set
+ * (m == 11, few selected m-mers), -1 = none (dense kernel only); g = probe
+ * stride in bases, n_selected = selected forward m-mers.  Builds the table on
+ * first use, like the first scan does. */
+int spsp_scan_filter_info(spsp_ctx *ctx, int *kind, int *g, uint64_t *n_selected);
 
 /* ---- sketch stage ------------------------------------------------------
  * Replaces the per-base loop of Subsampler::parse_fasta_test

@@ -87,6 +87,7 @@ def device_lib():
         L.spsp_cmp_run_device.argtypes = L.spsp_cmp_run.argtypes
         L.spsp_cmp_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.spsp_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.spsp_scan_filter_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
         L.spsp_sketch_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
         L.spsp_sketch_batch_device.argtypes = L.spsp_sketch_batch.argtypes
@@ -596,6 +597,12 @@ class DeviceContext:
 
     def config(self, mode: int):
         _dcheck(self.L.spsp_scan_config(self.h, mode), "spsp_scan_config")
+
+    def filter_info(self) -> dict:
+        """Filter table of this context: kind (0 bit, 1 byte, 2 bank-private bit + hash set, -1 none), g, n_selected."""
+        kind, g, n = C.c_int(), C.c_int(), C.c_uint64()
+        _dcheck(self.L.spsp_scan_filter_info(self.h, C.byref(kind), C.byref(g), C.byref(n)), "spsp_scan_filter_info")
+        return {"kind": int(kind.value), "g": int(g.value), "n_selected": int(n.value)}
 
     def scan(self, words: np.ndarray, n_bases: int, slot: int = 0) -> np.ndarray:
         """Host buffer in, hits out (submit + collect)."""

@@ -175,37 +175,55 @@ static double filter_cost(int m, int kind, int g, double n_sel, FilterParams *fp
     return n_probe * 5.5 + 30.0 + 20.0 * p_lane + lam * phases * 45.0;
 }
 
+// kind 2 (scan_rowbit_kernel): m == 11, few selected m-mers.  One conflict-free lookup per probe; a flagged
+// probe costs a parked entry and four exact checks in shared memory.
+static double rowbit_cost(int m, double n_sel, FilterParams *fp)
+{
+    if (m != 11) return 1e18;
+    if (n_sel > 4096.0) return 1e18;
+    int h = ROWBIT_MIN_HBITS;                                      // level-2 bits: <= 1/256 full where that fits
+    while (h < ROWBIT_MAX_HBITS && std::ldexp(1.0, h) < 256.0 * n_sel) h++;
+    const double delta = 1.0 - std::exp(-4.0 * n_sel / 32768.0);   // P(probe flagged): 4 phases, 15-bit key
+    const double p_lane = 1.0 - std::pow(1.0 - delta, 16.0);
+    fp->g = 4; fp->q = 8; fp->bits = 15; fp->hashed = 0; fp->rep_log2 = 5; fp->kind = 2; fp->hbits = h;
+    return 70.0 + 30.0 * p_lane + 16.0 * delta * 100.0;   // fitted: 51.5 us vs 58 us (byte table) at s=1000, 320 Mbp
+}
+
 static int build_filter(spsp_ctx *c)
 {
     const double p = (double)c->thr / 18446744073709551616.0;
     const double n_sel = std::ldexp(1.0, 2 * c->m) * p;
-    double best = 1e18;
-    FilterParams bfp{};
     const char *ek = getenv("SPSP_FILTER_KIND"), *eg = getenv("SPSP_FILTER_G");   // tuning overrides (experiments)
-    for (int kind = 0; kind < 2; kind++)
-        for (int g : {4, 2, 1}) {
-            if (ek && atoi(ek) != kind) continue;
-            if (eg && atoi(eg) != g && kind == 0) continue;
-            FilterParams fp{};
-            double cost = filter_cost(c->m, kind, g, n_sel, &fp);
-            if (cost < best) { best = cost; bfp = fp; }
-        }
-    const double dense_cost = 64.0 * 30.0;                 // full hash at every position
-    c->filter_profitable = best < dense_cost;
-    if (best >= 1e18) { c->filter_ready = false; return 0; }
-    c->fp = bfp;
-    CK(cudaMalloc(&c->d_table, filter_table_bytes(bfp)));
-    CK(cudaMalloc(&c->d_exact, ((size_t)1 << (2 * c->m)) / 8));
-    unsigned long long *d_n = nullptr;
-    CK(cudaMalloc(&d_n, sizeof(unsigned long long)));
-    CK(launch_filter_build(c->m, c->thr, bfp, c->d_table, c->d_exact, d_n, c->slots[0].stream));
-    c->launches++;
-    unsigned long long n = 0;
-    CK(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, c->slots[0].stream));
-    CK(cudaStreamSynchronize(c->slots[0].stream));
-    CK(cudaFree(d_n));
-    c->n_selected = n;
-    c->filter_ready = true;
+    for (int allow2 = 1; allow2 >= 0; allow2--) {
+        double best = 1e18;
+        FilterParams bfp{};
+        for (int kind = 0; kind < 3; kind++)
+            for (int g : {4, 2, 1}) {
+                if (ek && atoi(ek) != kind && !(atoi(ek) == 2 && !allow2)) continue;
+                if (eg && atoi(eg) != g && kind == 0) continue;
+                if (kind == 2 && (g != 4 || !allow2)) continue;
+                FilterParams fp{};
+                double cost = kind == 2 ? rowbit_cost(c->m, n_sel, &fp) : filter_cost(c->m, kind, g, n_sel, &fp);
+                if (cost < best) { best = cost; bfp = fp; }
+            }
+        const double dense_cost = 64.0 * 30.0;                 // full hash at every position
+        c->filter_profitable = best < dense_cost;
+        if (best >= 1e18) { c->filter_ready = false; return 0; }
+        c->fp = bfp;
+        CK(cudaMalloc(&c->d_table, filter_table_bytes(bfp)));
+        if (!c->d_exact) CK(cudaMalloc(&c->d_exact, ((size_t)1 << (2 * c->m)) / 8));
+        unsigned long long *d_n = nullptr;
+        CK(cudaMalloc(&d_n, sizeof(unsigned long long)));
+        CK(launch_filter_build(c->m, c->thr, bfp, c->d_table, c->d_exact, d_n, c->slots[0].stream));
+        c->launches++;
+        unsigned long long n = 0;
+        CK(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, c->slots[0].stream));
+        CK(cudaStreamSynchronize(c->slots[0].stream));
+        CK(cudaFree(d_n));
+        c->n_selected = n;
+        c->filter_ready = true;
+        return 0;
+    }
     return 0;
 }
 
@@ -303,6 +321,18 @@ extern "C" int spsp_scan_config(spsp_ctx *c, int mode)
         if (!c->filter_ready) return fail(-3, "spsp_scan_config: filter unavailable for this m");
     }
     c->mode = mode;
+    return 0;
+}
+
+extern "C" int spsp_scan_filter_info(spsp_ctx *c, int *kind, int *g, uint64_t *n_selected)
+{
+    if (!c) return fail(-3, "null ctx");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_filter(c);
+    if (rc) return rc;
+    if (kind) *kind = c->filter_ready ? c->fp.kind : -1;
+    if (g) *g = c->filter_ready ? c->fp.g : 0;
+    if (n_selected) *n_selected = c->n_selected;
     return 0;
 }
 

@@ -58,6 +58,22 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p)
     return v;
 }
 
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// Same as ld_stream_u4 with a memory clobber: later shared-memory reads cannot be scheduled
+// above it, which keeps a prefetch at the top of a loop body.
+__device__ __forceinline__ uint4 ld_stream_u4_pinned(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // 16 bases starting `o` bases into the word pair (w0 = earlier bases),
 // top-aligned: first base in bits 31..30.
 __device__ __forceinline__ uint32_t window16(uint32_t w0, uint32_t w1, int o)

@@ -20,6 +20,7 @@
 //
 // Input layout: 2-bit bases, 16 per little-endian u32, first base in the MSBs;
 // each thread owns 64 consecutive positions (one 128-bit load + 1 halo word).
+#include <cstdlib>
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -126,6 +127,18 @@ __global__ void filter_build_kernel(int m, uint64_t thr, FilterParams fp, uint32
             if (xxh64_8(cn) > thr) continue;
             bitsw |= 1u << b;
             local++;
+            if (fp.kind == 2) {
+                // level 2: one bit per selected m-mer in a hashed table of 2^hbits bits;
+                // level 1: one bit per aligned 2-byte key and phase (compact image, one word per row)
+                const uint32_t idx = (fw * 0x9E3779B1u) >> (32 - fp.hbits);
+                atomicOr(table + (idx >> 5), 1u << (idx & 31));
+                uint32_t *t1 = table + (1u << (fp.hbits - 5));
+                for (int r = 0; r < 4; r++) {
+                    uint32_t key = (fw >> (2 * (m - 8 - r))) & 0xFFFFu;
+                    atomicOr(t1 + (key >> 6), 0x80000000u >> (key & 31));
+                }
+                continue;
+            }
             for (int r = 0; r < fp.g; r++) {
                 // q-gram that starts r bases into the m-mer
                 uint32_t key = (fw >> (2 * (m - fp.q - r))) & ((1u << (2 * fp.q)) - 1u);
@@ -336,6 +349,189 @@ scan_filter_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int m,
     }
 }
 
+
+// ------------------------------------------------------------- row-bit filter
+//
+// kind 2, m == 11 (the reference's default).  An 11-mer that starts at base p
+// fully contains the two aligned sequence bytes b0 = ceil(p/4) and b0+1, so
+// probing the 16-bit key (byte b, byte b+1) at every byte b >= 1 finds every
+// occurrence exactly once, as (b0, r = 4*b0 - p); p = 0 is checked apart.
+//
+// Level 1: a bit table over 15 of the 16 key bits (row = key >> 6, bit =
+// key & 31), replicated so that lane l owns word [row][l]: the 32 lookups of
+// a warp fall into 32 different banks, i.e. ONE shared-memory wavefront per
+// probe instead of ~3.6 for random addresses in a single copy.  A set bit
+// means "some phase of some selected m-mer has this key".  The kernel is then
+// bound by instruction issue on the two integer pipes, so the work of a probe
+// is split between them: left shifts and the address are IMADs (multipliers
+// 2^n read from the constant bank, which keeps ptxas from turning them back
+// into shifts) on the FMA pipe; right shifts and the two funnel shifts that
+// move the wanted bit into the accumulator stay on the ALU pipe.  (Measured
+// on B200, 320 Mbp: all-ALU 53.0 us, IMAD.HI for the right shifts too 54.9 us,
+// this split 51.5 us; the byte-table kernel 58 us.)
+// Level 2: lanes with a flagged probe park {chunk, flags, their 5 sequence
+// words} in the warp's ring in shared memory; when 32 entries wait, every lane
+// takes one and tests the four m-mers (phases r = 0..3) of each flagged byte
+// against a hashed bit table of the selected forward m-mers (2^hbits bits,
+// also in shared memory); the few survivors are settled by the exact bitmap
+// over all 4^11 m-mers (global, L2-resident).  Nothing else after the
+// streaming load touches global memory except the hit records.
+//
+// A lane's chunk c covers the probes at bytes 16c+1 .. 16c+16, all inside its
+// five words (bytes 16c .. 16c+19), so the parked entry is self-contained.
+__constant__ uint32_t c_pow2[3] = {1u << 8, 1u << 16, 128u};
+
+__device__ __forceinline__ void rowbit_check(const uint32_t *l2, int l2sh, const uint32_t *__restrict__ exact, uint64_t p,
+                                             uint32_t fw, uint64_t n_bases, const ScanOut &out)
+{
+    const uint32_t idx = (fw * 0x9E3779B1u) >> l2sh;
+    if ((l2[idx >> 5] >> (idx & 31)) & 1u) {
+        if (p + 11 <= n_bases && ((__ldg(exact + (fw >> 5)) >> (fw & 31)) & 1u)) {
+            const uint32_t rc = rc_word(fw) >> 10;
+            emit_hit(out, p, min(fw, rc), rc < fw);
+        }
+    }
+}
+
+// one parked entry: every flagged byte, four phases each
+__device__ __forceinline__ void rowbit_verify(const uint32_t *q, uint32_t e, const uint32_t *l2, int l2sh,
+                                              const uint32_t *__restrict__ exact, uint64_t n_bases, const ScanOut &out)
+{
+    const uint32_t c = q[e];
+    uint32_t acc = q[ROWBIT_Q + e];
+    while (acc) {
+        const int b = 31 - __clz(acc);
+        acc ^= 1u << b;
+        const int i = 16 - b;                                   // byte 1..16 of the chunk's 20-byte window
+        const int j = i >> 2, ob = i & 3;
+        const uint32_t wa = j ? q[(1 + j) * ROWBIT_Q + e] : 0u;   // words j-1, j, j+1 of the window
+        const uint32_t wb = q[(2 + j) * ROWBIT_Q + e];
+        const uint32_t wc = j < 4 ? q[(3 + j) * ROWBIT_Q + e] : 0u;
+        const uint64_t p0 = ((uint64_t)c << 6) + (uint64_t)(4 * i);
+        // the four starts 4i-3 .. 4i sit 13+4ob .. 16+4ob bases into (wa, wb, wc)
+        const uint32_t hi = ob ? wb : wa, lo = ob ? wc : wb;      // 32-base window that holds all four
+        const int s0 = ob ? 4 * ob - 3 : 13;                      // first start inside (hi, lo); last start <= 16
+        uint32_t fw[4], any = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            // phase r starts at 4i - r = s0 + (3 - r); clamped shift: 32 yields lo
+            fw[r] = __funnelshift_lc(lo, hi, 2 * (s0 + 3 - r)) >> 10;
+            const uint32_t idx = (fw[r] * 0x9E3779B1u) >> l2sh;
+            any |= ((l2[idx >> 5] >> (idx & 31)) & 1u) << r;
+        }
+        if (any) {                                              // rare: settle with the exact bitmap
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if ((any >> r) & 1u) rowbit_check(l2, l2sh, exact, p0 - r, fw[r], n_bases, out);
+        }
+    }
+}
+
+template <int NOVERIFY>
+__global__ void __launch_bounds__(1024, 1)
+scan_rowbit_kernel(const uint32_t *__restrict__ packed, uint64_t n_bases, int hbits, const uint32_t *__restrict__ table_g,
+                   const uint32_t *__restrict__ exact, ScanOut out)
+{
+    extern __shared__ __align__(128) uint32_t smem[];
+    uint32_t *t1 = smem;                                        // [ROWBIT_ROWS][32]
+    uint32_t *l2 = smem + ROWBIT_ROWS * 32;                     // 2^hbits bits
+    uint32_t *qbase = l2 + (1u << (hbits - 5));                 // rings; first 4 KB = staging of the compact table
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *q = qbase + warp * (ROWBIT_Q * ROWBIT_EW);        // [word][slot]
+    const int l2sh = 32 - hbits;
+
+    __shared__ __align__(8) uint64_t tbl_bar;
+    if (threadIdx.x == 0) mbar_init(&tbl_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) tma_load_1d(l2, table_g, (1u << (hbits - 3)) + ROWBIT_ROWS * 4u, &tbl_bar);
+
+    if (n_bases < 11) { mbar_wait(&tbl_bar, 0); return; }
+    const uint64_t n_pos = n_bases - 11 + 1;
+    const uint64_t b0max = (n_pos - 1 + 3) >> 2;                // last byte that can be a first full byte
+    const uint32_t n_chunks = (uint32_t)((b0max + 15) >> 4);
+    const uint32_t n_pass = (n_chunks + 31) >> 5;
+    const uint32_t n_warps = gridDim.x * 32u;
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(packed);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+
+    uint32_t pass = blockIdx.x * 32u + warp;
+    uint4 nv = make_uint4(0, 0, 0, 0);
+    uint32_t nw4 = 0;
+    if (pass < n_pass) {
+        const uint32_t c = min(pass * 32u + lane, n_chunks);  // chunk n_chunks (padding) supplies the last halo word
+        nv = __ldg(p4 + c);
+        if (lane == 31) nw4 = __ldg(packed + 4 * (size_t)c + 4);
+    }
+    mbar_wait(&tbl_bar, 0);
+    {
+        const uint32_t *stage = qbase;                          // compact table: one word per row
+        for (int w = warp; w < ROWBIT_ROWS; w += 32) t1[w * 32 + lane] = stage[w];
+    }
+    __syncthreads();                                            // the staging area becomes ring space
+
+    if (blockIdx.x == 0 && threadIdx.x == 0)                    // p = 0 has no first full byte >= 1
+        rowbit_check(l2, l2sh, exact, 0, __ldg(packed) >> 10, n_bases, out);
+
+    const char *t1b = reinterpret_cast<const char *>(t1);
+    const uint32_t k8 = c_pow2[0], k16 = c_pow2[1], k128 = c_pow2[2];
+    uint32_t head = 0, cnt = 0;                                 // ring state (warp-uniform)
+    for (; pass < n_pass; pass += n_warps) {
+        uint32_t W[5];
+        W[0] = nv.x; W[1] = nv.y; W[2] = nv.z; W[3] = nv.w;
+        W[4] = __shfl_down_sync(0xffffffffu, nv.x, 1);
+        if (lane == 31) W[4] = nw4;
+        const uint32_t c = pass * 32u + lane;
+        {
+            // next pass of this warp; past the end the padding chunk is re-read (cached, and never used):
+            // no branch, so the loads stay ahead of the probes
+            uint32_t cn = (pass + n_warps) * 32u + lane;
+            cn = min(cn, n_chunks);
+            nv = ld_stream_u4_pinned(p4 + cn);
+            if (lane == 31) nw4 = ld_stream_u32(packed + 4 * (size_t)cn + 4);
+        }
+        uint32_t acc = 0;                                       // probe of byte i -> bit 16 - i
+#pragma unroll
+        for (int i = 1; i <= 16; i++) {
+            const int j = i >> 2, ob = i & 3;
+            // x: key in the top 16 bits; row = x >> 22; ks: any word whose low 5 bits are key bits 4..0
+            uint32_t x, ks;
+            if (ob == 0) { x = W[j]; ks = W[j] >> 16; }
+            else if (ob == 1) { x = W[j] * k8; ks = W[j] >> 8; }
+            else if (ob == 2) { x = W[j] * k16; ks = W[j]; }
+            else { x = __funnelshift_l(W[j + 1], W[j], 24); ks = x >> 16; }
+            const uint32_t addr = (x >> 22) * k128 + lane4;
+            const uint32_t word = *reinterpret_cast<const uint32_t *>(t1b + addr);
+            const uint32_t t = __funnelshift_l(0u, word, ks);   // wanted bit -> bit 31 (shift taken mod 32)
+            acc = __funnelshift_l(t, acc, 1);
+        }
+        const bool pos = c < n_chunks && acc != 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, pos);
+        if (pos) {
+            const uint32_t e = (head + cnt + __popc(bal & lt_mask)) & (ROWBIT_Q - 1);
+            q[e] = c;
+            q[ROWBIT_Q + e] = acc;
+#pragma unroll
+            for (int j = 0; j < 5; j++) q[(2 + j) * ROWBIT_Q + e] = W[j];
+        }
+        cnt += __popc(bal);
+        if (cnt > ROWBIT_Q - 32) {                              // room for the next pass: drain one round of 32
+            __syncwarp();
+            if (!NOVERIFY) rowbit_verify(q, (head + lane) & (ROWBIT_Q - 1), l2, l2sh, exact, n_bases, out);
+            __syncwarp();
+            head = (head + 32) & (ROWBIT_Q - 1);
+            cnt -= 32;
+        }
+    }
+    __syncwarp();
+    while (cnt) {
+        const uint32_t n = cnt < 32 ? cnt : 32;
+        if ((uint32_t)lane < n) rowbit_verify(q, (head + lane) & (ROWBIT_Q - 1), l2, l2sh, exact, n_bases, out);
+        head = (head + n) & (ROWBIT_Q - 1);
+        cnt -= n;
+    }
+}
+
 // ------------------------------------------------------------- launchers
 
 static int g_sm_count = 0;
@@ -413,11 +609,47 @@ static cudaError_t launch_filter_m(const uint32_t *d_packed, uint64_t n_bases, i
     return launch_filter_t<G, MODE, 1024, 1>(d_packed, n_bases, m, fp, d_table, d_exact, out, st);
 }
 
+
+static size_t rowbit_smem(int hbits)
+{
+    return (size_t)ROWBIT_ROWS * 32 * 4 + ((size_t)1 << (hbits - 3)) + (size_t)32 * ROWBIT_Q * ROWBIT_EW * 4;
+}
+
+static cudaError_t launch_rowbit(const uint32_t *d_packed, uint64_t n_bases, FilterParams fp, const uint32_t *d_table,
+                                 const uint32_t *d_exact, ScanOut out, cudaStream_t st)
+{
+    static const bool noverify = getenv("SPSP_ROWBIT_NOVERIFY") != nullptr;   // timing experiments only: drops the hits
+    auto kern = noverify ? scan_rowbit_kernel<1> : scan_rowbit_kernel<0>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (auto kf : {scan_rowbit_kernel<1>, scan_rowbit_kernel<0>}) {
+            cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)rowbit_smem(ROWBIT_MAX_HBITS));
+            if (e != cudaSuccess) return e;
+        }
+        attr_set = true;
+    }
+    const uint64_t n_pos = n_bases - 11 + 1;
+    const uint64_t n_chunks = ((((n_pos - 1 + 3) >> 2) + 15) >> 4);
+    if (n_chunks >= (1ull << 32) - 64) return cudaErrorInvalidValue;
+    uint64_t n_pass = (n_chunks + 31) >> 5;
+    uint64_t blocks = (uint64_t)sm_count();
+    const uint64_t want = (n_pass + 31) / 32;
+    if (blocks > want) blocks = want;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, 1024, rowbit_smem(fp.hbits), st>>>(d_packed, n_bases, fp.hbits, d_table, d_exact, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan_filter(const uint32_t *d_packed, uint64_t n_bases, int m, uint64_t thr, FilterParams fp,
                                const uint32_t *d_table, const uint32_t *d_exact, ScanOut out, cudaStream_t st)
 {
     (void)thr;
     if (n_bases < (uint64_t)m) return cudaSuccess;
+    if (fp.kind == 2) {
+        if (m != 11 || fp.hbits < ROWBIT_MIN_HBITS || fp.hbits > ROWBIT_MAX_HBITS) return cudaErrorInvalidValue;
+        return launch_rowbit(d_packed, n_bases, fp, d_table, d_exact, out, st);
+    }
 #define SPSP_F(G_, M_) return launch_filter_m<G_, M_>(d_packed, n_bases, m, fp, d_table, d_exact, out, st)
     if (fp.kind == 1) {
         if (fp.g != 4 || 2 * fp.q > 16) return cudaErrorInvalidValue;

@@ -78,6 +78,46 @@ def test_scan_random_lengths(oracle):
         ctx.close()
 
 
+def test_scan_rowbit_filter(oracle, monkeypatch):
+    """kind 2 (bank-private bit table + exact hash set, m == 11): same hit set as the closed form over ragged
+    lengths, dense and sparse thresholds, all-A / repeated sequence (every probe flagged) and position 0."""
+    monkeypatch.setenv("SPSP_FILTER_KIND", "2")
+    rng = np.random.default_rng(17)
+    for s in (250.0, 1000.0, 6000.0):
+        thr = S.threshold(31, 11, s)
+        ctx = S.DeviceContext(31, 11, thr)
+        assert ctx.filter_info()["kind"] == 2, ctx.filter_info()
+        ctx.config(capi.SCAN_FILTER)
+        # a selected 11-mer planted at position 0 and at every alignment near chunk / pass boundaries
+        probe = synth.random_genome(400000, 5)
+        pos, cn, rv, _ = oracle.hits(probe, 11, thr)
+        assert pos.size > 0
+        sel = probe[int(pos[0]):int(pos[0]) + 11].copy()
+        lens = [0, 1, 10, 11, 12, 15, 63, 64, 65, 74, 75, 127, 2047, 2048, 2049, 2048 + 11, 4096 + 3, 65536 + 63,
+                int(rng.integers(100000, 300000)), 1_500_000]
+        for n in lens:
+            seq = synth.random_genome(n, int(rng.integers(1 << 30)))
+            if n >= 11:
+                for at in (0, 1, 2, 3, 4, 53, 54, 60, 61, 62, 63, 64, 65, 2037, 2040, 2048, n - 11, n - 12):
+                    if 0 <= at and at + 11 <= n:
+                        seq[at:at + 11] = sel
+            fa = b">r\n" + seq.tobytes() + b"\n"
+            words, nb, _ = S.pack_fasta(fa, 1)
+            assert nb == n
+            pos, cn, rv, _ = oracle.hits(seq, 11, thr)
+            h = sorted_hits(ctx.scan(words, nb))
+            assert np.array_equal(h["pos"], pos), (s, n, h.size, pos.size)
+            assert np.array_equal(h["canon"], cn)
+            assert np.array_equal(h["rev"], rv.astype(np.uint32))
+        # the selected 11-mer repeated back to back: every probe of every lane is flagged, rings wrap
+        seq = np.tile(sel, 30000)
+        words, nb, _ = S.pack_fasta(b">r\n" + seq.tobytes() + b"\n", 1)
+        pos, cn, rv, _ = oracle.hits(seq, 11, thr)
+        h = sorted_hits(ctx.scan(words, nb))
+        assert np.array_equal(h["pos"], pos) and np.array_equal(h["canon"], cn)
+        ctx.close()
+
+
 @pytest.mark.parametrize("name", sorted(SKETCH_CASES))
 def test_sketch_bytes_match_reference(name, golden):
     inp, k, m, s, a = SKETCH_CASES[name]

@@ -20,6 +20,7 @@ def run(k, m, s, mode, n_bases=320_000_000, reps=20):
     d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
     ctx = S.DeviceContext(k, m, thr)
     ctx.config(mode)
+    finfo = ctx.filter_info() if mode != 1 else {}
     ms = []
     for i in range(reps + 3):
         ctx.scan_device(d[i % nrep].data_ptr(), n_bases, d_hits.data_ptr(), cap, d_cnt.data_ptr())
@@ -33,7 +34,7 @@ def run(k, m, s, mode, n_bases=320_000_000, reps=20):
                       "rep": os.environ.get("SPSP_FILTER_REP"), "ms": round(t, 4), "min_ms": round(min(ms), 4),
                       "tbp_s": round(n_bases / (t * 1e-3) / 1e12, 3), "gb_s": round(gbs, 1),
                       "frac_hbm": round(gbs / 6534.8, 4), "hits": n, "n_bases": n_bases,
-                      "kind": os.environ.get("SPSP_FILTER_KIND")}), flush=True)
+                      "kind": os.environ.get("SPSP_FILTER_KIND"), "filter": finfo}), flush=True)
     ctx.close()
 
 if __name__ == "__main__":
