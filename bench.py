@@ -290,11 +290,13 @@ def b200_arm(args, rank, world, local_rank):
     # last compare is drained inside the timed region.  --no-pipelining runs the stages back to back.
     from concurrent.futures import ThreadPoolExecutor
     depth = 1 if args.no_pipelining else 2
+    rdepth = 1 if args.no_pipelining else max(2, args.depth)     # device-resident path: batches in flight
+    args.warmup = max(args.warmup, rdepth)      # every context has run (tables, buffers) before the clock starts
     # host-buffer path: the public pipeline (pack on host threads -> pinned -> H2D -> scan -> post-pass -> compare)
     pipes = [S.Pipeline(k, m, s, device=local_rank, threads=threads) for _ in range(depth)]
     pctxs = [p_.device_context() for p_ in pipes]
     # device-resident path: contexts of their own; all genomes packed back to back, R replicas in HBM
-    dctxs = [S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank) for _ in range(depth)]
+    dctxs = [S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank) for _ in range(rdepth)]
     ws, ros = [], []
     for fa in fastas:
         w, nb, offs = S.pack_fasta(fa, k)
@@ -332,18 +334,33 @@ def b200_arm(args, rank, world, local_rank):
         return res
 
     class Resident:
-        """Device-resident steps: sketch of batch i on context i % depth, its compare on the background thread."""
+        """Device-resident steps, `rdepth` batches in flight: the sketch of batch i runs on context i % rdepth from
+        a pool of host threads (the post-pass is a chain of small latency-bound kernels, so batches on different
+        streams overlap on the device); the compare stages run one at a time in step order on one thread (one
+        NCCL exchange in flight).  A context is reused only after its previous batch has been retired."""
 
         def __init__(self):
-            self.pool = ThreadPoolExecutor(1)
-            self.pending = None
+            self.sk_pool = ThreadPoolExecutor(rdepth)
+            self.cmp_pool = ThreadPoolExecutor(1)
+            self.inflight = []
 
-        def finish(self, record):
-            if self.pending is None:
-                return None
-            sks, fut, info, cinfo, nl, t_sk = self.pending
-            self.pending = None
-            res = fut.result()
+        def _sketch(self, i):
+            ctx = dctxs[i % rdepth]
+            t0 = time.perf_counter()
+            info = {}
+            l0 = ctx.launches()
+            sks = ctx.sketch_batch(None, n_total, rec_begin, rec_end, rec_input, n_in, s,
+                                   device_ptr=d_packed[i % replicas].data_ptr(), info=info)
+            return sks, info, ctx.launches() - l0, time.perf_counter() - t0
+
+        def _compare(self, i, fut):
+            sks, info, nl, t_sk = fut.result()
+            cinfo = {}
+            res = compare_device(dctxs[i % rdepth], info["elem_off"], cinfo)
+            return sks, res, info, cinfo, nl, t_sk
+
+        def _retire(self, record):
+            sks, res, info, cinfo, nl, t_sk = self.inflight.pop(0).result()
             if record:
                 stats["scan_ms"].append(info["scan_ms"]); stats["post_ms"].append(info["post_ms"])
                 stats["cmp_ms"].append(cinfo.get("kernel_ms", 0.0))
@@ -354,19 +371,15 @@ def b200_arm(args, rank, world, local_rank):
             return sks, res
 
         def step(self, i, record):
-            ctx = dctxs[i % depth]
-            t0 = time.perf_counter()
-            info, cinfo = {}, {}
-            l0 = ctx.launches()
-            sks = ctx.sketch_batch(None, n_total, rec_begin, rec_end, rec_input, n_in, s,
-                                   device_ptr=d_packed[i % replicas].data_ptr(), info=info)
-            nl = ctx.launches() - l0
-            t_sk = time.perf_counter() - t0
-            out = self.finish(record)                       # compare of the previous batch ran meanwhile
-            fut = self.pool.submit(compare_device, ctx, info["elem_off"], cinfo)
-            self.pending = (sks, fut, info, cinfo, nl, t_sk)
-            if depth == 1:
-                out = self.finish(record)
+            out = self._retire(record) if len(self.inflight) >= rdepth else None
+            fut = self.sk_pool.submit(self._sketch, i)
+            self.inflight.append(self.cmp_pool.submit(self._compare, i, fut))
+            return out
+
+        def finish(self, record):
+            out = None
+            while self.inflight:
+                out = self._retire(record)
             return out
 
     class HostBuffers:
@@ -459,7 +472,14 @@ def b200_arm(args, rank, world, local_rank):
     total_bases = total_bases_rank * world
     pairs = n_gen_total * (n_gen_total - 1) // 2
     step_s = t_res / args.steps
-    scan_ms = statistics.mean(stats["scan_ms"])
+    # the scan kernel's launch duration (CUDA events on its own stream): taken from the e2e region, where no other
+    # batch shares the SMs with it; the value region overlaps several batches, its per-launch figure is kept beside it
+    finfo = dctxs[0].filter_info()
+    scan_kernel_name = {2: "scan_rowbit_kernel (bank-private bit table + hashed m-mer table, DESIGN.md 3.3b)",
+                        1: "scan_filter_kernel (byte table of phase masks, DESIGN.md 3.3)",
+                        0: "scan_filter_kernel (bit table, DESIGN.md 3.3)"}.get(finfo["kind"], "scan_dense_kernel")
+    scan_ms_value_region = statistics.mean(stats["scan_ms"])
+    scan_ms = statistics.mean(x["scan_ms"] for x in stats["e2e"])
     algo_bytes = n_total / 4 + 16 * stats["hits"]
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
     sizes = cmp_res[1]
@@ -479,20 +499,24 @@ def b200_arm(args, rank, world, local_rank):
                 "gpu_launches": int(sum(x["launches"] for x in e2)),
                 "api": "supersampler_b200.BatchStream.submit(FASTA bytes in host memory) over two Pipelines "
                        "(.sketch() + .compare(), the compare of batch i overlapping the sketch of batch i+1)"},
-        "pipelining": "off" if depth == 1 else "one batch deep: compare(i) on a background thread / second context while sketch(i+1) runs",
+        "pipelining": "off" if depth == 1 else
+                      f"value: {rdepth} batches in flight (sketches on {rdepth} contexts / streams, compare stages serialised on one thread); "
+                      "e2e: one batch deep (compare(i) on a background thread / second context while sketch(i+1) runs)",
         "gpu_launches": stats["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(n_total)[0], "traffic_source": measured_traffic(n_total)[1],
-                     "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src, "kernel": "scan (q-gram filter or dense, see DESIGN.md)",
+                     "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src, "kernel": scan_kernel_name,
                      "kernel_ms": scan_ms, "bases_per_launch": int(n_total), "hits_per_launch": int(stats["hits"]),
                      "kernel_tbp_per_s": n_total / (scan_ms * 1e-3) / 1e12,
+                     "kernel_ms_timed_in": "e2e region (CUDA events on the launching stream)",
+                     "kernel_ms_in_value_region": scan_ms_value_region,
                      "kernel_share_of_step": scan_ms / (step_s * 1e3),
                      "ncu_pipes_pct_of_peak": measured_traffic(n_total)[2],
                      "note": "the kernel that streams every input byte; the rest of the step works on n/s-sized data "
                              "(latency-bound post-pass, INT/LSU-bound compare), see DESIGN.md section 6"},
         "phases_ms": {"sketch": statistics.mean(stats["sketch_s"]) * 1e3,
                       "compare": statistics.mean(stats["compare_s"]) * 1e3,
-                      "scan_kernel": scan_ms, "postpass_device": statistics.mean(stats["post_ms"]),
+                      "scan_kernel": scan_ms_value_region, "postpass_device": statistics.mean(stats["post_ms"]),
                       "compare_kernel": statistics.mean(stats["cmp_ms"])},
         "d2h_bytes_per_step": int(stats["d2h"]),
         "compare": {"pairs": pairs, "pairs_per_s": pairs / statistics.mean(stats["compare_s"]),
@@ -543,6 +567,7 @@ def main():
     ap.add_argument("-s", type=float, default=1000.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelining", action="store_true", help="run sketch and compare of a step back to back")
+    ap.add_argument("--depth", type=int, default=4, help="device-resident path: batches in flight")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

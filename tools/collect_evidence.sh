@@ -8,7 +8,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/ev_bench_ref.json 2> 
 python bench.py --steps 5 --warmup 3 > $O/ev_bench_n1.json 2> $O/ev_bench_n1.err || { tail -5 $O/ev_bench_n1.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/ev_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ev_ncu_launches.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:scan_filter -c 2 -o $O/ev_prof_scan \
+ncu --set full --import-source on --clock-control none -k regex:"scan_filter|scan_rowbit" -c 2 -o $O/ev_prof_scan \
     python tools/profile_batch.py 64 1000 2 > $O/ev_ncu_scan.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:"pp_chain|hashjoin|pp_emit" -c 4 -o $O/ev_prof_post \
     python tools/profile_batch.py 64 1000 1 > $O/ev_ncu_post.log 2>&1

@@ -18,7 +18,7 @@ def main():
     with open(os.path.join(P, f"{R}_bench_launch_summary.md"), "w") as f:
         f.write("# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (per-launch times are cold and serialised: compare shares)\n\n")
         f.write(run(sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(G, "ev_launches.csv")))
-    for rep, name, title in (("ev_prof_scan", "scan_ncu", "scan_filter_kernel, bench workload"),
+    for rep, name, title in (("ev_prof_scan", "scan_ncu", "scan kernel of the bench workload (scan_rowbit_kernel at k31 m11 s1000)"),
                              ("ev_prof_post", "postpass_compare_ncu", "pp_chain_kernel / pp_emit_kernel / hashjoin_kernel, bench workload"),
                              ("ev_prof_dense", "dense_ncu", "dense_rows_kernel / dense_segments_kernel, bench workload")):
         path = os.path.join(G, rep + ".ncu-rep")
@@ -45,6 +45,7 @@ def main():
                            "lsu_wavefronts": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                            "issue_active": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                            "alu": pct("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                           "fma": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                            "dram": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")},
                        "source": f"ncu --set full --clock-control none, profiles/{R}_scan_ncu.md launch 0"}, f, indent=1)
     for t in ("ev_batch_s1000.txt", "ev_batch_s100.txt"):
