@@ -9,7 +9,13 @@ the G sketches all-vs-all.
   value : inputs (2-bit packed genomes) resident in HBM; per step: one scan
           launch over the batch, the exact post-pass on the device (hits ->
           super-k-mers -> buckets -> sketch bytes), sketch bytes D2H, compare
-          kernel on the device-resident elements, matrix D2H.
+          kernel on the device-resident elements, matrix D2H.  --depth
+          batches (default 4) are in flight on their own contexts / streams;
+          the timed region ends when the last one has been retired.
+  roofline : a third region, rank 0: the scan kernel alone over the rotating
+          device-resident replicas, CUDA events on its launching stream
+          (the in-step per-launch figures of both other regions are kept
+          beside it in the JSON line).
   e2e   : the same work through the public host API with HOST buffers
           (supersampler_b200.Pipeline): FASTA text in host memory -> host
           threads clean/pack into pinned memory -> async H2D per input -> scan ->
