@@ -186,7 +186,9 @@ static double rowbit_cost(int m, double n_sel, FilterParams *fp)
     const double delta = 1.0 - std::exp(-4.0 * n_sel / 32768.0);   // P(probe flagged): 4 phases, 15-bit key
     const double p_lane = 1.0 - std::pow(1.0 - delta, 16.0);
     fp->g = 4; fp->q = 8; fp->bits = 15; fp->hashed = 0; fp->rep_log2 = 5; fp->kind = 2; fp->hbits = h;
-    return 70.0 + 30.0 * p_lane + 16.0 * delta * 100.0;   // fitted: 51.5 us vs 58 us (byte table) at s=1000, 320 Mbp
+    // fitted to 320 Mbp launches at m = 11: 51.5 vs 58 us (byte table) at s = 1000, 59.9 vs 63.7 at 700, 67.0 vs 70.8 at 550,
+    // 85 vs 82 at 400: the two cross near 450 selected m-mers
+    return 70.0 + 25.0 * p_lane + 16.0 * delta * 72.0;
 }
 
 static int build_filter(spsp_ctx *c)
