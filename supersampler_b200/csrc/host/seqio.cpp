@@ -104,30 +104,39 @@ static inline void emit64(uint32_t *w, uint64_t &widx, uint64_t acc)
     memcpy(w + widx, &acc, 8);
     widx += 2;
 }
-// Reverse the 16 two-bit groups of every u32 in w[0, n).
-static void words_to_msb_first(uint32_t *w, uint64_t n)
+// dst[i] = src[i] with its 16 two-bit groups reversed, i in [0, n).  The destination is the (pinned) staging
+// buffer, written exactly once: non-temporal stores keep it from being read first (no read-for-ownership) and
+// from displacing the text that is being streamed through the caches.
+static inline uint32_t word_to_msb_first(uint32_t x)
+{
+    x = __builtin_bswap32(x);
+    x = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+    return ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
+}
+static void words_to_msb_first(const uint32_t *src, uint32_t *dst, uint64_t n)
 {
     uint64_t i = 0;
 #if defined(__AVX2__)
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31u)) { dst[i] = word_to_msb_first(src[i]); i++; }
     const __m256i rev4 = _mm256_setr_epi8(0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15,
                                           0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15);   // nibble ab -> ba (2-bit groups)
     const __m256i bswap = _mm256_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12,
                                            3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12);
     const __m256i lo4 = _mm256_set1_epi8(0x0F);
+    static const bool nt = getenv("SPSP_PACK_NO_NT") == nullptr;          // experiments: plain stores
+    const bool streamed = nt && i + 8 <= n;
     for (; i + 8 <= n; i += 8) {
-        __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(w + i));
+        __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
         const __m256i l = _mm256_shuffle_epi8(rev4, _mm256_and_si256(x, lo4));
         const __m256i h = _mm256_shuffle_epi8(rev4, _mm256_and_si256(_mm256_srli_epi16(x, 4), lo4));
         x = _mm256_or_si256(_mm256_slli_epi16(l, 4), h);                   // groups reversed inside every byte
-        _mm256_storeu_si256(reinterpret_cast<__m256i *>(w + i), _mm256_shuffle_epi8(x, bswap));
+        x = _mm256_shuffle_epi8(x, bswap);
+        if (nt) _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), x);
+        else _mm256_store_si256(reinterpret_cast<__m256i *>(dst + i), x);
     }
+    if (streamed) _mm_sfence();                                            // before the words are handed to a copy
 #endif
-    for (; i < n; i++) {
-        uint32_t x = __builtin_bswap32(w[i]);
-        x = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
-        x = ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
-        w[i] = x;
-    }
+    for (; i < n; i++) dst[i] = word_to_msb_first(src[i]);
 }
 
 // The block loops run ~50 uops per 32 bytes, so the out-of-order window only covers a few cache lines of
@@ -236,12 +245,28 @@ static bool have_avx512_packer()
 static bool have_avx512_packer() { return false; }
 #endif
 
+// Words that are not final yet live in scratch_ (scratch_[0] is output word converted_), in the packer's
+// "low first" bit order; commit() / finish() move them to the output buffer in output order.  Long inputs are
+// fed in pieces so that the scratch stays cache-resident between the two passes.
 void FastaPacker::feed(const uint8_t *p, size_t n)
+{
+    constexpr size_t PIECE = (size_t)512 << 10;
+    while (n > PIECE) {
+        feed_piece(p, PIECE);
+        commit();
+        p += PIECE; n -= PIECE;
+    }
+    feed_piece(p, n);
+}
+
+void FastaPacker::feed_piece(const uint8_t *p, size_t n)
 {
     if (!n) return;
     any_input_ = true;
     out_.words.reserve(word_idx_ + n / 16 + 4);       // every byte is at most one base
-    uint32_t *w = out_.words.data();
+    if (scratch_.size() < word_idx_ - converted_ + n / 16 + 8) scratch_.resize(word_idx_ - converted_ + n / 16 + 8);
+    // w + widx addresses scratch word widx - converted_ (converted_ does not move inside this call)
+    uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(scratch_.data()) - converted_ * sizeof(uint32_t));
     const uint8_t *const begin = p, *end = p + n;
     uint64_t acc = acc_;
     int fill = fill_;
@@ -301,7 +326,9 @@ uint64_t FastaPacker::commit()
     uint64_t stable = (out_.n_bases - rec_start_ >= min_len_) ? word_idx_ : ck_word_idx_;
     stable &= ~(uint64_t)1;                                     // whole 64-bit units
     if (stable > converted_) {
-        words_to_msb_first(out_.words.data() + converted_, stable - converted_);
+        const uint64_t n = stable - converted_, rest = word_idx_ - stable;
+        words_to_msb_first(scratch_.data(), out_.words.data() + converted_, n);
+        if (rest) memmove(scratch_.data(), scratch_.data() + n, rest * sizeof(uint32_t));
         converted_ = stable;
     }
     return converted_;
@@ -312,11 +339,13 @@ void FastaPacker::finish()
     end_record();
     uint64_t need = spsp_packed_words(out_.n_bases);
     out_.words.reserve(std::max<uint64_t>(need, word_idx_ + 2));
-    uint32_t *w = out_.words.data();
+    if (scratch_.size() < word_idx_ - converted_ + 2) scratch_.resize(word_idx_ - converted_ + 2);
+    uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(scratch_.data()) - converted_ * sizeof(uint32_t));
     uint64_t widx = word_idx_;
     if (fill_) emit64(w, widx, acc_);                 // bits above fill_ are zero: left-aligned after the sweep
-    if (widx > converted_) words_to_msb_first(w + converted_, widx - converted_);
+    if (widx > converted_) words_to_msb_first(scratch_.data(), out_.words.data() + converted_, widx - converted_);
     converted_ = widx;
+    w = out_.words.data();
     widx = (out_.n_bases + 15) / 16;                  // zero padding for the kernels
     for (; widx < need; widx++) w[widx] = 0;
 }

@@ -56,7 +56,9 @@ public:
 
 private:
     void end_record();
+    void feed_piece(const uint8_t *p, size_t n);
     PackedInput &out_;
+    std::vector<uint32_t> scratch_;    // words [converted_, word_idx_) before the sweep into the output buffer
     uint32_t min_len_;
     enum State { HEADER, LINE_START, SEQ } state_ = HEADER;
     // Pending bases not yet written: base j of the run at bits 2j..2j+1 (little-endian
