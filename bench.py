@@ -284,7 +284,7 @@ def b200_arm(args, rank, world, local_rank):
             dist.barrier()
 
     cores = os.cpu_count() or 1
-    threads = max(1, min(32, cores // world))
+    threads = args.threads if args.threads > 0 else max(1, min(32, cores // world))
     k, m, s = args.k, args.m, args.s
     fastas, names = make_fastas(args.genomes, args.bases, rank * args.genomes)
     total_bases_rank = sum(args.bases for _ in fastas)
@@ -590,6 +590,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelining", action="store_true", help="run sketch and compare of a step back to back")
     ap.add_argument("--depth", type=int, default=4, help="device-resident path: batches in flight")
+    ap.add_argument("--threads", type=int, default=0, help="host packing threads per rank (default: cores / ranks)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
