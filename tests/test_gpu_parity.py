@@ -78,6 +78,20 @@ def test_scan_random_lengths(oracle):
         ctx.close()
 
 
+def test_scan_kernel_choice():
+    """The cost model's choice per (m, T): (kind, probe stride).  Row-bit kernel for the reference's defaults, byte
+    table of phase masks just below its crossover, bit tables (hashed where 2q > 20 bits) for dense thresholds
+    and for m = 13 (C5).  Every choice returns the same hits (the tests above); this pins the selection."""
+    want = {(31, 11, 1000.0): (2, 4), (31, 11, 600.0): (2, 4), (31, 11, 400.0): (1, 4), (31, 11, 100.0): (0, 2),
+            (31, 13, 200.0): (0, 2)}
+    for (k, m, s), (kind, g) in want.items():
+        ctx = S.DeviceContext(k, m, S.threshold(k, m, s))
+        info = ctx.filter_info()
+        assert (info["kind"], info["g"]) == (kind, g), ((k, m, s), info)
+        assert info["n_selected"] > 0
+        ctx.close()
+
+
 def test_scan_rowbit_filter(oracle, monkeypatch):
     """kind 2 (bank-private bit table + exact hash set, m == 11): same hit set as the closed form over ragged
     lengths, dense and sparse thresholds, all-A / repeated sequence (every probe flagged) and position 0."""
