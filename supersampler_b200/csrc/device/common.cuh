@@ -2,8 +2,26 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace spsp {
+
+// Function attributes (opt-in shared memory sizes) belong to a device, and a process may drive several GPUs
+// from several host threads: one bit per device, set after the attribute call succeeded there.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done{0};
+    template <class F> cudaError_t run(F &&f)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const uint64_t bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+        e = f();
+        if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
 
 // XXH64 of one 8-byte little-endian word with seed 1312: what the reference's
 // unrevhash computes (SubSampler.cpp:64-67 -> include/xxhash64.h:158-163,

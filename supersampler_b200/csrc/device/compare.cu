@@ -253,13 +253,14 @@ cudaError_t launch_hashjoin(const CmpData &d, bool has_hi, const uint2 *d_tiles,
 {
     if (!n_tiles) return cudaSuccess;
     size_t smem = hashjoin_smem_bytes(has_hi);
-    static bool attr[2] = {false, false};
-    if (!attr[has_hi]) {
-        cudaError_t e = has_hi
-            ? cudaFuncSetAttribute(hashjoin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(hashjoin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        static PerDeviceOnce once[2];
+        cudaError_t e = once[has_hi].run([&] {
+            return has_hi
+                ? cudaFuncSetAttribute(hashjoin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                : cudaFuncSetAttribute(hashjoin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
         if (e != cudaSuccess) return e;
-        attr[has_hi] = true;
     }
     dim3 grid(n_tiles, chunk_groups);
     if (has_hi)

@@ -1074,11 +1074,10 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     // ---- reconstruction: walk every bucket's chains once (visit order + byte sizes), offsets; bytes are emitted below
     const size_t rc_smem = rc_smem_bytes(hi128);
     {
-        static bool attr_done = false;
-        if (!attr_done) {
-            PP_CK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc_smem_bytes(true)));
-            attr_done = true;
-        }
+        static PerDeviceOnce once;
+        PP_CK(once.run([] {
+            return cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc_smem_bytes(true));
+        }));
     }
     const unsigned rc_grid = (unsigned)std::min<uint64_t>((bound + RC_WARPS - 1) / RC_WARPS, 148 * 8);
     PP_CK(b->bbytes.ensure(bound * 4)); PP_CK(b->bnmax.ensure(bound * 4)); PP_CK(b->boff.ensure(bound * 8));

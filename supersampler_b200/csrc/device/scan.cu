@@ -579,13 +579,14 @@ static cudaError_t launch_filter_t(const uint32_t *d_packed, uint64_t n_bases, i
 {
     auto kern = scan_filter_kernel<G, MODE, THREADS, CTAS>;
     size_t smem = filter_table_bytes(fp) + (size_t)(THREADS / 32) * (FILTER_WQ * 3) * sizeof(uint32_t);
-    static bool attr_set = false;
-    static int per_sm = 0;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(FILTER_MAX_SMEM + (THREADS / 32) * (FILTER_WQ * 3) * sizeof(uint32_t)));
+    int per_sm = 0;
+    {
+        static PerDeviceOnce once;                  // one per template instance = per kernel
+        cudaError_t e = once.run([&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(FILTER_MAX_SMEM + (THREADS / 32) * (FILTER_WQ * 3) * sizeof(uint32_t)));
+        });
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (per_sm < 1) per_sm = 1;
@@ -620,14 +621,12 @@ static cudaError_t launch_rowbit(const uint32_t *d_packed, uint64_t n_bases, Fil
 {
     static const bool noverify = getenv("SPSP_ROWBIT_NOVERIFY") != nullptr;   // timing experiments only: drops the hits
     auto kern = noverify ? scan_rowbit_kernel<1> : scan_rowbit_kernel<0>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (auto kf : {scan_rowbit_kernel<1>, scan_rowbit_kernel<0>}) {
-            cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)rowbit_smem(ROWBIT_MAX_HBITS));
-            if (e != cudaSuccess) return e;
-        }
-        attr_set = true;
+    {
+        static PerDeviceOnce once[2];
+        cudaError_t e = once[noverify ? 1 : 0].run([&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowbit_smem(ROWBIT_MAX_HBITS));
+        });
+        if (e != cudaSuccess) return e;
     }
     const uint64_t n_pos = n_bases - 11 + 1;
     const uint64_t n_chunks = ((((n_pos - 1 + 3) >> 2) + 15) >> 4);
