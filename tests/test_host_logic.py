@@ -211,3 +211,37 @@ def test_packer_random_messy_inputs(oracle):
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1]
+
+
+def test_packer_long_messy_input_crosses_sweep_pieces(oracle):
+    """Inputs longer than the packer's internal piece (512 KB of text between two sweeps into the output
+    buffer): thousands of records of every length around min_len, so that short records are taken back and
+    pending words are carried over right at the piece boundaries; plus one long record crossing several pieces."""
+    from tests.test_gpu_parity import _random_fasta
+    rng = np.random.default_rng(2024)
+    parts = []
+    size = 0
+    while size < 2_300_000:
+        if rng.integers(0, 40) == 0:
+            L = int(rng.integers(200_000, 700_000))              # a record that spans pieces
+            seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=L)].tobytes()
+            w = int(rng.integers(40, 100))
+            piece = b">long\n" + b"\n".join(seq[i:i + w] for i in range(0, L, w)) + b"\n"
+        else:
+            piece = _random_fasta(rng, int(rng.integers(1, 30)))
+            if not piece.endswith(b"\n"):
+                piece += b"\n"
+        parts.append(piece)
+        size += len(piece)
+    fa = b"".join(parts)
+    bases, o = oracle.clean(fa)
+    for k in (1, 31, 63):
+        words, nb, offs = S.pack_fasta(fa, k)
+        keep = [(int(o[i]), int(o[i + 1])) for i in range(len(o) - 1) if int(o[i + 1]) - int(o[i]) >= k]
+        want = np.concatenate([bases[a:b] for a, b in keep]) if keep else np.zeros(0, np.uint8)
+        assert nb == want.size, k
+        assert np.array_equal(unpack(words, nb), want), k
+        assert list(np.diff(offs.astype(np.int64))) == [b - a for a, b in keep]
+        assert words.size == S.packed_words(nb)
+        assert (unpack(words, words.size * 16)[nb:] == ord("A")).all()
+
