@@ -23,7 +23,15 @@ the G sketches all-vs-all.
           copies inside the timed region.
   --impl reference : the unmodified reference binaries (oracle/_ref, built from
           /root/reference in the build container) on this box's host cores,
-          same files / parameters; C restatement if the binaries are absent.
+          same files / parameters (64 x N genomes for --gpus N); C restatement
+          if the binaries are absent.
+  parity : after the timed regions rank 0 runs oracle/_ref on the job's own
+          FASTA files (all 64 x N genomes) and compares every sketch and both
+          CSV matrices byte for byte (`parity_vs_reference`).
+  extra : BASELINE configs 3, 4, 5 at their stated sizes, once, outside the
+          headline regions, inputs synthesised on the device, each with its own
+          parity block against oracle/_ref (N > 1: config 3 only, as one fixed
+          job over the ranks = the strong-scaling figure).
 
 Launch:  python bench.py --gpus N --steps K --warmup W        (N=1)
          python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -66,6 +74,17 @@ def measured_traffic(bases_per_launch):
     except Exception:
         pass
     return None, None, None
+
+
+def measured_compare_pipes():
+    """ALU / LSU / issue-active percentages of hashjoin_kernel from the committed ncu capture (profiles/)."""
+    for nm in ("r02_compare_pipes.json", "r01_compare_pipes.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", nm)) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return {}
 
 
 def measured_peaks():
@@ -128,10 +147,29 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ data
 
-def make_fastas(n_genomes: int, n_bases: int, first: int, seed: int = 42):
+def _fasta_member(a):
     from supersampler_b200 import synth
-    fam = synth.Family(n_bases, seed)
-    return [fam.fasta(first + i) for i in range(n_genomes)], [f"g{first + i:05d}" for i in range(n_genomes)]
+    n_bases, seed, idx = a
+    fam = _fasta_member.fam.get((n_bases, seed))
+    if fam is None:
+        fam = _fasta_member.fam[(n_bases, seed)] = synth.Family(n_bases, seed)
+    return fam.fasta(idx)
+
+
+_fasta_member.fam = {}
+
+
+def make_fastas(n_genomes: int, n_bases: int, first: int, seed: int = 42, procs: int = 1):
+    """Members first .. first+n-1 of the C2 family as FASTA text (numpy streams: the same genome
+    whatever the rank layout).  procs > 1: worker processes (the reference arm of an N-GPU run
+    needs 64 x N genomes on one rank)."""
+    names = [f"g{first + i:05d}" for i in range(n_genomes)]
+    jobs = [(n_bases, seed, first + i) for i in range(n_genomes)]
+    if procs > 1 and n_genomes > 64:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(procs, n_genomes)) as pool:
+            return pool.map(_fasta_member, jobs, chunksize=4), names
+    return [_fasta_member(j) for j in jobs], names
 
 
 def write_files(fastas, names, d):
@@ -149,7 +187,51 @@ def scratch_dir():
     return tempfile.mkdtemp(prefix="spsp_bench_", dir=base)
 
 
+def scratch_free_bytes():
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    try:
+        st = os.statvfs(base)
+        return st.f_bavail * st.f_frsize
+    except OSError:
+        return 0
+
+
 # ------------------------------------------------------- reference CPU path
+
+def ref_sketch(paths, k, m, s, wd, cores):
+    """oracle/_ref/sub_sampler -f over `paths` -> (seconds, sketch gz paths in input order)."""
+    from oracle import oracle as O
+    fof = os.path.join(wd, "in.txt")
+    with open(fof, "w") as f:
+        f.write("\n".join(paths) + "\n")
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(O.REF_DIR, "sub_sampler"), "-f", fof, "-k", str(k), "-m", str(m), "-s", str(s),
+                    "-t", str(cores), "-v", "0"], cwd=wd, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, check=True)
+    t = time.perf_counter() - t0
+    return t, [os.path.join(wd, "subsampled_" + os.path.basename(p).split(".")[0] + ".gz") for p in paths]
+
+
+def ref_compare(sketch_paths, wd, tag="res", queries=None):
+    """oracle/_ref/comparator -> (wall seconds, its own 'Comparisons lasted' seconds, csv paths)."""
+    from oracle import oracle as O
+    skf = os.path.join(wd, tag + "_sk.txt")
+    with open(skf, "w") as f:
+        f.write("\n".join(sketch_paths) + "\n")
+    cmd = [os.path.join(O.REF_DIR, "comparator"), "-f", skf, "-o", os.path.join(wd, tag)]
+    if queries:
+        qf = os.path.join(wd, tag + "_q.txt")
+        with open(qf, "w") as f:
+            f.write("\n".join(queries) + "\n")
+        cmd += ["-q", qf]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, cwd=wd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, text=True, check=True)
+    t = time.perf_counter() - t0
+    lasted = None
+    for ln in r.stdout.splitlines():
+        if ln.startswith("Comparisons lasted"):
+            lasted = float(ln.split()[2])
+    return t, lasted, (os.path.join(wd, tag + "_containment.csv.gz"), os.path.join(wd, tag + "_jaccard.csv.gz"))
+
 
 def run_reference_step(paths, args, wd, cores):
     """One pass of the reference's own path: sub_sampler -f ... -t cores, then comparator.
@@ -159,26 +241,9 @@ def run_reference_step(paths, args, wd, cores):
         if f.startswith("subsampled_") or f.startswith("res_"):
             os.remove(os.path.join(wd, f))
     if O.have_ref():
-        fof = os.path.join(wd, "in.txt")
-        with open(fof, "w") as f:
-            f.write("\n".join(paths) + "\n")
-        t0 = time.perf_counter()
-        subprocess.run([os.path.join(O.REF_DIR, "sub_sampler"), "-f", fof, "-k", str(args.k), "-m", str(args.m),
-                        "-s", str(args.s), "-t", str(cores), "-v", "0"], cwd=wd, stdin=subprocess.DEVNULL,
-                       stdout=subprocess.DEVNULL, check=True)
-        t1 = time.perf_counter()
-        sk = [os.path.join(wd, "subsampled_" + os.path.basename(p).split(".")[0] + ".gz") for p in paths]
-        skf = os.path.join(wd, "sk.txt")
-        with open(skf, "w") as f:
-            f.write("\n".join(sk) + "\n")
-        r = subprocess.run([os.path.join(O.REF_DIR, "comparator"), "-f", skf, "-o", os.path.join(wd, "res")], cwd=wd,
-                           stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, text=True, check=True)
-        t2 = time.perf_counter()
-        lasted = None
-        for ln in r.stdout.splitlines():
-            if ln.startswith("Comparisons lasted"):
-                lasted = float(ln.split()[2])
-        return t1 - t0, t2 - t1, lasted, "reference"
+        t_sk, sk = ref_sketch(paths, args.k, args.m, args.s, wd, cores)
+        t_c, lasted, _ = ref_compare(sk, wd)
+        return t_sk, t_c, lasted, "reference"
     # C restatement (single-threaded per call; ctypes drops the GIL so threads scale)
     from concurrent.futures import ThreadPoolExecutor
     datas = [open(p, "rb").read() for p in paths]
@@ -191,34 +256,51 @@ def run_reference_step(paths, args, wd, cores):
     return t1 - t0, t2 - t1, t2 - t1, "port"
 
 
+def sketches_identical(ref_gz_paths, ours):
+    import gzip
+    n = 0
+    for p, sk in zip(ref_gz_paths, ours):
+        with gzip.open(p, "rb") as f:
+            n += int(f.read() == sk)
+    return n
+
+
+def csv_identical(csv_paths, names, query_size, inter, full_rows, sizes, S):
+    """Our containment / Jaccard CSV text (`-p 6`) against the files the reference comparator wrote."""
+    import gzip
+    out = {}
+    for path, tag, jac in ((csv_paths[0], "containment", False), (csv_paths[1], "jaccard", True)):
+        with gzip.open(path, "rb") as f:
+            ref = f.read()
+        ours = S.format_csv(names, query_size, inter, full_rows, sizes, jac, 6, 0.0)
+        out[f"{tag}_csv_identical"] = bool(ours == ref)
+    return out
+
+
 def reference_parity(wd, names, sketches, cmp_res, S):
     """Byte parity of this step's outputs with the files the unmodified reference just wrote for the same
     inputs: every gunzipped sketch, and both CSV matrices (`-p 6`).  Checker only, outside any timed region."""
-    import gzip
-    out = {"sketches_identical": 0, "sketches": len(names)}
-    for nm, sk in zip(names, sketches):
-        with gzip.open(os.path.join(wd, "subsampled_" + nm + ".gz"), "rb") as f:
-            out["sketches_identical"] += int(f.read() == sk)
+    sk_paths = [os.path.join(wd, "subsampled_" + nm + ".gz") for nm in names]
+    out = {"sketches_identical": sketches_identical(sk_paths, sketches), "sketches": len(names)}
     inter, sizes, full = cmp_res
-    csv_names = [os.path.join(wd, "subsampled_" + nm + ".gz") for nm in names]
-    for tag, jac in (("containment", False), ("jaccard", True)):
-        with gzip.open(os.path.join(wd, f"res_{tag}.csv.gz"), "rb") as f:
-            ref = f.read()
-        ours = S.format_csv(csv_names, len(names), inter, full, sizes, jac, 6, 0.0)
-        out[f"{tag}_csv_identical"] = bool(ours == ref)
+    out.update(csv_identical((os.path.join(wd, "res_containment.csv.gz"), os.path.join(wd, "res_jaccard.csv.gz")),
+                             sk_paths, len(names), inter, full, sizes, S))
     out["ok"] = bool(out["sketches_identical"] == out["sketches"] and out["containment_csv_identical"]
                      and out["jaccard_csv_identical"])
     return out
 
 
 def reference_arm(args, rank, world):
+    """The reference's own CPU implementation on the SAME job as the B200 arm at this N: 64 x N genomes
+    sketched with every host core and compared all-vs-all (single-threaded by construction)."""
     if rank != 0:
         return
     from oracle import oracle as O
     O.build(with_ref=os.path.isdir(O.REFERENCE_SRC))
     cores = os.cpu_count() or 1
-    fastas, names = make_fastas(args.genomes, args.bases, 0)
-    total_bases = args.genomes * args.bases
+    n_gen = args.genomes * max(1, args.gpus)
+    fastas, names = make_fastas(n_gen, args.bases, 0, procs=cores)
+    total_bases = n_gen * args.bases
     wd = scratch_dir()
     try:
         paths = write_files(fastas, names, wd)
@@ -234,18 +316,19 @@ def reference_arm(args, rank, world):
     finally:
         shutil.rmtree(wd, ignore_errors=True)
     step = t_all / args.steps
-    pairs = args.genomes * (args.genomes - 1) // 2
+    pairs = n_gen * (n_gen - 1) // 2
     value = total_bases / step / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(1, args.gpus)),
         "sketch_only_gbp_per_s": total_bases / statistics.mean(ts) / 1e9,
         "compare": {"pairs": pairs, "pairs_per_s": pairs / statistics.mean(tl), "seconds": statistics.mean(tl),
                     "note": "reference comparator is single-threaded; time = its own 'Comparisons lasted' line"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"full workload: {args.genomes} x {args.bases} bp, sub_sampler -f -t {cores} + comparator, files on tmpfs"},
+                         "sample": f"full workload of the {max(1, args.gpus)}-GPU job: {n_gen} x {args.bases} bp, "
+                                   f"sub_sampler -f -t {cores} + comparator, files on tmpfs"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -258,6 +341,310 @@ def workload_config(args, world):
             "k": args.k, "m": args.m, "s": args.s, "genomes_per_gpu": args.genomes, "bases_per_genome": args.bases,
             "ranks": world,
             "l2": "device-resident inputs rotate over replicas totalling > 126 MB (L2) between timed iterations"}
+
+
+# ------------------------------------------------------- extras: C3 / C4 / C5 at full size
+
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ResidentSet:
+    """Sketches of a job that runs as several device batches: the sketch bytes go to the host, the compare
+    elements of every batch are kept on the device (torch tensors: plumbing) for ONE compare at the end."""
+
+    def __init__(self, ctx, k, m, s):
+        self.ctx, self.k, self.m, self.s = ctx, k, m, s
+        self.sketches, self.sizes = [], []
+        self.mn, self.lo = [], []
+        self.scan_ms = self.post_ms = self.sketch_s = 0.0
+        self.hits = self.bases = self.batches = 0
+
+    def add_batch(self, d_words, n_bases, rec_begin, rec_end, rec_input, n_inputs, rec_device=None):
+        import torch
+        info = {}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sks = self.ctx.sketch_batch(None, n_bases, rec_begin, rec_end, rec_input, n_inputs, self.s,
+                                    device_ptr=d_words.data_ptr(), info=info, rec_device=rec_device)
+        off = np.asarray(info["elem_off"], np.int64)
+        e = int(off[-1])
+        if e:
+            a, b, _ = self.ctx.batch_element_ptrs()
+            dev = d_words.device
+            self.mn.append(torch.as_tensor(_DevArray(a, e, "<i4"), device=dev).clone())
+            self.lo.append(torch.as_tensor(_DevArray(b, e, "<i8"), device=dev).clone())
+        torch.cuda.synchronize()
+        self.sketch_s += time.perf_counter() - t0
+        self.sketches += sks
+        self.sizes.append(np.diff(off))
+        self.scan_ms += info["scan_ms"]; self.post_ms += info["post_ms"]
+        self.hits += info["n_hits"]; self.bases += n_bases; self.batches += 1
+
+    def elements(self):
+        import torch
+        sizes = np.concatenate(self.sizes) if self.sizes else np.zeros(0, np.int64)
+        mn = torch.cat(self.mn) if self.mn else torch.zeros(1, dtype=torch.int32, device="cuda")
+        lo = torch.cat(self.lo) if self.lo else torch.zeros(1, dtype=torch.int64, device="cuda")
+        return sizes, mn, lo
+
+    def compare(self, query_size=None):
+        """-> (inter, sizes, seconds, kernel_ms); all-vs-all (upper triangle valid) or rows of the first
+        query_size sketches against all."""
+        import torch
+        sizes, mn, lo = self.elements()
+        n = sizes.size
+        sk_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.ctx.cmp_load_device(sk_off, mn.data_ptr(), lo.data_ptr(), None)
+        if query_size is None:
+            inter = self.ctx.cmp_run((0, n), (0, n), True)
+        else:
+            inter = self.ctx.cmp_run((0, query_size), (0, n), False)
+        t = time.perf_counter() - t0
+        return inter, sizes.astype(np.uint64), t, self.ctx.cmp_kernel_ms()
+
+
+def _kernel_name(finfo):
+    return {2: "scan_rowbit_kernel", 1: "scan_filter_kernel(byte table)", 0: "scan_filter_kernel(bit table)"}.get(
+        finfo["kind"], "scan_dense_kernel")
+
+
+def extra_c3(S, SD, rank, world, dist, local_rank, cores, quick):
+    """BASELINE config 3 at its stated size: 1 024 x 5 Mbp, k31 m11 s=100, all-vs-all; one fixed job dealt over
+    the ranks (strong scaling): rank r sketches genomes [r*1024/W, (r+1)*1024/W), the elements are exchanged,
+    the 32x32 tiles are dealt round-robin.  Parity: reference sub_sampler on every genome (N=1, when the
+    scratch space allows) or on the first 128, reference comparator on the first 128 sketches."""
+    import torch
+    from supersampler_b200 import distributed as D
+    from oracle import oracle as O
+    k, m, s = 31, 11, 100.0
+    G, nb = (128, 1_000_000) if quick else (1024, 5_000_000)
+    per = G // world
+    g0 = rank * per
+    fam = SD.DeviceFamily(nb, seed=4242)
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
+    rs = ResidentSet(ctx, k, m, s)
+    bsz = max(1, min(200, (1 << 30) // (SD.words_per_input(nb) * 16)))
+    b0 = fam.packed_batch(g0, 1)
+    ctx.sketch_batch(None, *b0[1:], 1, s, device_ptr=b0[0].data_ptr())      # tables, buffers: outside the timed calls
+    for a in range(g0, g0 + per, bsz):
+        cnt = min(bsz, g0 + per - a)
+        buf, n_total, rb, re_, ri = fam.packed_batch(a, cnt)
+        rs.add_batch(buf, n_total, rb, re_, ri, cnt)
+        del buf
+    t_sk = torch.tensor([rs.sketch_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_sk, op=dist.ReduceOp.MAX)
+    # compare
+    cinfo = {}
+    if dist is None:
+        inter, sizes, t_cmp, cmp_ms = rs.compare()
+    else:
+        sizes_l, mn, lo = rs.elements()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        all_sizes, g_mn, g_lo, _ = D.exchange_tensors(sizes_l, mn, lo, None, False, torch.device("cuda", local_rank))
+        inter, sizes, _ = D.compare_gathered(all_sizes, g_mn, g_lo, None, rank, world, ctx, cinfo)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0, cinfo.get("kernel_ms", 0.0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_cmp, cmp_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        ctx.close()
+        return None
+    pairs = G * (G - 1) // 2
+    t_sk = float(t_sk.item())
+    keycmp = float((sizes.astype(np.float64).sum() * (G - 1)))          # sum over pairs of |K_i| + |K_j|
+    out = {"workload": f"C3: {G} x {nb} bp genomes, k{k} m{m} s{int(s)}, all-vs-all, one fixed job over {world} GPU(s)",
+           "scaling": "strong", "value_gbp_per_s": G * nb / (t_sk + t_cmp) / 1e9, "sketch_gbp_per_s": G * nb / t_sk / 1e9,
+           "sketch_s": t_sk, "compare_s": t_cmp, "scan_ms": rs.scan_ms, "postpass_ms": rs.post_ms,
+           "compare_kernel_ms": cmp_ms, "batches_per_rank": rs.batches, "kernel": _kernel_name(ctx.filter_info()),
+           "hits_per_rank": rs.hits, "elements": int(sizes.sum()), "pairs": pairs, "pairs_per_s": pairs / t_cmp,
+           "kernel_pairs_per_s": pairs / max(1e-9, cmp_ms * 1e-3), "key_comparisons_per_s": keycmp / max(1e-9, cmp_ms * 1e-3)}
+    # ---- parity against oracle/_ref (checker only, not timed)
+    if O.have_ref():
+        n_par = per if (world == 1 and scratch_free_bytes() > 2.5 * G * nb and not quick) else min(128, per)
+        n_cmp = min(128, n_par)
+        wd = scratch_dir()
+        try:
+            paths = []
+            for a in range(0, n_par, 64):
+                fas = fam.fasta(a, min(64, n_par - a))
+                paths += write_files(fas, [f"g{a + i:05d}" for i in range(len(fas))], wd)
+                del fas
+            t_ref, sk_paths = ref_sketch(paths, k, m, s, wd, cores)
+            for p_ in paths:
+                os.remove(p_)
+            ident = sketches_identical(sk_paths, rs.sketches[:n_par])
+            t_rc, lasted, csvs = ref_compare(sk_paths[:n_cmp], wd)
+            sub = np.ascontiguousarray(inter[:n_cmp, :n_cmp])
+            par = {"sketches": n_par, "sketches_identical": ident, "compare_subset": n_cmp,
+                   "reference_sketch_s": t_ref, "reference_sketch_gbp_per_s": n_par * nb / t_ref / 1e9,
+                   "reference_compare_s": lasted if lasted else t_rc,
+                   "reference_pairs_per_s": n_cmp * (n_cmp - 1) / 2 / (lasted if lasted else t_rc)}
+            par.update(csv_identical(csvs, sk_paths[:n_cmp], n_cmp, sub, False, sizes[:n_cmp], S))
+            par["ok"] = bool(ident == n_par and par["containment_csv_identical"] and par["jaccard_csv_identical"])
+            out["parity"] = par
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+    ctx.close()
+    return out
+
+
+def extra_c4(S, SD, local_rank, cores, threads, quick):
+    """BASELINE config 4: 1 Gbp read sets of 150 bp reads (6 666 667 records each), k31 m11 s1000.
+    `value`: reads resident in HBM (packed + record tables), one batch per read set.  `from_files`: the
+    public Pipeline on the FASTA files (read, clean, pack, H2D, scan, post-pass).  Parity: every sketch
+    against oracle/_ref sub_sampler on the same files (the reference uses one thread per file)."""
+    import torch
+    from oracle import oracle as O
+    k, m, s = 31, 11, 1000.0
+    n_sets, n_reads = (2, 200_000) if quick else (4, 6_666_667)
+    L = 150
+    rsrc = SD.DeviceReadSet(50_000_000 if not quick else 2_000_000, L, seed=7)
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
+    rs = ResidentSet(ctx, k, m, s)
+    wd = scratch_dir()
+    try:
+        paths = []
+        for i in range(n_sets):
+            codes = rsrc.codes(i, n_reads)
+            buf, n_total, b, e, inp = rsrc.packed(codes)
+            if i == 0:       # warm the context (tables, buffers) outside the timed calls
+                ctx.sketch_batch(None, n_total, None, None, None, 1, s, device_ptr=buf.data_ptr(),
+                                 rec_device=(b.data_ptr(), e.data_ptr(), inp.data_ptr(), n_reads))
+            rs.add_batch(buf, n_total, None, None, None, 1,
+                         rec_device=(b.data_ptr(), e.data_ptr(), inp.data_ptr(), n_reads))
+            p = os.path.join(wd, f"reads{i:02d}.fa")
+            with open(p, "wb") as f:
+                f.write(rsrc.fasta(codes))
+            paths.append(p)
+            del codes, buf, b, e, inp
+        torch.cuda.empty_cache()
+        bases = n_sets * n_reads * L
+        out = {"workload": f"C4: {n_sets} read sets of {n_reads} x {L} bp reads (2-line FASTA), k{k} m{m} s{int(s)}",
+               "value_gbp_per_s": bases / rs.sketch_s / 1e9, "sketch_s": rs.sketch_s, "scan_ms": rs.scan_ms,
+               "postpass_ms": rs.post_ms, "records_per_set": n_reads, "hits": rs.hits,
+               "kernel": _kernel_name(ctx.filter_info()),
+               "scan_tbp_per_s": rs.bases / max(1e-9, rs.scan_ms * 1e-3) / 1e12}
+        ctx.close()
+        # the public pipeline on the files
+        pl = S.Pipeline(k, m, s, device=local_rank, threads=threads)
+        pl.sketch(paths[:1])
+        info = {}
+        t0 = time.perf_counter()
+        sks_files = pl.sketch(paths, info=info)
+        t_files = time.perf_counter() - t0
+        pl.close()
+        out["from_files"] = {"gbp_per_s": bases / t_files / 1e9, "seconds": t_files, "host_threads": threads,
+                             "pack_s": info.get("pack_s"), "device_s": info.get("device_s"),
+                             "api": "supersampler_b200.Pipeline.sketch(paths of the FASTA files on tmpfs)"}
+        out["routes_agree"] = bool(sks_files == rs.sketches)
+        if O.have_ref():
+            t_ref, sk_paths = ref_sketch(paths, k, m, s, wd, cores)
+            ident = sketches_identical(sk_paths, rs.sketches)
+            out["parity"] = {"sketches": n_sets, "sketches_identical": ident, "reference_sketch_s": t_ref,
+                             "reference_sketch_gbp_per_s": bases / t_ref / 1e9,
+                             "reference_threads_used": min(cores, n_sets), "ok": bool(ident == n_sets and out["routes_agree"])}
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    return out
+
+
+def extra_c5(S, SD, local_rank, cores, quick):
+    """BASELINE config 5: 100 query sketches vs 10 000 reference sketches, k31 m13 s200, `-q` mode:
+    10 100 x 5 Mbp genomes sketched from HBM in 1 Gbp batches, Q x N compare on the device.
+    Parity: reference sub_sampler on the 100 queries + the first 156 references, reference
+    `comparator -q` on those 256; our Q x 256 block of the full answer must give the same CSV bytes."""
+    import torch
+    from oracle import oracle as O
+    k, m, s = 31, 13, 200.0
+    Q, R, nb = (10, 150, 1_000_000) if quick else (100, 10_000, 5_000_000)
+    N = Q + R
+    fam = SD.DeviceFamily(nb, seed=555)
+    ctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
+    rs = ResidentSet(ctx, k, m, s)
+    bsz = max(1, min(200, (1 << 30) // (SD.words_per_input(nb) * 16)))
+    b0 = fam.packed_batch(0, 1)
+    ctx.sketch_batch(None, *b0[1:], 1, s, device_ptr=b0[0].data_ptr())
+    for a in range(0, N, bsz):
+        cnt = min(bsz, N - a)
+        buf, n_total, rb, re_, ri = fam.packed_batch(a, cnt)
+        rs.add_batch(buf, n_total, rb, re_, ri, cnt)
+        del buf
+    inter, sizes, t_cmp, cmp_ms = rs.compare(query_size=Q)
+    pairs = Q * R
+    out = {"workload": f"C5: {Q} queries vs {R} references ({N} x {nb} bp genomes), k{k} m{m} s{int(s)}, -q mode",
+           "sketch_gbp_per_s": N * nb / rs.sketch_s / 1e9, "sketch_s": rs.sketch_s, "scan_ms": rs.scan_ms,
+           "postpass_ms": rs.post_ms, "batches": rs.batches, "kernel": _kernel_name(ctx.filter_info()),
+           "elements": int(sizes.sum()), "compare_s": t_cmp, "compare_kernel_ms": cmp_ms, "query_ref_pairs": pairs,
+           "pairs_per_s": pairs / t_cmp, "kernel_pairs_per_s": pairs / max(1e-9, cmp_ms * 1e-3),
+           "value_gbp_per_s": N * nb / (rs.sketch_s + t_cmp) / 1e9}
+    if O.have_ref():
+        n_ref = min(156, R)
+        sel = list(range(Q + n_ref))                    # queries first, then references: the comparator's order
+        wd = scratch_dir()
+        try:
+            paths = []
+            for a in range(0, len(sel), 64):
+                fas = fam.fasta(a, min(64, len(sel) - a))
+                paths += write_files(fas, [f"g{a + i:05d}" for i in range(len(fas))], wd)
+                del fas
+            t_ref, sk_paths = ref_sketch(paths, k, m, s, wd, cores)
+            for p_ in paths:
+                os.remove(p_)
+            ident = sketches_identical(sk_paths, [rs.sketches[i] for i in sel])
+            t_rc, lasted, csvs = ref_compare(sk_paths[Q:], wd, queries=sk_paths[:Q])
+            sub = np.ascontiguousarray(inter[:, :len(sel)])
+            par = {"sketches": len(sel), "of": N, "sketches_identical": ident, "compare_subset": f"{Q} x {len(sel)}",
+                   "reference_sketch_s": t_ref, "reference_sketch_gbp_per_s": len(sel) * nb / t_ref / 1e9,
+                   "reference_compare_s": lasted if lasted else t_rc}
+            par.update(csv_identical(csvs, sk_paths, Q, sub, True, sizes[:len(sel)], S))
+            par["ok"] = bool(ident == len(sel) and par["containment_csv_identical"] and par["jaccard_csv_identical"])
+            out["parity"] = par
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+    ctx.close()
+    return out
+
+
+def run_extras(S, rank, world, dist, local_rank, cores, threads, args):
+    """C3 / C4 / C5 of BASELINE.json at their stated sizes, run once, outside the headline timed regions.
+    N > 1: C3 only (a fixed job over the ranks: the strong-scaling figure)."""
+    import torch
+    from supersampler_b200 import synth_device as SD
+    extra = {}
+    todo = [c for c in args.extras.split(",") if c]
+    for name in todo:
+        if name != "c3" and world > 1:
+            continue
+        t0 = time.perf_counter()
+        try:
+            if name == "c3":
+                r = extra_c3(S, SD, rank, world, dist, local_rank, cores, args.quick_extras)
+            elif name == "c4":
+                r = extra_c4(S, SD, local_rank, cores, threads, args.quick_extras)
+            elif name == "c5":
+                r = extra_c5(S, SD, local_rank, cores, args.quick_extras)
+            else:
+                continue
+        except Exception as ex:                      # an extra must not take the headline line with it
+            import traceback
+            log(traceback.format_exc())
+            r = {"error": f"{type(ex).__name__}: {ex}"}
+            if dist is not None:
+                raise
+        torch.cuda.empty_cache()
+        if r is not None:
+            r["wall_s"] = time.perf_counter() - t0
+            extra[name] = r
+            log(f"[extra {name}] {json.dumps(r)}")
+    return extra
 
 
 # ------------------------------------------------------------- B200 arm
@@ -342,13 +729,13 @@ def b200_arm(args, rank, world, local_rank):
 
     class Resident:
         """Device-resident steps, `rdepth` batches in flight: the sketch of batch i runs on context i % rdepth from
-        a pool of host threads (the post-pass is a chain of small latency-bound kernels, so batches on different
-        streams overlap on the device); the compare stages run one at a time in step order on one thread (one
-        NCCL exchange in flight).  A context is reused only after its previous batch has been retired."""
+        a pool of host threads (batches on different streams overlap on the device); the compare stages run in
+        step order on `cdepth` threads (each context has its own NCCL communicator, so exchanges of different
+        contexts may be in flight together).  A context is reused only after its previous batch has been retired."""
 
         def __init__(self):
             self.sk_pool = ThreadPoolExecutor(rdepth)
-            self.cmp_pool = ThreadPoolExecutor(1)
+            self.cmp_pool = ThreadPoolExecutor(max(1, args.cmp_depth))
             self.inflight = []
 
         def _sketch(self, i):
@@ -421,39 +808,47 @@ def b200_arm(args, rank, world, local_rank):
         def finish(self, record):
             return self._note(self.stream.drain(), record)
 
-    def timed(runner, steps, warmup, ctx):
-        """K steps bracketed by barrier + synchronize; CUDA events on a stream the kernels are launched on;
-        the pipeline is drained inside the timed region (every step's results have reached the host)."""
+    def timed(runner, steps, warmup, ctx, min_total=0.5, max_regions=400):
+        """Timed regions of EXACTLY `steps` steps each, every one bracketed by barrier + synchronize, CUDA events on
+        a stream the kernels are launched on, the pipeline drained inside the region (every step's results have
+        reached the host), max over ranks.  Regions are repeated until >= min_total seconds have been measured
+        (a 20-step region of this workload lasts a few milliseconds); the caller reports the median region."""
         ext = torch.cuda.ExternalStream(ctx.stream(0))
         for i in range(warmup):
             runner.step(i, False)
         runner.finish(False)
-        barrier(); torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(ext)
-        out = None
-        for i in range(steps):
-            o = runner.step(warmup + i, True)
+        regions, out, n_done, total = [], None, warmup, 0.0
+        while True:
+            barrier(); torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record(ext)
+            for i in range(steps):
+                o = runner.step(n_done + i, True)
+                out = o if o is not None else out
+            o = runner.finish(True)
             out = o if o is not None else out
-        o = runner.finish(True)
-        out = o if o is not None else out
-        ev1.record(ext)
-        torch.cuda.synchronize(); barrier()
-        wall = time.perf_counter() - t0
-        dev = ev0.elapsed_time(ev1) / 1e3
-        t = torch.tensor([max(wall, dev)], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), out
+            ev1.record(ext)
+            torch.cuda.synchronize(); barrier()
+            wall = time.perf_counter() - t0
+            dev = ev0.elapsed_time(ev1) / 1e3
+            t = torch.tensor([max(wall, dev)], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_done += steps
+            regions.append(float(t.item()))              # identical on every rank: so is the decision to stop
+            total += regions[-1]
+            if total >= min_total or len(regions) >= max_regions:
+                return regions, out
 
     # nvidia-smi needs ~0.2 s to start reporting: sample over both timed regions (device busy throughout)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    t_res, (sks_res, cmp_res) = timed(Resident(), args.steps, args.warmup, dctxs[0])
-    t_e2e, (sks_e2e, cmp_e2e) = timed(HostBuffers(), args.steps, args.warmup, pctxs[0])
+    reg_res, (sks_res, cmp_res) = timed(Resident(), args.steps, args.warmup, dctxs[0], args.min_seconds)
+    reg_e2e, (sks_e2e, cmp_e2e) = timed(HostBuffers(), args.steps, args.warmup, pctxs[0], args.min_seconds)
+    t_res, t_e2e = statistics.median(reg_res), statistics.median(reg_e2e)
     # third region: the scan kernel alone (what roofline.achieved is quoted on): one launch per replica in turn
     # (> L2 between launches), CUDA events on the launching stream around each launch
     scan_alone = []
@@ -468,20 +863,69 @@ def b200_arm(args, rank, world, local_rank):
             if i >= args.warmup:
                 scan_alone.append(dctxs[0].scan_kernel_ms())
         assert int(d_cnt.item()) == stats["hits"], "scan alone and scan inside the step disagree on the hit count"
+        del d_hits
     clocks = sampler.stop() if rank == 0 else None
 
     # both paths must produce the same bytes / counts
     assert sks_res == sks_e2e, "device-resident and host-buffer paths disagree"
     assert np.array_equal(cmp_res[1], cmp_e2e[1])
     if rank == 0:
-        assert np.array_equal(cmp_res[0], cmp_e2e[0])
+        assert np.array_equal(np.triu(cmp_res[0], 1), np.triu(cmp_e2e[0], 1))
     if dist is not None and use_native:
         # the exchange inside the C ABI must give what the torch.distributed exchange gives
-        last = pipes[(args.warmup + args.steps - 1) % depth]
-        chk = D.allgather_compare_device(last.elem_off()[0], pctxs[pipes.index(last)], rank, world, {})
+        last = pipes[0]
+        chk = D.allgather_compare_device(last.elem_off()[0], pctxs[0], rank, world, {})
         assert np.array_equal(chk[1], cmp_res[1])
         if rank == 0:
             assert np.array_equal(np.triu(chk[0], 1), np.triu(cmp_res[0], 1)), "native and torch exchange disagree"
+
+    # ---- parity against the unmodified reference at this N (checker only, outside every timed region):
+    # every rank's FASTA files go to one scratch directory, rank 0 runs oracle/_ref over the 64 x N genomes and
+    # holds every sketch of the job and the N x N matrix of the last step against the reference's files.
+    parity, cpu_base = None, None
+    from oracle import oracle as O
+    if not args.no_cpu_baseline and (O.have_ref() or world == 1):
+        wd_box = [scratch_dir() if rank == 0 else None]
+        if dist is not None:
+            dist.broadcast_object_list(wd_box, src=0)
+        wd = wd_box[0]
+        try:
+            my_paths = write_files(fastas, names, wd)
+            all_sks, all_names = [sks_res], [names]
+            if dist is not None:
+                all_sks, all_names = [None] * world, [None] * world
+                dist.all_gather_object(all_sks, sks_res)
+                dist.all_gather_object(all_names, names)
+                barrier()
+            if rank == 0:
+                names_all = [n_ for part in all_names for n_ in part]
+                paths = [os.path.join(wd, n_ + ".fa") for n_ in names_all]
+                a, b, c, kind = run_reference_step(paths, args, wd, cores)
+                if kind == "reference":
+                    parity = reference_parity(wd, names_all, [x for part in all_sks for x in part], cmp_res, S)
+                    parity["n_gpus"] = world
+                    parity["checked"] = (f"all {len(names_all)} sketches of the {world}-GPU job and the "
+                                         f"{len(names_all)} x {len(names_all)} matrix of the last timed step")
+                tb = args.bases * len(names_all)
+                prs = len(names_all) * (len(names_all) - 1) // 2
+                cpu_base = {"value": tb / (a + b) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": f"full workload once: {len(names_all)} x {args.bases} bp, sub_sampler -f -t {cores} "
+                                      f"({a:.2f} s) + comparator ({b:.2f} s, single-threaded by construction)",
+                            "sketch_gbp_per_s": tb / a / 1e9, "compare_pairs_per_s": prs / (c if c else b)}
+            barrier()
+        finally:
+            if rank == 0:
+                shutil.rmtree(wd, ignore_errors=True)
+
+    finfo = dctxs[0].filter_info()
+    # free the headline's device state before the extras
+    del d_packed
+    for p_ in pipes:
+        p_.close()
+    for c_ in dctxs:
+        c_.close()
+    torch.cuda.empty_cache()
+    extra = run_extras(S, rank, world, dist, local_rank, cores, threads, args) if args.extras else {}
 
     if rank != 0:
         if dist is not None:
@@ -493,13 +937,13 @@ def b200_arm(args, rank, world, local_rank):
     total_bases = total_bases_rank * world
     pairs = n_gen_total * (n_gen_total - 1) // 2
     step_s = t_res / args.steps
+    val = lambda t: total_bases / (t / args.steps) / 1e9
     # the scan kernel's launch duration (CUDA events on its launching stream): quoted on the kernel-alone region;
     # inside the two pipelined regions it shares the SMs / the copy engines with other batches, those per-launch
     # figures are kept beside it
     scan_ms_value_region = statistics.mean(stats["scan_ms"])
     scan_ms_e2e_region = statistics.mean(x["scan_ms"] for x in stats["e2e"])
     scan_ms = statistics.mean(scan_alone)
-    finfo = dctxs[0].filter_info()
     scan_kernel_name = {2: "scan_rowbit_kernel (bank-private bit table + hashed m-mer table, DESIGN.md 3.3b)",
                         1: "scan_filter_kernel (byte table of phase masks, DESIGN.md 3.3)",
                         0: "scan_filter_kernel (bit table, DESIGN.md 3.3)"}.get(finfo["kind"], "scan_dense_kernel")
@@ -508,24 +952,32 @@ def b200_arm(args, rank, world, local_rank):
     sizes = cmp_res[1]
     e2 = stats["e2e"]
     mean = lambda key: statistics.mean(x[key] for x in e2)
+    cmp_kernel_ms = statistics.mean(stats["cmp_ms"])
+    keycmp = float(sizes.astype(np.float64).sum()) * (n_gen_total - 1)        # sum over pairs of |K_i| + |K_j|
+    cmp_ncu = measured_compare_pipes()
     line = {
-        "metric": METRIC, "value": total_bases / step_s / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": val(t_res), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": w_req, "warmup_done": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
-        "e2e": {"value": total_bases / (t_e2e / args.steps) / 1e9, "unit": UNIT,
+        "regions": {"note": f"timed regions of exactly {args.steps} steps each, repeated until >= {args.min_seconds} s were "
+                            "measured; value / e2e / ms_per_step are the MEDIAN region",
+                    "value": {"n": len(reg_res), "median": val(t_res), "min": val(max(reg_res)), "max": val(min(reg_res))},
+                    "e2e": {"n": len(reg_e2e), "median": val(t_e2e), "min": val(max(reg_e2e)), "max": val(min(reg_e2e))}},
+        "e2e": {"value": val(t_e2e), "unit": UNIT,
                 "h2d_bytes_per_step": int(mean("h2d_bytes")), "d2h_bytes_per_step": int(mean("d2h_bytes")),
                 "ms_per_step": t_e2e / args.steps * 1e3, "host_threads": threads,
                 "phases_ms": {"pack_and_h2d": mean("pack_s") * 1e3, "device": mean("device_s") * 1e3,
                               "assemble": mean("assemble_s") * 1e3, "scan_kernel": mean("scan_ms"),
                               "postpass_device": mean("post_ms"), "compare_kernel": mean("cmp_kernel_ms")},
-                "gpu_launches": int(sum(x["launches"] for x in e2)),
+                "gpu_launches": int(sum(x["launches"] for x in e2) / max(1, len(reg_e2e))),
                 "api": "supersampler_b200.BatchStream.submit(FASTA bytes in host memory) over two Pipelines "
                        "(.sketch() + .compare(), the compare of batch i overlapping the sketch of batch i+1)"},
         "pipelining": "off" if depth == 1 else
-                      f"value: {rdepth} batches in flight (sketches on {rdepth} contexts / streams, compare stages serialised on one thread); "
+                      f"value: {rdepth} batches in flight (sketches on {rdepth} contexts / streams, compare stages on "
+                      f"{max(1, args.cmp_depth)} thread(s)); "
                       "e2e: one batch deep (compare(i) on a background thread / second context while sketch(i+1) runs)",
-        "gpu_launches": stats["launches"],
+        "gpu_launches": int(stats["launches"] / max(1, len(reg_res))),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(n_total)[0], "traffic_source": measured_traffic(n_total)[1],
                      "algorithmic_bytes": int(algo_bytes), "peak_source": peak_src, "kernel": scan_kernel_name,
@@ -534,41 +986,33 @@ def b200_arm(args, rank, world, local_rank):
                      "kernel_ms_timed_in": f"kernel-alone region: {len(scan_alone)} launches over the rotating replicas, CUDA events on the launching stream",
                      "kernel_ms_in_value_region": scan_ms_value_region, "kernel_ms_in_e2e_region": scan_ms_e2e_region,
                      "kernel_share_of_step": scan_ms / (step_s * 1e3),
+                     "step_frac": algo_bytes * world / step_s / 1e9 / (peak * world),
+                     "step_frac_note": "the same algorithmic bytes over the whole `value` step (scan + post-pass + compare, "
+                                       "per GPU) instead of over the scan kernel alone",
                      "ncu_pipes_pct_of_peak": measured_traffic(n_total)[2],
                      "note": "the kernel that streams every input byte; the rest of the step works on n/s-sized data "
                              "(latency-bound post-pass, INT/LSU-bound compare), see DESIGN.md section 6"},
         "phases_ms": {"sketch": statistics.mean(stats["sketch_s"]) * 1e3,
                       "compare": statistics.mean(stats["compare_s"]) * 1e3,
                       "scan_kernel": scan_ms_value_region, "postpass_device": statistics.mean(stats["post_ms"]),
-                      "compare_kernel": statistics.mean(stats["cmp_ms"])},
+                      "compare_kernel": cmp_kernel_ms},
         "d2h_bytes_per_step": int(stats["d2h"]),
         "compare": {"pairs": pairs, "pairs_per_s": pairs / statistics.mean(stats["compare_s"]),
-                    "kernel_pairs_per_s": pairs / max(1e-9, statistics.mean(stats["cmp_ms"]) * 1e-3),
-                    "elements": int(sizes.sum())},
+                    "kernel_pairs_per_s": pairs / max(1e-9, cmp_kernel_ms * 1e-3),
+                    "elements": int(sizes.sum()),
+                    "roofline": {"bound": "INT/LSU (shared-memory hash join), not HBM",
+                                 "key_comparisons_per_s": keycmp / max(1e-9, cmp_kernel_ms * 1e-3),
+                                 "unit_note": "one pair = |K_i| + |K_j| key comparisons (SURVEY 8d); kernel time = max over "
+                                              "ranks of hashjoin_kernel on this step's tiles",
+                                 **cmp_ncu}},
+        "parity_vs_reference": parity,
     }
-    # CPU baseline on this box's host cores (rank 0, N=1 only): the reference binaries on the same workload
-    if world == 1 and not args.no_cpu_baseline:
-        wd = scratch_dir()
-        wd_keep = wd
-        try:
-            paths = write_files(fastas, names, wd)
-            a, b, c, kind = run_reference_step(paths, args, wd, cores)
-            for p_ in paths:
-                os.remove(p_)
-        except Exception:
-            shutil.rmtree(wd, ignore_errors=True)
-            raise
-        # the same run is the parity check at full size: the reference's files against this step's results
-        parity = None
-        if kind == "reference":
-            parity = reference_parity(wd_keep, names, sks_res, cmp_res, S)
-        line["parity_vs_reference"] = parity
-        shutil.rmtree(wd, ignore_errors=True)
-        line["cpu_baseline"] = {"value": total_bases / (a + b) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"full workload once: {args.genomes} x {args.bases} bp, sub_sampler -f -t {cores} "
-                                          f"({a:.2f} s) + comparator ({b:.2f} s, single-threaded by construction)",
-                                "sketch_gbp_per_s": total_bases / a / 1e9,
-                                "compare_pairs_per_s": pairs / (c if c else b)}
+    if cpu_base is not None and world == 1:
+        line["cpu_baseline"] = cpu_base
+    elif cpu_base is not None:
+        line["reference_same_job"] = cpu_base
+    if extra:
+        line["extra"] = extra
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -588,10 +1032,14 @@ def main():
     ap.add_argument("-k", type=int, default=31)
     ap.add_argument("-m", type=int, default=11)
     ap.add_argument("-s", type=float, default=1000.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run (cpu_baseline + parity)")
     ap.add_argument("--no-pipelining", action="store_true", help="run sketch and compare of a step back to back")
     ap.add_argument("--depth", type=int, default=4, help="device-resident path: batches in flight")
+    ap.add_argument("--cmp-depth", type=int, default=2, help="device-resident path: compare stages in flight")
     ap.add_argument("--threads", type=int, default=0, help="host packing threads per rank (default: cores / ranks)")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step timed region until this much was measured")
+    ap.add_argument("--extras", default="c3,c4,c5", help="full-size BASELINE configs run once after the headline ('' = none)")
+    ap.add_argument("--quick-extras", action="store_true", help="small shapes of the extras (smoke run)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -154,6 +154,10 @@ int spsp_cmp_last_kernel_ms(spsp_ctx *ctx, float *ms);
  * Records are described by host arrays (n_rec entries, ascending, global base
  * offsets into the packed buffer): [rec_begin, rec_end) and the input each
  * record belongs to (0 <= rec_input < n_inputs, non-decreasing).
+ * The three record arrays may also be DEVICE memory (all three): they are then
+ * used in place, without validation or copy (read sets of short reads carry
+ * millions of records per batch; a caller that keeps them resident pays the
+ * upload once).
  * Result pointers stay valid until the next batch call on the same slot. */
 typedef struct {
     const uint8_t *body;         /* sketch bytes after the header line, inputs back to back   */

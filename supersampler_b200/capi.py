@@ -636,12 +636,21 @@ class DeviceContext:
         return int(p.value or 0)
 
     def sketch_batch(self, words, n_bases: int, rec_begin, rec_end, rec_input, n_inputs: int, s: float,
-                     abundance: int = 1, slot: int = 0, device_ptr: Optional[int] = None, info: Optional[dict] = None):
+                     abundance: int = 1, slot: int = 0, device_ptr: Optional[int] = None, info: Optional[dict] = None,
+                     rec_device: Optional[Tuple[int, int, int, int]] = None):
         """Scan + device post-pass of a whole batch.  `words` is a host array (copied) unless
-        device_ptr gives a device-resident packed buffer.  Returns the sketch bytes of every input."""
-        rec_begin = np.ascontiguousarray(rec_begin, np.uint64)
-        rec_end = np.ascontiguousarray(rec_end, np.uint64)
-        rec_input = np.ascontiguousarray(rec_input, np.uint32)
+        device_ptr gives a device-resident packed buffer.  rec_device = (d_begin, d_end, d_input, n_rec)
+        passes record tables that already live on the device.  Returns the sketch bytes of every input."""
+        if rec_device is not None:
+            class _P:                                     # raw device pointers behind the ndarray attributes used below
+                def __init__(self, ptr, n):
+                    self.ctypes = type("c", (), {"data": ptr})
+                    self.size = n
+            rec_begin, rec_end, rec_input = (_P(rec_device[i], rec_device[3]) for i in range(3))
+        else:
+            rec_begin = np.ascontiguousarray(rec_begin, np.uint64)
+            rec_end = np.ascontiguousarray(rec_end, np.uint64)
+            rec_input = np.ascontiguousarray(rec_input, np.uint32)
         res = BatchResult()
         if device_ptr is None:
             words = np.ascontiguousarray(words, np.uint32)

@@ -122,6 +122,12 @@ struct spsp_ctx {
 };
 
 static int ensure_packed(struct Slot &s, uint64_t words);
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice;
+}
 static int check_records(const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec,
                          uint64_t n_bases, uint32_t n_inputs, const char *who);
 
@@ -620,14 +626,27 @@ static int batch_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n
                       unsigned abundance, spsp_batch_result *res)
 {
     if (!res) return fail(-3, "spsp_sketch_batch: null result");
-    { int rc_ = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_sketch_batch"); if (rc_) return rc_; }
     cudaStream_t st = s.stream;
-    const size_t nr = n_rec ? n_rec : 1;
-    CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
-    if (n_rec) {
-        CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, st));
+    // Record tables may already live on the device (a caller that keeps its inputs resident: millions of short
+    // records cost more to re-validate and re-upload than to scan); they are then used in place, unchecked.
+    const bool rec_on_device = n_rec && is_device_ptr(rec_begin);
+    const uint64_t *d_rec_begin = rec_begin, *d_rec_end = rec_end;
+    const uint32_t *d_rec_input = rec_input;
+    if (rec_on_device) {
+        if (!is_device_ptr(rec_end) || !is_device_ptr(rec_input))
+            return fail(-3, "spsp_sketch_batch: record arrays must all be host or all be device memory");
+    } else {
+        { int rc_ = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_sketch_batch"); if (rc_) return rc_; }
+        const size_t nr = n_rec ? n_rec : 1;
+        CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
+        if (n_rec) {
+            CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, st));
+        }
+        d_rec_begin = static_cast<const uint64_t *>(s.b_rec_begin.p);
+        d_rec_end = static_cast<const uint64_t *>(s.b_rec_end.p);
+        d_rec_input = static_cast<const uint32_t *>(s.b_rec_input.p);
     }
     // scan (grow the hit buffer and rescan if the estimate was too small)
     const double p = (double)c->thr / 18446744073709551616.0;
@@ -652,9 +671,7 @@ static int batch_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n
     if (!s.pp) s.pp = postpass_buffers_create();
     PostpassIn in{};
     in.d_packed = d_packed; in.n_bases = n_bases; in.d_hits = s.d_hits; in.n_hits = n_hits;
-    in.d_rec_begin = static_cast<const uint64_t *>(s.b_rec_begin.p);
-    in.d_rec_end = static_cast<const uint64_t *>(s.b_rec_end.p);
-    in.d_rec_input = static_cast<const uint32_t *>(s.b_rec_input.p);
+    in.d_rec_begin = d_rec_begin; in.d_rec_end = d_rec_end; in.d_rec_input = d_rec_input;
     in.n_rec = n_rec; in.n_inputs = n_inputs; in.k = c->k; in.m = c->m; in.abundance = abundance;
     CK(cudaEventRecord(s.ev1, st));
     cudaError_t e = postpass_run(s.pp, in, &s.last_batch, st);
