@@ -648,44 +648,55 @@ static int batch_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n
         d_rec_end = static_cast<const uint64_t *>(s.b_rec_end.p);
         d_rec_input = static_cast<const uint32_t *>(s.b_rec_input.p);
     }
-    // scan (grow the hit buffer and rescan if the estimate was too small)
+    // scan + post-pass are enqueued back to back: the hit count stays on the device, the host synchronises once,
+    // when the sketch bytes have arrived.  A capacity that turns out too small (hits, pieces, bytes) makes the
+    // pass report a retry; the buffers remember the larger size.
     const double p = (double)c->thr / 18446744073709551616.0;
     uint64_t guess = (uint64_t)((double)n_bases * p * 1.5) + 4096;
     if (guess > n_bases + 1) guess = n_bases + 1;
     int rc = ensure_hits(s, guess);
     if (rc) return rc;
-    uint64_t n_hits = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        ScanOut so{s.d_hits, s.d_count, s.hits_cap};
-        rc = launch_scan(c, s, d_packed, n_bases, so);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        n_hits = *s.h_count;
-        if (n_hits <= s.hits_cap) break;
-        rc = ensure_hits(s, n_hits + n_hits / 8 + 1024);
-        if (rc) return rc;
-    }
-    float scan_ms = 0;
-    CK(cudaEventElapsedTime(&scan_ms, s.ev0, s.ev1));
     if (!s.pp) s.pp = postpass_buffers_create();
-    PostpassIn in{};
-    in.d_packed = d_packed; in.n_bases = n_bases; in.d_hits = s.d_hits; in.n_hits = n_hits;
-    in.d_rec_begin = d_rec_begin; in.d_rec_end = d_rec_end; in.d_rec_input = d_rec_input;
-    in.n_rec = n_rec; in.n_inputs = n_inputs; in.k = c->k; in.m = c->m; in.abundance = abundance;
-    CK(cudaEventRecord(s.ev1, st));
-    cudaError_t e = postpass_run(s.pp, in, &s.last_batch, st);
-    if (e != cudaSuccess) {
-        s.has_batch = false;
-        return fail(e == cudaErrorInvalidValue ? -4 : -1, std::string("device post-pass: ") + cudaGetErrorString(e));
+    uint64_t n_hits = 0;
+    float scan_ms = 0, post_ms = 0;
+    uint32_t launched = 0;
+    bool rescan = true;
+    for (int attempt = 0;; attempt++) {
+        if (attempt == 6) return fail(-1, "spsp_sketch_batch: capacities did not converge");
+        if (rescan) {
+            ScanOut so{s.d_hits, s.d_count, s.hits_cap};
+            rc = launch_scan(c, s, d_packed, n_bases, so);
+            if (rc) return rc;
+        } else {
+            CK(cudaEventRecord(s.ev1, st));
+        }
+        PostpassIn in{};
+        in.d_packed = d_packed; in.n_bases = n_bases; in.d_hits = s.d_hits; in.d_hit_count = s.d_count; in.hits_cap = s.hits_cap;
+        in.d_rec_begin = d_rec_begin; in.d_rec_end = d_rec_end; in.d_rec_input = d_rec_input;
+        in.n_rec = n_rec; in.n_inputs = n_inputs; in.k = c->k; in.m = c->m; in.abundance = abundance;
+        cudaError_t e = postpass_run(s.pp, in, &s.last_batch, st);
+        if (e != cudaSuccess) {
+            s.has_batch = false;
+            return fail(e == cudaErrorInvalidValue ? -4 : -1, std::string("device post-pass: ") + cudaGetErrorString(e));
+        }
+        launched += s.last_batch.kernels_launched;
+        n_hits = s.last_batch.n_hits;
+        if (s.last_batch.retry == PP_RETRY_HITS) {
+            rc = ensure_hits(s, n_hits + n_hits / 8 + 1024);
+            if (rc) return rc;
+            rescan = true;
+            continue;
+        }
+        if (s.last_batch.retry == PP_RETRY_POSTPASS) { rescan = false; continue; }
+        break;
     }
     CK(cudaEventRecord(s.ev2, st));
     CK(cudaEventSynchronize(s.ev2));
-    float post_ms = 0;
+    if (rescan) CK(cudaEventElapsedTime(&scan_ms, s.ev0, s.ev1));
     CK(cudaEventElapsedTime(&post_ms, s.ev1, s.ev2));
     {
         std::lock_guard<std::mutex> g(c->mu);
-        c->launches += s.last_batch.kernels_launched;
+        c->launches += launched;
     }
     s.has_batch = true;
     s.last_batch_inputs = n_inputs;

@@ -16,8 +16,9 @@ struct PostpassBuffers;      // grow-only device scratch, owned by the context
 struct PostpassIn {
     const uint32_t *d_packed;        // 2-bit sequence of the whole batch
     uint64_t n_bases;
-    const spsp_hit *d_hits;          // scan output (unordered)
-    uint64_t n_hits;
+    const spsp_hit *d_hits;          // scan output (unordered), hits_cap entries
+    const unsigned long long *d_hit_count;   // device: hits the scan found (may exceed hits_cap: then nothing is used)
+    uint64_t hits_cap;
     const uint64_t *d_rec_begin;     // [n_rec] global base offsets, ascending
     const uint64_t *d_rec_end;       // [n_rec]
     const uint32_t *d_rec_input;     // [n_rec] input (file) of each record
@@ -37,12 +38,17 @@ struct PostpassOut {
     const uint32_t *d_minim;
     const uint64_t *d_klo, *d_khi;   // d_khi null when k <= 32
     uint64_t n_elems;
-    uint32_t kernels_launched;       // hand-written kernels (CUB's are not counted)
+    uint64_t n_hits;                 // what the scan counted
+    uint32_t kernels_launched;       // kernels of this file (cub::DeviceRadixSort's, large batches only, are not counted)
+    int retry;                       // PP_RETRY_*: a capacity was too small, nothing above is valid, run again
 };
+enum { PP_RETRY_NONE = 0, PP_RETRY_HITS = 1 /* grow the hit buffer, rescan */, PP_RETRY_POSTPASS = 2 /* rerun the post-pass */ };
 
 PostpassBuffers *postpass_buffers_create();
 void postpass_buffers_destroy(PostpassBuffers *b);
-// Runs on `st` and synchronises it before returning.  Returns cudaSuccess or the first error.
+// Enqueues the whole pass on `st` behind the scan (no host round trip in between: the hit count stays on the
+// device), then synchronises once and delivers the results.  Returns cudaSuccess or the first error;
+// out->retry != 0 asks the caller to run again (capacities are remembered in the buffers).
 cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *out, cudaStream_t st);
 
 }  // namespace spsp
