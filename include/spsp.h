@@ -131,13 +131,14 @@ int spsp_cmp_load_device(spsp_ctx *ctx, uint32_t n_sketches, const uint64_t *ske
  * out[(i-row_begin)*ld + (j-col_begin)] += |K_i ∩ K_j| (row-major uint32,
  * ld >= col_end-col_begin, zeroed by the caller).  With symmetric != 0 only
  * tiles on or above the diagonal are computed (entries with i < j are valid).
- * tile_rank / tile_ranks deal the tile list round-robin for multi-GPU runs
- * (0 / 1 for a single GPU).  out is HOST memory (synchronous call). */
+ * tile_rank / tile_ranks deal the work units (a column tile x a run of row
+ * tiles) round-robin for multi-GPU runs (0 / 1 for a single GPU).  out is HOST
+ * memory; load + run synchronise once, when the counts have arrived. */
 int spsp_cmp_run(spsp_ctx *ctx, uint32_t row_begin, uint32_t row_end, uint32_t col_begin,
                  uint32_t col_end, int symmetric, uint32_t tile_rank, uint32_t tile_ranks,
                  uint32_t *out, uint64_t ld);
-/* Device-output variant: d_out is a device pointer (not zeroed by the call),
- * launches on slot 0's stream without synchronising. */
+/* Device-output variant: d_out is a device pointer (not zeroed by the call);
+ * returns when the counts are in d_out. */
 int spsp_cmp_run_device(spsp_ctx *ctx, uint32_t row_begin, uint32_t row_end, uint32_t col_begin,
                         uint32_t col_end, int symmetric, uint32_t tile_rank, uint32_t tile_ranks,
                         uint32_t *d_out, uint64_t ld);
@@ -223,20 +224,33 @@ int spsp_dense_stats_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const uin
  * The compare stage's only exchange step, on NCCL over NVLink (libnccl.so.2 is
  * loaded at run time; single-GPU callers never need it).  Rank 0 creates an id
  * (spsp_nccl_unique_id, 128 bytes), hands it to every rank by any side channel
- * (torch.distributed broadcast, MPI, a file), every rank calls spsp_nccl_init.
+ * (torch.distributed broadcast, MPI, a file), every rank calls spsp_nccl_init
+ * (at most 64 ranks).  A context owns its communicator, so exchanges of
+ * different contexts may be in flight at the same time.
  *
- * spsp_cmp_exchange_batch: all-vs-all compare of the union of the sketches the
- * last batch left on every rank's device (rank-major order): all-gather of
- * counts, then of the sizes and element arrays (one NCCL group, in place),
- * sketch ranges built on the device, the 32x32 tiles dealt round-robin to the
- * ranks, hash join, sum-reduce of the disjoint tiles to rank 0.  On rank 0
- * inter_out (row-major, ld >= N, zeroed by the call's semantics: overwritten)
- * receives the N x N counts (entries i < j valid); every rank receives
- * sizes_out[N] (|K_i|) and *n_total = N.  cap_sketches = capacity of the output
- * arrays in sketches (-2 with *n_total set when too small).  Collective: every
- * rank must call it. */
+ * spsp_cmp_exchange: every rank brings n_local sketches -- the first q_local
+ * of them queries (Comparator.cpp:7-21, 512-515: `-q` lists go first) -- as
+ * device-resident element arrays plus a host size list.  The union, in the
+ * order [queries of rank 0, 1, ... | references of rank 0, 1, ...], is compared
+ * all-vs-all (symmetric != 0; then q_local == n_local) or queries x all
+ * (Comparator.cpp:328-359).  One payload all-gather into fixed-capacity slots
+ * (counts travel inside the payload), the tile plan and the join on the device,
+ * the owned tiles sent to rank 0, one host synchronisation.  Rank 0 receives
+ * inter_out (rows x columns, row-major, ld >= columns, overwritten; all-vs-all:
+ * entries i < j valid); every rank receives sizes_out[columns] (|K_i|, may be
+ * NULL), *n_rows and *n_cols.  cap_rows / cap_cols = capacity of the outputs
+ * (-2 with the dimensions set when too small).  Collective: every rank must
+ * call it with the same `symmetric`; argument errors that only one rank can
+ * see travel in the payload, so no rank is left waiting.
+ *
+ * spsp_cmp_exchange_batch: the same, all-vs-all, for the sketches the last
+ * batch on `slot` left on every rank's device. */
 int spsp_nccl_unique_id(uint8_t *id128);
 int spsp_nccl_init(spsp_ctx *ctx, const uint8_t *id128, int rank, int world);
+int spsp_cmp_exchange(spsp_ctx *ctx, uint32_t n_local, uint32_t q_local, const uint64_t *sizes_local,
+                      const uint32_t *d_minimizer, const uint64_t *d_kmer_lo, const uint64_t *d_kmer_hi, int symmetric,
+                      uint32_t *inter_out, uint64_t ld, uint64_t *sizes_out, uint32_t cap_rows, uint32_t cap_cols,
+                      uint32_t *n_rows, uint32_t *n_cols, float *kernel_ms);
 int spsp_cmp_exchange_batch(spsp_ctx *ctx, int slot, uint32_t *inter_out, uint64_t ld, uint64_t *sizes_out,
                             uint32_t cap_sketches, uint32_t *n_total, float *kernel_ms);
 

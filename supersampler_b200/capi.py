@@ -101,6 +101,9 @@ def device_lib():
         L.spsp_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.spsp_cmp_exchange_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                               C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.spsp_cmp_exchange.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32,
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.spsp_batch_reserve.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
         L.spsp_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
         L.spsp_sketch_batch_staged.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -736,6 +739,28 @@ class DeviceContext:
             info.update(kernel_ms=float(ms.value), launches=self.launches() - l0)
         nt = int(n.value)
         return (inter[:nt, :nt] if inter is not None else None), sizes[:nt]
+
+    def cmp_exchange(self, sizes_local, d_minim: int, d_klo: int, d_khi: Optional[int], n_queries_local: Optional[int],
+                     cap_rows: int, cap_cols: int, rank: int, info: Optional[dict] = None):
+        """Collective compare of the union of every rank's sketches (device-resident elements, host size list).
+        n_queries_local = None: all-vs-all; else this rank's first n_queries_local sketches are queries and the
+        result is queries x all, in the order [all queries rank-major | all references rank-major].
+        -> (inter[rows, cols] uint32 on rank 0 (None elsewhere), sizes[cols] uint64)."""
+        sizes_local = np.ascontiguousarray(sizes_local, np.uint64)
+        n_local = int(sizes_local.size)
+        sym = n_queries_local is None
+        q_local = n_local if sym else int(n_queries_local)
+        inter = np.zeros((cap_rows, cap_cols), np.uint32) if rank == 0 else None
+        sizes = np.zeros(cap_cols, np.uint64)
+        nr, nc, ms = C.c_uint32(), C.c_uint32(), C.c_float()
+        l0 = self.launches()
+        _dcheck(self.L.spsp_cmp_exchange(self.h, n_local, q_local, sizes_local.ctypes.data, d_minim, d_klo, d_khi, int(sym),
+                                         inter.ctypes.data if inter is not None else None, cap_cols, sizes.ctypes.data,
+                                         cap_rows, cap_cols, C.byref(nr), C.byref(nc), C.byref(ms)), "spsp_cmp_exchange")
+        if info is not None:
+            info.update(kernel_ms=float(ms.value), launches=self.launches() - l0)
+        r_, c_ = int(nr.value), int(nc.value)
+        return (np.ascontiguousarray(inter[:r_, :c_]) if inter is not None else None), sizes[:c_]
 
     def cmp_load_batch(self, slot: int = 0):
         _dcheck(self.L.spsp_cmp_load_batch(self.h, slot), "spsp_cmp_load_batch")

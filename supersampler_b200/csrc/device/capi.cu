@@ -109,14 +109,15 @@ struct spsp_ctx {
     bool has_hi = false, owns_cmp = false;
     CmpData cmp{};
     DevBuf b_minim, b_klo, b_khi, b_sk_off, b_chunk_off, b_tiles, b_out;
-    PinBuf p_stage, p_out;
-    cudaEvent_t cev0 = nullptr, cev1 = nullptr;
+    PinBuf p_stage, p_out, p_units, p_skoff;
+    cudaEvent_t cev0 = nullptr, cev1 = nullptr, ev_stage = nullptr;   // ev_stage: last copy out of the pinned staging buffers
     bool cmp_timed = false;
     // multi-GPU exchange (one process per GPU)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
-    DevBuf x_hdr, x_sizes, x_klo, x_khi, x_min, x_begin, x_end, x_compact, x_out;
-    PinBuf xp_hdr, xp_sizes, xp_out;
+    DevBuf x_hdrsz, x_klo, x_khi, x_min, x_begin, x_end, x_compact, x_units, x_dims, x_tiles, x_recv, x_neg;
+    PinBuf xp_hdrsz, xp_out, xp_neg;
+    uint64_t x_ncap = 0, x_qcap = 0, x_ecap = 0;      // negotiated slot capacities (identical on every rank)
     uint64_t launches = 0;
     std::mutex mu;
 };
@@ -273,6 +274,7 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
     }
     CK(cudaEventCreate(&c->cev0));
     CK(cudaEventCreate(&c->cev1));
+    CK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
     *out = c;                        // the q-gram filter table is built on first scan
     return 0;
 }
@@ -281,7 +283,7 @@ static void free_cmp(spsp_ctx *c)
 {
     c->b_minim.release(); c->b_klo.release(); c->b_khi.release(); c->b_sk_off.release();
     c->b_chunk_off.release(); c->b_tiles.release(); c->b_out.release();
-    c->p_stage.release(); c->p_out.release();
+    c->p_stage.release(); c->p_out.release(); c->p_units.release(); c->p_skoff.release();
     c->owns_cmp = false;
     c->n_sketches = 0;
 }
@@ -314,6 +316,7 @@ extern "C" int spsp_destroy(spsp_ctx *c)
     cudaFree(c->d_exact);
     if (c->cev0) cudaEventDestroy(c->cev0);
     if (c->cev1) cudaEventDestroy(c->cev1);
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
     delete c;
     return 0;
 }
@@ -466,6 +469,7 @@ extern "C" int spsp_stream(spsp_ctx *c, int slot, void **stream)
 
 // ----------------------------------------------------------------- compare
 
+// Everything below is enqueued on slot 0's stream; nothing synchronises until a result is needed on the host.
 static int finish_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *sketch_off)
 {
     cudaStream_t st = c->slots[0].stream;
@@ -474,7 +478,13 @@ static int finish_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *ske
     for (uint32_t i = 0; i < n_sketches; i++)
         if (sketch_off[i] > sketch_off[i + 1]) return fail(-3, "spsp_cmp_load: sketch_off not monotone");
     CK(c->b_sk_off.ensure((size_t)(n_sketches + 1) * sizeof(uint64_t)));
-    CK(cudaMemcpyAsync(c->b_sk_off.p, sketch_off, (size_t)(n_sketches + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    // the caller's offsets may be gone before the copy runs: stage them in pinned memory (the event orders this
+    // against the previous copy out of the staging buffer; in the steady state it has long completed)
+    CK(cudaEventSynchronize(c->ev_stage));
+    CK(c->p_skoff.ensure((size_t)(n_sketches + 1) * sizeof(uint64_t)));
+    memcpy(c->p_skoff.p, sketch_off, (size_t)(n_sketches + 1) * sizeof(uint64_t));
+    CK(cudaMemcpyAsync(c->b_sk_off.p, c->p_skoff.p, (size_t)(n_sketches + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ev_stage, st));
     double avg = n_sketches ? (double)c->n_elems / n_sketches : 0.0;
     uint64_t chunks = (uint64_t)std::ceil(32.0 * avg / (0.7 * CMP_CAP));
     if (chunks < 1) chunks = 1;
@@ -484,9 +494,8 @@ static int finish_cmp_load(spsp_ctx *c, uint32_t n_sketches, const uint64_t *ske
     c->cmp.sk_off = static_cast<const uint64_t *>(c->b_sk_off.p);
     c->cmp.sk_end = nullptr;
     c->cmp.chunk_off = static_cast<uint64_t *>(c->b_chunk_off.p);
-    CK(launch_chunk_offsets(c->cmp, n_sketches, c->n_chunks, c->m, st));
+    CK(launch_chunk_offsets(c->cmp, n_sketches, nullptr, c->n_chunks, c->m, st));
     c->launches++;
-    CK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -533,11 +542,22 @@ extern "C" int spsp_cmp_load_device(spsp_ctx *c, uint32_t n_sketches, const uint
     if (!c || !sketch_off_host) return fail(-3, "spsp_cmp_load_device: bad args");
     if ((c->k > 32) != (d_kmer_hi != nullptr)) return fail(-3, "spsp_cmp_load_device: kmer_hi must be given iff k > 32");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->slots[0].stream));
     c->owns_cmp = false;
     c->has_hi = d_kmer_hi != nullptr;
     c->cmp.minim = d_minimizer; c->cmp.klo = d_kmer_lo; c->cmp.khi = d_kmer_hi;
     return finish_cmp_load(c, n_sketches, sketch_off_host);
+}
+
+// Units of the tile grid in dealing order (the device twin is exchange_plan_kernel): column tile jb, row tiles in
+// runs of rt; symmetric: only row tiles 0 .. jb.  f(index, jb, ib0, n_ib).
+template <class F>
+static void for_each_unit(uint32_t nI, uint32_t nJ, bool symmetric, uint32_t rt, F f)
+{
+    uint64_t idx = 0;
+    for (uint32_t jb = 0; jb < nJ; jb++) {
+        const uint32_t lim = symmetric ? std::min(jb + 1, nI) : nI;
+        for (uint32_t ib0 = 0; ib0 < lim; ib0 += rt, idx++) f(idx, jb, ib0, std::min(rt, lim - ib0));
+    }
 }
 
 static int cmp_run_impl(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint32_t col_end,
@@ -550,31 +570,40 @@ static int cmp_run_impl(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint3
     if (symmetric && (row_begin != col_begin || row_end != col_end))
         return fail(-3, "spsp_cmp_run: symmetric needs identical row and column ranges");
     cudaStream_t st = c->slots[0].stream;
-    uint32_t nI = (row_end - row_begin + 31) / 32, nJ = (col_end - col_begin + 31) / 32;
-    std::vector<uint2> tiles;
-    uint64_t t = 0;
-    for (uint32_t ib = 0; ib < nI; ib++)
-        for (uint32_t jb = symmetric ? ib : 0; jb < nJ; jb++, t++)
-            if (t % tile_ranks == tile_rank) tiles.push_back(make_uint2(ib, jb));
+    const uint32_t nI = (row_end - row_begin + 31) / 32, nJ = (col_end - col_begin + 31) / 32;
+    if (nI > 0xFFFFu || nJ > 0xFFFFu) return fail(-3, "spsp_cmp_run: more than 2^21 sketches per side");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    // row tiles per unit: as many as share one table build (CMP_RT) when the grid is large; fewer when that would
+    // leave SMs without a CTA (small jobs are bound by the longest CTA, not by the table builds)
+    uint32_t rt = c->has_hi ? CMP_RT_HI : CMP_RT;
+    std::vector<uint2> units;
+    for (;; rt /= 2) {
+        units.clear();
+        for_each_unit(nI, nJ, symmetric != 0, rt, [&](uint64_t idx, uint32_t jb, uint32_t ib0, uint32_t n_ib) {
+            if (idx % tile_ranks == tile_rank) units.push_back(make_uint2(jb | (ib0 << 16), n_ib));
+        });
+        if (rt == 1 || units.size() * (uint64_t)c->n_chunks >= 2ull * sms) break;
+    }
     CK(cudaEventRecord(c->cev0, st));
-    if (!tiles.empty()) {
-        CK(c->b_tiles.ensure(tiles.size() * sizeof(uint2)));
-        uint2 *d_tiles = static_cast<uint2 *>(c->b_tiles.p);
-        CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    if (!units.empty()) {
+        // pinned staging that outlives the call: no stream synchronisation for the copy
+        CK(cudaEventSynchronize(c->ev_stage));
+        CK(c->p_units.ensure(units.size() * sizeof(uint2)));
+        memcpy(c->p_units.p, units.data(), units.size() * sizeof(uint2));
+        CK(c->b_tiles.ensure(units.size() * sizeof(uint2)));
+        uint2 *d_units = static_cast<uint2 *>(c->b_tiles.p);
+        CK(cudaMemcpyAsync(d_units, c->p_units.p, units.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->ev_stage, st));
         CK(cudaEventRecord(c->cev0, st));
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        uint64_t groups = (4ull * sms + tiles.size() - 1) / tiles.size();
+        uint64_t groups = (2ull * sms + units.size() - 1) / units.size();
         if (groups < 1) groups = 1;
         if (groups > c->n_chunks) groups = c->n_chunks;
-        CK(launch_hashjoin(c->cmp, c->has_hi, d_tiles, (uint32_t)tiles.size(), c->n_chunks, (uint32_t)groups, row_begin,
+        CK(launch_hashjoin(c->cmp, c->has_hi, d_units, (uint32_t)units.size(), nullptr, c->n_chunks, (uint32_t)groups, row_begin,
                            row_end, col_begin, col_end, d_out, ld, st));
         c->launches++;
-        CK(cudaEventRecord(c->cev1, st));
-        CK(cudaStreamSynchronize(st));      // the host tile vector must outlive the copy
-    } else {
-        CK(cudaEventRecord(c->cev1, st));
     }
+    CK(cudaEventRecord(c->cev1, st));
     c->cmp_timed = true;
     return 0;
 }
@@ -585,7 +614,10 @@ extern "C" int spsp_cmp_run_device(spsp_ctx *c, uint32_t row_begin, uint32_t row
 {
     if (!c || !d_out) return fail(-3, "spsp_cmp_run_device: bad args");
     CK(cudaSetDevice(c->device));
-    return cmp_run_impl(c, row_begin, row_end, col_begin, col_end, symmetric, tile_rank, tile_ranks, d_out, ld);
+    int rc = cmp_run_impl(c, row_begin, row_end, col_begin, col_end, symmetric, tile_rank, tile_ranks, d_out, ld);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->slots[0].stream));       // documented: the call returns when the counts are in d_out
+    return 0;
 }
 
 extern "C" int spsp_cmp_run(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint32_t col_end,
@@ -604,7 +636,7 @@ extern "C" int spsp_cmp_run(spsp_ctx *c, uint32_t row_begin, uint32_t row_end, u
     if (rc) return rc;
     const uint32_t *tmp = static_cast<const uint32_t *>(c->p_out.p);
     CK(cudaMemcpyAsync(c->p_out.p, d_out, rows * cols * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(st));                       // the only synchronisation of load + run
     for (uint64_t r = 0; r < rows; r++)
         for (uint64_t q = 0; q < cols; q++) out[r * ld + q] += tmp[r * cols + q];
     return 0;
@@ -904,7 +936,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -920,11 +953,12 @@ NcclApi *nccl_api()
         api.h = h;
 #define SPSP_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
         SPSP_SYM(GetUniqueId, "ncclGetUniqueId"); SPSP_SYM(CommInitRank, "ncclCommInitRank");
-        SPSP_SYM(CommDestroy, "ncclCommDestroy"); SPSP_SYM(AllGather, "ncclAllGather"); SPSP_SYM(Reduce, "ncclReduce");
-        SPSP_SYM(GroupStart, "ncclGroupStart"); SPSP_SYM(GroupEnd, "ncclGroupEnd"); SPSP_SYM(GetErrorString, "ncclGetErrorString");
+        SPSP_SYM(CommDestroy, "ncclCommDestroy"); SPSP_SYM(AllGather, "ncclAllGather"); SPSP_SYM(Send, "ncclSend");
+        SPSP_SYM(Recv, "ncclRecv"); SPSP_SYM(GroupStart, "ncclGroupStart"); SPSP_SYM(GroupEnd, "ncclGroupEnd");
+        SPSP_SYM(GetErrorString, "ncclGetErrorString");
 #undef SPSP_SYM
-        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Reduce || !api.GroupStart ||
-            !api.GroupEnd || !api.GetErrorString)
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Send || !api.Recv ||
+            !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
             api.h = nullptr;
     });
     return api.h ? &api : nullptr;
@@ -941,9 +975,10 @@ static void nccl_release(spsp_ctx *c)
 {
     if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
     c->comm = nullptr;
-    c->x_hdr.release(); c->x_sizes.release(); c->x_klo.release(); c->x_khi.release(); c->x_min.release();
-    c->x_begin.release(); c->x_end.release(); c->x_compact.release(); c->x_out.release();
-    c->xp_hdr.release(); c->xp_sizes.release(); c->xp_out.release();
+    c->x_hdrsz.release(); c->x_klo.release(); c->x_khi.release(); c->x_min.release();
+    c->x_begin.release(); c->x_end.release(); c->x_compact.release(); c->x_units.release(); c->x_dims.release();
+    c->x_tiles.release(); c->x_recv.release(); c->x_neg.release();
+    c->xp_hdrsz.release(); c->xp_out.release(); c->xp_neg.release();
 }
 
 extern "C" int spsp_nccl_unique_id(uint8_t *id128)
@@ -961,6 +996,7 @@ extern "C" int spsp_nccl_unique_id(uint8_t *id128)
 extern "C" int spsp_nccl_init(spsp_ctx *c, const uint8_t *id128, int rank, int world)
 {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(-3, "spsp_nccl_init: bad args");
+    if (world > CMP_MAX_WORLD) return fail(-3, "spsp_nccl_init: at most 64 ranks");
     NcclApi *n = nccl_api();
     if (!n) return fail(-1, "spsp_nccl_init: libnccl.so.2 not found");
     CK(cudaSetDevice(c->device));
@@ -969,110 +1005,247 @@ extern "C" int spsp_nccl_init(spsp_ctx *c, const uint8_t *id128, int rank, int w
     memcpy(&id, id128, 128);
     NK(n->CommInitRank(&c->comm, world, id, rank));
     c->rank = rank; c->world = world;
+    c->x_ncap = c->x_qcap = c->x_ecap = 0;
     return 0;
+}
+
+static uint64_t slot_cap(uint64_t v) { return std::max<uint64_t>(16, (v + v / 4 + 15) & ~(uint64_t)15); }
+
+// Units a rank can be dealt at most for the given slot capacities (same arithmetic on every rank).
+static uint64_t units_cap_for(uint32_t W, uint64_t n_cap, uint64_t q_cap, bool symmetric, uint32_t rt)
+{
+    const uint64_t nJ = (W * n_cap + 31) / 32, nI = symmetric ? nJ : (W * q_cap + 31) / 32;
+    uint64_t total = 0;
+    if (symmetric) {
+        const uint64_t full = nJ / rt, rem = nJ % rt;
+        total = rt * full * (full + 1) / 2 + rem * (full + 1);
+    } else {
+        total = nJ * ((nI + rt - 1) / rt);
+    }
+    return (total + W - 1) / W;
+}
+
+// The compare stage's only exchange step.  Every rank brings n_local sketches (the first q_local of them queries)
+// as device arrays + a host size list; the union is compared (all-vs-all when symmetric, else queries x all) and
+// rank 0 receives the matrix.  ONE payload all-gather into fixed-capacity slots (the counts travel inside the
+// payload; the capacities were agreed once and are re-derived by every rank from the same headers when a rank
+// outgrows them), the plan and the join on the device, one grouped send/receive of the owned tiles to rank 0, one
+// host synchronisation.  Every decision that changes the sequence of collectives is taken from the gathered
+// headers, which every rank sees: no rank can leave the others waiting in a collective.
+static int exchange_impl(spsp_ctx *c, uint64_t n_local, uint64_t q_local, const uint64_t *h_sizes, const uint32_t *d_min,
+                         const uint64_t *d_klo, const uint64_t *d_khi, bool symmetric, uint32_t *inter_out, uint64_t ld,
+                         uint64_t *sizes_out, uint32_t cap_rows, uint32_t cap_cols, uint32_t *n_rows, uint32_t *n_cols,
+                         float *kernel_ms)
+{
+    NcclApi *n = nccl_api();
+    cudaStream_t st = c->slots[0].stream;
+    const uint32_t W = (uint32_t)c->world, R = (uint32_t)c->rank;
+    const bool hi = c->k > 32;
+    const uint32_t rt_max = hi ? CMP_RT_HI : CMP_RT;                 // also the tile slots per unit in the compact output
+    uint64_t e_local = 0;
+    for (uint64_t i = 0; i < n_local; i++) e_local += h_sizes[i];
+    static const bool timing = getenv("SPSP_XCHG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+
+    if (!c->x_ncap) {
+        // first call on this communicator: agree on the slot capacities (one small all-gather + synchronisation)
+        CK(c->x_neg.ensure(3 * W * 8)); CK(c->xp_neg.ensure(3 * W * 8));
+        uint64_t *h = static_cast<uint64_t *>(c->xp_neg.p), *d = static_cast<uint64_t *>(c->x_neg.p);
+        h[3 * R] = n_local; h[3 * R + 1] = q_local; h[3 * R + 2] = e_local;
+        CK(cudaMemcpyAsync(d + 3 * R, h + 3 * R, 24, cudaMemcpyHostToDevice, st));
+        NK(n->AllGather(d + 3 * R, d, 3, ncclUint64, c->comm, st));
+        CK(cudaMemcpyAsync(h, d, 3 * W * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint64_t mn = 0, mq = 0, me = 0;
+        for (uint32_t r = 0; r < W; r++) { mn = std::max(mn, h[3 * r]); mq = std::max(mq, h[3 * r + 1]); me = std::max(me, h[3 * r + 2]); }
+        c->x_ncap = slot_cap(mn); c->x_qcap = slot_cap(mq); c->x_ecap = slot_cap(me);
+    }
+    for (int attempt = 0; attempt < 3; attempt++) {
+        const uint64_t n_cap = c->x_ncap, q_cap = c->x_qcap, e_cap = c->x_ecap;
+        const uint64_t stride = XHDR_WORDS + n_cap, N_cap = W * n_cap;
+        const bool over = n_local > n_cap || q_local > q_cap || e_local > e_cap;
+        // row tiles per unit: fewer than rt_max when the job is too small to give every SM of every rank a CTA
+        // (derived from the agreed capacities, so every rank picks the same value)
+        const double avg0 = n_local ? (double)e_local / (double)n_local : 1.0;
+        const uint64_t chunks0 = std::min<uint64_t>(std::max<uint64_t>((uint64_t)std::ceil(32.0 * (double)e_cap / (double)n_cap / (0.7 * CMP_CAP)), 1), 8192);
+        (void)avg0;
+        uint32_t rt = rt_max;
+        while (rt > 1 && units_cap_for(W, n_cap, q_cap, symmetric, rt) * chunks0 < 2ull * 148) rt /= 2;
+        const uint64_t u_cap = units_cap_for(W, n_cap, q_cap, symmetric, rt);
+        const uint64_t tile_words = u_cap * rt_max * 1024;                 // uint32 per rank
+        // ---- pack this rank's slot
+        CK(c->x_hdrsz.ensure(W * stride * 8)); CK(c->xp_hdrsz.ensure(stride * 8));
+        CK(c->x_klo.ensure(W * e_cap * 8)); CK(c->x_min.ensure(W * e_cap * 4));
+        if (hi) CK(c->x_khi.ensure(W * e_cap * 8));
+        CK(cudaEventSynchronize(c->ev_stage));
+        uint64_t *hp = static_cast<uint64_t *>(c->xp_hdrsz.p);
+        uint64_t flags = (over ? 1u : 0u) | (symmetric ? 2u : 0u);
+        if (R == 0 && !inter_out) flags |= 4u;
+        hp[0] = n_local; hp[1] = q_local; hp[2] = e_local; hp[3] = flags;
+        for (uint64_t i = 0; i < n_cap; i++) hp[XHDR_WORDS + i] = (!over && i < n_local) ? h_sizes[i] : 0;
+        uint64_t *d_hs = static_cast<uint64_t *>(c->x_hdrsz.p);
+        uint64_t *g_klo = static_cast<uint64_t *>(c->x_klo.p), *g_khi = static_cast<uint64_t *>(c->x_khi.p);
+        uint32_t *g_min = static_cast<uint32_t *>(c->x_min.p);
+        CK(cudaMemcpyAsync(d_hs + R * stride, hp, stride * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->ev_stage, st));
+        if (!over && e_local) {
+            CK(cudaMemcpyAsync(g_klo + R * e_cap, d_klo, e_local * 8, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(g_min + R * e_cap, d_min, e_local * 4, cudaMemcpyDeviceToDevice, st));
+            if (hi) CK(cudaMemcpyAsync(g_khi + R * e_cap, d_khi, e_local * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        // ---- the exchange: one group
+        NK(n->GroupStart());
+        NK(n->AllGather(d_hs + R * stride, d_hs, stride, ncclUint64, c->comm, st));
+        NK(n->AllGather(g_klo + R * e_cap, g_klo, e_cap, ncclUint64, c->comm, st));
+        NK(n->AllGather(g_min + R * e_cap, g_min, e_cap, ncclUint32, c->comm, st));
+        if (hi) NK(n->AllGather(g_khi + R * e_cap, g_khi, e_cap, ncclUint64, c->comm, st));
+        NK(n->GroupEnd());
+        const double t1 = now();
+        // ---- plan + join on the device
+        CK(c->x_begin.ensure(N_cap * 8)); CK(c->x_end.ensure(N_cap * 8)); CK(c->x_compact.ensure(N_cap * 8));
+        CK(c->x_units.ensure(u_cap * sizeof(uint2))); CK(c->x_dims.ensure(32));
+        CK(c->x_tiles.ensure(tile_words * 4));
+        uint32_t *d_dims = static_cast<uint32_t *>(c->x_dims.p);
+        uint2 *d_units = static_cast<uint2 *>(c->x_units.p);
+        uint32_t *d_tiles = static_cast<uint32_t *>(c->x_tiles.p);
+        CK(cudaMemsetAsync(d_tiles, 0, tile_words * 4, st));
+        CK(launch_exchange_plan(d_hs, W, R, n_cap, e_cap, symmetric ? 1 : 0, rt, (uint32_t)u_cap,
+                                static_cast<uint64_t *>(c->x_begin.p), static_cast<uint64_t *>(c->x_end.p),
+                                static_cast<uint64_t *>(c->x_compact.p), d_units, d_dims, st));
+        c->owns_cmp = false;
+        c->has_hi = hi;
+        c->n_sketches = 0;                                                 // the gathered set is not a loaded set
+        c->cmp.minim = g_min; c->cmp.klo = g_klo; c->cmp.khi = hi ? g_khi : nullptr;
+        c->cmp.sk_off = static_cast<const uint64_t *>(c->x_begin.p);
+        c->cmp.sk_end = static_cast<const uint64_t *>(c->x_end.p);
+        const double avg = n_local ? (double)e_local / (double)n_local : 1.0;
+        uint64_t chunks = (uint64_t)std::ceil(32.0 * avg / (0.7 * CMP_CAP));
+        chunks = std::min<uint64_t>(std::max<uint64_t>(chunks, 1), 8192);
+        c->n_chunks = (uint32_t)chunks;
+        CK(c->b_chunk_off.ensure((size_t)N_cap * (chunks + 1) * sizeof(uint64_t)));
+        c->cmp.chunk_off = static_cast<uint64_t *>(c->b_chunk_off.p);
+        CK(launch_chunk_offsets(c->cmp, (uint32_t)N_cap, d_dims, c->n_chunks, c->m, st));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        uint64_t groups = (2ull * sms + u_cap - 1) / u_cap;
+        groups = std::min<uint64_t>(std::max<uint64_t>(groups, 1), chunks);
+        CK(cudaEventRecord(c->cev0, st));
+        CK(launch_hashjoin(c->cmp, hi, d_units, (uint32_t)u_cap, d_dims, c->n_chunks, (uint32_t)groups, 0, 0, 0, 0, d_tiles, 0, st));
+        CK(cudaEventRecord(c->cev1, st));
+        c->cmp_timed = true;
+        c->launches += 3;
+        // ---- owned tiles to rank 0, everything the host needs in one sweep, ONE synchronisation
+        const size_t meta_bytes = W * stride * 8 + N_cap * 8 + 32;
+        CK(c->xp_out.ensure(meta_bytes + (R == 0 ? (size_t)W * tile_words * 4 : 0)));
+        uint8_t *h_out = static_cast<uint8_t *>(c->xp_out.p);
+        uint32_t *d_recv = nullptr;
+        if (R == 0 && W > 1) {
+            CK(c->x_recv.ensure((size_t)W * tile_words * 4));
+            d_recv = static_cast<uint32_t *>(c->x_recv.p);
+        }
+        if (W > 1) {
+            NK(n->GroupStart());
+            if (R == 0) {
+                for (uint32_t r = 1; r < W; r++) NK(n->Recv(d_recv + (size_t)r * tile_words, tile_words, ncclUint32, (int)r, c->comm, st));
+            } else {
+                NK(n->Send(d_tiles, tile_words, ncclUint32, 0, c->comm, st));
+            }
+            NK(n->GroupEnd());
+        }
+        CK(cudaMemcpyAsync(h_out, d_hs, W * stride * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_out + W * stride * 8, c->x_compact.p, N_cap * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_out + W * stride * 8 + N_cap * 8, d_dims, 32, cudaMemcpyDeviceToHost, st));
+        if (R == 0) {
+            CK(cudaMemcpyAsync(h_out + meta_bytes, d_tiles, tile_words * 4, cudaMemcpyDeviceToHost, st));
+            if (W > 1)
+                CK(cudaMemcpyAsync(h_out + meta_bytes + tile_words * 4, d_recv + tile_words, (size_t)(W - 1) * tile_words * 4,
+                                   cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        const double t2 = now();
+        // ---- every rank reads the same headers: same verdict everywhere
+        const uint64_t *hh = reinterpret_cast<const uint64_t *>(h_out);
+        bool any_over = false, bad_args = false, mode_mismatch = false;
+        uint64_t mn = 0, mq = 0, me = 0;
+        for (uint32_t r = 0; r < W; r++) {
+            const uint64_t *h = hh + r * stride;
+            mn = std::max(mn, h[0]); mq = std::max(mq, h[1]); me = std::max(me, h[2]);
+            any_over |= (h[3] & 1u) != 0; bad_args |= (h[3] & 4u) != 0;
+            mode_mismatch |= ((h[3] & 2u) != 0) != symmetric;
+        }
+        if (any_over) {                                                    // some rank outgrew its slot: larger slots, again
+            c->x_ncap = std::max(c->x_ncap, slot_cap(mn)); c->x_qcap = std::max(c->x_qcap, slot_cap(mq));
+            c->x_ecap = std::max(c->x_ecap, slot_cap(me));
+            continue;
+        }
+        if (bad_args) return fail(-3, "spsp_cmp_exchange: rank 0 passed no output arrays");
+        if (mode_mismatch) return fail(-3, "spsp_cmp_exchange: the ranks disagree on all-vs-all / query mode");
+        const uint32_t *dims = reinterpret_cast<const uint32_t *>(h_out + W * stride * 8 + N_cap * 8);
+        const uint32_t rows = dims[0], N = dims[1];
+        if (dims[4] > dims[2]) return fail(-1, "spsp_cmp_exchange: unit capacity bound violated");
+        if (n_rows) *n_rows = rows;
+        if (n_cols) *n_cols = N;
+        if (kernel_ms) spsp_cmp_last_kernel_ms(c, kernel_ms);
+        if (N > cap_cols || rows > cap_rows) return fail(-2, "spsp_cmp_exchange: output arrays too small");
+        if (sizes_out) memcpy(sizes_out, h_out + W * stride * 8, (size_t)N * 8);
+        if (R == 0) {
+            if (ld < N) return fail(-3, "spsp_cmp_exchange: ld too small");
+            const uint32_t *tiles = reinterpret_cast<const uint32_t *>(h_out + meta_bytes);
+            for (uint64_t i = 0; i < rows; i++) memset(inter_out + i * ld, 0, (size_t)N * 4);
+            const uint32_t nJ = (N + 31) / 32, nI = (rows + 31) / 32;
+            for_each_unit(nI, nJ, symmetric, rt, [&](uint64_t idx, uint32_t jb, uint32_t ib0, uint32_t n_ib) {
+                const uint32_t *src = tiles + (size_t)(idx % W) * tile_words + (size_t)(idx / W) * rt_max * 1024;
+                for (uint32_t t = 0; t < n_ib; t++)
+                    for (uint32_t rr = 0; rr < 32; rr++) {
+                        const uint64_t i = (uint64_t)(ib0 + t) * 32 + rr;
+                        if (i >= rows) break;
+                        const uint32_t cols = std::min<uint32_t>(32, N - jb * 32);
+                        memcpy(inter_out + i * ld + (uint64_t)jb * 32, src + (size_t)t * 1024 + rr * 32, cols * 4);
+                    }
+            });
+        }
+        if (timing && R == 0)
+            fprintf(stderr, "[xchg] enqueue gather %.0f us | plan+join+collect+sync %.0f | scatter %.0f (N=%u rows=%u units/rank<=%llu)\n",
+                    t1 - t0, t2 - t1, now() - t2, N, rows, (unsigned long long)u_cap);
+        return 0;
+    }
+    return fail(-1, "spsp_cmp_exchange: slot capacities did not converge");
+}
+
+extern "C" int spsp_cmp_exchange(spsp_ctx *c, uint32_t n_local, uint32_t q_local, const uint64_t *sizes_local,
+                                 const uint32_t *d_minimizer, const uint64_t *d_kmer_lo, const uint64_t *d_kmer_hi,
+                                 int symmetric, uint32_t *inter_out, uint64_t ld, uint64_t *sizes_out, uint32_t cap_rows,
+                                 uint32_t cap_cols, uint32_t *n_rows, uint32_t *n_cols, float *kernel_ms)
+{
+    if (!c) return fail(-3, "spsp_cmp_exchange: null context");
+    if (!nccl_api() || !c->comm) return fail(-3, "spsp_cmp_exchange: call spsp_nccl_init first");
+    if (n_local && !sizes_local) return fail(-3, "spsp_cmp_exchange: null size list");
+    if (q_local > n_local) return fail(-3, "spsp_cmp_exchange: more queries than sketches");
+    if (symmetric && q_local != n_local) return fail(-3, "spsp_cmp_exchange: all-vs-all needs q_local == n_local");
+    if ((c->k > 32) && n_local && !d_kmer_hi) return fail(-3, "spsp_cmp_exchange: kmer_hi must be given when k > 32");
+    CK(cudaSetDevice(c->device));
+    return exchange_impl(c, n_local, q_local, sizes_local, d_minimizer, d_kmer_lo, d_kmer_hi, symmetric != 0, inter_out, ld,
+                         sizes_out, cap_rows, cap_cols, n_rows, n_cols, kernel_ms);
 }
 
 extern "C" int spsp_cmp_exchange_batch(spsp_ctx *c, int slot, uint32_t *inter_out, uint64_t ld, uint64_t *sizes_out,
                                        uint32_t cap_sketches, uint32_t *n_total, float *kernel_ms)
 {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || !n_total) return fail(-3, "spsp_cmp_exchange_batch: bad args");
-    NcclApi *n = nccl_api();
-    if (!n || !c->comm) return fail(-3, "spsp_cmp_exchange_batch: call spsp_nccl_init first");
+    if (!nccl_api() || !c->comm) return fail(-3, "spsp_cmp_exchange_batch: call spsp_nccl_init first");
     Slot &s = c->slots[slot];
     if (!s.has_batch) return fail(-3, "spsp_cmp_exchange_batch: no batch on this slot");
     CK(cudaSetDevice(c->device));
-    cudaStream_t st = c->slots[0].stream;
     if (slot != 0) CK(cudaStreamSynchronize(s.stream));
-    const uint32_t W = (uint32_t)c->world, R = (uint32_t)c->rank;
-    const bool hi = c->k > 32;
-    const uint64_t n_local = s.last_batch_inputs, e_local = s.last_batch.n_elems;
-    static const bool timing = getenv("SPSP_XCHG_TIMING") != nullptr;
-    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double tp[6] = {0, 0, 0, 0, 0, 0};
-    tp[0] = now();
-    // ---- stage A: how many sketches / elements every rank brings
-    CK(c->x_hdr.ensure(2 * W * 8)); CK(c->xp_hdr.ensure(2 * W * 8));
-    uint64_t *h_hdr = static_cast<uint64_t *>(c->xp_hdr.p);
-    uint64_t *d_hdr = static_cast<uint64_t *>(c->x_hdr.p);
-    h_hdr[2 * R] = n_local; h_hdr[2 * R + 1] = e_local;
-    CK(cudaMemcpyAsync(d_hdr + 2 * R, h_hdr + 2 * R, 16, cudaMemcpyHostToDevice, st));
-    NK(n->AllGather(d_hdr + 2 * R, d_hdr, 2, ncclUint64, c->comm, st));
-    CK(cudaMemcpyAsync(h_hdr, d_hdr, 2 * W * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    tp[1] = now();
-    uint64_t N = 0, E = 0, n_max = 1, e_max = 1;
-    for (uint32_t r = 0; r < W; r++) {
-        N += h_hdr[2 * r]; E += h_hdr[2 * r + 1];
-        n_max = std::max(n_max, h_hdr[2 * r]); e_max = std::max(e_max, h_hdr[2 * r + 1]);
-    }
-    *n_total = (uint32_t)N;
-    if (N > cap_sketches) return fail(-2, "spsp_cmp_exchange_batch: output arrays too small");
-    if (R == 0 && N && (!inter_out || ld < N)) return fail(-3, "spsp_cmp_exchange_batch: bad output matrix");
-    if (N == 0) return 0;
-    // ---- stage B: sizes and elements of every rank, in place, one group
-    CK(c->x_sizes.ensure(W * n_max * 8)); CK(c->xp_sizes.ensure(n_max * 8));
-    CK(c->x_klo.ensure(W * e_max * 8)); CK(c->x_min.ensure(W * e_max * 4));
-    if (hi) CK(c->x_khi.ensure(W * e_max * 8));
-    uint64_t *h_sz = static_cast<uint64_t *>(c->xp_sizes.p);
-    for (uint64_t i = 0; i < n_max; i++) h_sz[i] = i < n_local ? s.last_batch.h_elem_off[i + 1] - s.last_batch.h_elem_off[i] : 0;
-    uint64_t *d_sz = static_cast<uint64_t *>(c->x_sizes.p);
-    uint64_t *d_klo = static_cast<uint64_t *>(c->x_klo.p), *d_khi = static_cast<uint64_t *>(c->x_khi.p);
-    uint32_t *d_min = static_cast<uint32_t *>(c->x_min.p);
-    CK(cudaMemcpyAsync(d_sz + R * n_max, h_sz, n_max * 8, cudaMemcpyHostToDevice, st));
-    if (e_local) {
-        CK(cudaMemcpyAsync(d_klo + R * e_max, s.last_batch.d_klo, e_local * 8, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(d_min + R * e_max, s.last_batch.d_minim, e_local * 4, cudaMemcpyDeviceToDevice, st));
-        if (hi) CK(cudaMemcpyAsync(d_khi + R * e_max, s.last_batch.d_khi, e_local * 8, cudaMemcpyDeviceToDevice, st));
-    }
-    NK(n->GroupStart());
-    NK(n->AllGather(d_sz + R * n_max, d_sz, n_max, ncclUint64, c->comm, st));
-    NK(n->AllGather(d_klo + R * e_max, d_klo, e_max, ncclUint64, c->comm, st));
-    NK(n->AllGather(d_min + R * e_max, d_min, e_max, ncclUint32, c->comm, st));
-    if (hi) NK(n->AllGather(d_khi + R * e_max, d_khi, e_max, ncclUint64, c->comm, st));
-    NK(n->GroupEnd());
-    if (timing) { CK(cudaStreamSynchronize(st)); }
-    tp[2] = now();
-    // ---- sketch ranges of the union (rank-major), chunk offsets, this rank's tiles
-    CK(c->x_begin.ensure(N * 8)); CK(c->x_end.ensure(N * 8)); CK(c->x_compact.ensure(N * 8));
-    CK(launch_gathered_ranges(d_hdr, d_sz, W, n_max, e_max, static_cast<uint64_t *>(c->x_begin.p),
-                              static_cast<uint64_t *>(c->x_end.p), static_cast<uint64_t *>(c->x_compact.p), st));
-    c->owns_cmp = false;
-    c->has_hi = hi;
-    c->n_sketches = (uint32_t)N;
-    c->n_elems = E;
-    c->cmp.minim = d_min; c->cmp.klo = d_klo; c->cmp.khi = hi ? d_khi : nullptr;
-    c->cmp.sk_off = static_cast<const uint64_t *>(c->x_begin.p);
-    c->cmp.sk_end = static_cast<const uint64_t *>(c->x_end.p);
-    const double avg = (double)E / (double)N;
-    uint64_t chunks = (uint64_t)std::ceil(32.0 * avg / (0.7 * CMP_CAP));
-    chunks = std::min<uint64_t>(std::max<uint64_t>(chunks, 1), 8192);
-    c->n_chunks = (uint32_t)chunks;
-    CK(c->b_chunk_off.ensure((size_t)N * (chunks + 1) * sizeof(uint64_t)));
-    c->cmp.chunk_off = static_cast<uint64_t *>(c->b_chunk_off.p);
-    CK(launch_chunk_offsets(c->cmp, (uint32_t)N, c->n_chunks, c->m, st));
-    c->launches += 2;
-    CK(c->x_out.ensure(N * N * 4)); CK(c->xp_out.ensure(N * N * 4 + N * 8));
-    uint32_t *d_out = static_cast<uint32_t *>(c->x_out.p);
-    CK(cudaMemsetAsync(d_out, 0, N * N * 4, st));
-    int rc = cmp_run_impl(c, 0, (uint32_t)N, 0, (uint32_t)N, 1, R, W, d_out, N);     // synchronises the stream
-    if (rc) return rc;
-    tp[3] = now();
-    if (kernel_ms) spsp_cmp_last_kernel_ms(c, kernel_ms);
-    // ---- disjoint tiles: the sum over ranks is the gather to rank 0
-    NK(n->Reduce(d_out, d_out, N * N, ncclUint32, ncclSum, 0, c->comm, st));
-    uint8_t *h_out = static_cast<uint8_t *>(c->xp_out.p);
-    if (R == 0) CK(cudaMemcpyAsync(h_out, d_out, N * N * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_out + N * N * 4, c->x_compact.p, N * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    tp[4] = now();
-    if (R == 0)
-        for (uint64_t i = 0; i < N; i++) memcpy(inter_out + i * ld, h_out + i * N * 4, N * 4);
-    if (sizes_out) memcpy(sizes_out, h_out + N * N * 4, N * 8);
-    tp[5] = now();
-    if (timing && R == 0)
-        fprintf(stderr, "[xchg] counts+sync %.0f us | gather %.0f | ranges+chunks+join %.0f | reduce+D2H %.0f | copy out %.0f\n",
-                tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
-    return 0;
+    const uint32_t n_local = s.last_batch_inputs;
+    std::vector<uint64_t> sz(n_local ? n_local : 1);
+    for (uint32_t i = 0; i < n_local; i++) sz[i] = s.last_batch.h_elem_off[i + 1] - s.last_batch.h_elem_off[i];
+    uint32_t rows = 0, cols = 0;
+    int rc = exchange_impl(c, n_local, n_local, sz.data(), s.last_batch.d_minim, s.last_batch.d_klo, s.last_batch.d_khi, true,
+                           inter_out, ld, sizes_out, cap_sketches, cap_sketches, &rows, &cols, kernel_ms);
+    *n_total = cols;
+    return rc;
 }
 
 extern "C" int spsp_launch_count(spsp_ctx *c, uint64_t *n)

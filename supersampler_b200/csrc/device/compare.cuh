@@ -17,15 +17,24 @@ struct CmpData {
 constexpr int CMP_THREADS = 512;      // 16 warps, 2 row sketches per warp
 constexpr int CMP_CAP = 6144;         // column elements per hash-table pass
 constexpr int CMP_SLOTS = 16384;      // open-addressing slots (load <= 0.375)
+constexpr int CMP_RT = 8;             // row tiles that share one table build (k <= 32)
+constexpr int CMP_RT_HI = 4;          // ... when the 128-bit keys take the shared memory (k > 32)
+constexpr int CMP_MAX_WORLD = 64;     // ranks of a multi-GPU exchange
+constexpr int XHDR_WORDS = 4;         // exchange header per rank: {sketches, queries, elements, flags}, then the size list
 
-// sk_begin/sk_end of the union of all ranks' sketches from the gathered per-rank size lists
-// (sizes_all[r * n_max + i], elements of rank r start at r * e_max); also the compact size list.
-cudaError_t launch_gathered_ranges(const uint64_t *d_hdr_all, const uint64_t *d_sizes_all, uint32_t world, uint64_t n_max,
-                                   uint64_t e_max, uint64_t *sk_begin, uint64_t *sk_end, uint64_t *sizes_compact,
-                                   cudaStream_t st);
-cudaError_t launch_chunk_offsets(const CmpData &d, uint32_t n_sketches, uint32_t n_chunks, int m, cudaStream_t st);
+// Multi-GPU plan (after the all-gather): global sketch order (queries of all ranks, then references), element
+// ranges inside the gathered arrays, job dimensions dims = {rows, columns, units of this rank, queries, units
+// before capping} and this rank's units of the tile grid.
+cudaError_t launch_exchange_plan(const uint64_t *d_hdrsz, uint32_t world, uint32_t rank, uint64_t n_cap, uint64_t e_cap,
+                                 int symmetric, uint32_t rt, uint32_t units_cap, uint64_t *sk_begin, uint64_t *sk_end,
+                                 uint64_t *sizes_compact, uint2 *units, uint32_t *dims, cudaStream_t st);
+// n_sketches is the capacity when dev_dims (device: dims[1] = sketches) is given.
+cudaError_t launch_chunk_offsets(const CmpData &d, uint32_t n_sketches, const uint32_t *dev_dims, uint32_t n_chunks, int m,
+                                 cudaStream_t st);
 size_t hashjoin_smem_bytes(bool has_hi);
-cudaError_t launch_hashjoin(const CmpData &d, bool has_hi, const uint2 *d_tiles, uint32_t n_tiles,
+// units[u] = {jb | ib0 << 16, n_ib}; grid = n_units x chunk_groups.  dev_dims != null: device-side dimensions and
+// compact per-unit output tiles (see compare.cu).
+cudaError_t launch_hashjoin(const CmpData &d, bool has_hi, const uint2 *d_units, uint32_t n_units, const uint32_t *dev_dims,
                             uint32_t n_chunks, uint32_t chunk_groups, uint32_t row_begin, uint32_t row_end,
                             uint32_t col_begin, uint32_t col_end, uint32_t *d_out, uint64_t ld, cudaStream_t st);
 

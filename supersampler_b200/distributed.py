@@ -15,17 +15,44 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 
-def tiles_for_rank(n_rows: int, n_cols: int, symmetric: bool, rank: int, ranks: int) -> List[Tuple[int, int]]:
-    """The 32x32 tiles spsp_cmp_run deals to `rank` (same enumeration as
-    csrc/device/capi.cu cmp_run_impl: row-major, upper triangle when symmetric,
-    round-robin)."""
+RT = 8   # row tiles that share one column-table build (csrc/device/compare.cuh CMP_RT; 4 when k > 32)
+
+
+def units_for_rank(n_rows: int, n_cols: int, symmetric: bool, rank: int, ranks: int, rt: int = RT):
+    """The work units spsp_cmp_run / spsp_cmp_exchange deal to `rank`: (jb, ib0, n_ib) = column tile jb with row
+    tiles ib0 .. ib0 + n_ib - 1 (same enumeration as csrc/device/capi.cu for_each_unit and
+    exchange_plan_kernel: column-tile major, runs of rt row tiles, only row tiles <= jb when symmetric,
+    round-robin over the ranks)."""
     n_i, n_j = (n_rows + 31) // 32, (n_cols + 31) // 32
-    out, t = [], 0
-    for ib in range(n_i):
-        for jb in range(ib if symmetric else 0, n_j):
-            if t % ranks == rank:
-                out.append((ib, jb))
-            t += 1
+    out, idx = [], 0
+    for jb in range(n_j):
+        lim = min(jb + 1, n_i) if symmetric else n_i
+        for ib0 in range(0, lim, rt):
+            if idx % ranks == rank:
+                out.append((jb, ib0, min(rt, lim - ib0)))
+            idx += 1
+    return out
+
+
+def tiles_for_rank(n_rows: int, n_cols: int, symmetric: bool, rank: int, ranks: int, rt: int = RT) -> List[Tuple[int, int]]:
+    """The 32x32 tiles (ib, jb) inside the units dealt to `rank`."""
+    return [(ib, jb) for jb, ib0, n_ib in units_for_rank(n_rows, n_cols, symmetric, rank, ranks, rt)
+            for ib in range(ib0, ib0 + n_ib)]
+
+
+def global_order(n_locals: Sequence[int], q_locals: Sequence[int]):
+    """Where the sketches of every rank end up in the union that spsp_cmp_exchange compares: all queries
+    rank-major, then all references rank-major (the reference's comparator lists the `-q` files first,
+    Comparator.cpp:7-21, 512-515).  -> list over ranks of index arrays (local sketch -> global index)."""
+    q_tot = int(sum(q_locals))
+    q_off = np.concatenate([[0], np.cumsum(q_locals)])
+    r_off = np.concatenate([[0], np.cumsum(np.asarray(n_locals) - np.asarray(q_locals))])
+    out = []
+    for r, (n, q) in enumerate(zip(n_locals, q_locals)):
+        idx = np.empty(n, np.int64)
+        idx[:q] = q_off[r] + np.arange(q)
+        idx[q:] = q_tot + r_off[r] + np.arange(n - q)
+        out.append(idx)
     return out
 
 
