@@ -188,6 +188,46 @@ int spsp_batch_upload(spsp_ctx *ctx, int slot, uint64_t word_off, const uint32_t
 int spsp_sketch_batch_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const uint64_t *rec_begin,
                              const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
                              unsigned abundance, spsp_batch_result *res);
+/* ---- device-side ingest (optional front end of the staged batch) -----------
+ * Replaces getLineFasta + clean_dna (utils.cpp:706-718, :675-702) and the 2-bit
+ * packing (utils.cpp:13-16) for inputs whose raw FASTA text is sent to the GPU
+ * as it is (csrc/device/ingest.cu): the first line of an input and every line
+ * that starts with '>' is a header; on the other lines ACGTacgt are bases,
+ * everything else is deleted.  Used when host cores are scarce (several GPUs
+ * per box) or records are short (read sets): the host only moves bytes.
+ *
+ *   reserve : device text buffer of text_bytes (grow-only; synchronises when it grows)
+ *   upload  : async H2D of a slice of text to byte offset byte_off (host_text
+ *             pinned for true overlap; callable from any thread) on copy lane
+ *             `lane` (0 / 1; < 0: the lanes alternate)
+ *   pack    : for n_text inputs -- text [text_off[i], +text_len[i]) (text_off a
+ *             multiple of 16), region of the staged batch buffer starting at
+ *             word word_off[i] (spsp_batch_reserve'd, spsp_packed_words(text_len[i])
+ *             words, ascending), batch input index input_index[i] (ascending) --
+ *             runs the three ingest passes; the record table (every header line
+ *             starts a record, empty and short records included) stays on the
+ *             slot and is merged into the next spsp_sketch_batch_staged call,
+ *             whose host record arrays then describe the host-packed inputs only.
+ *             n_bases_out / n_rec_out (may be NULL): cleaned bases / records per input.
+ *             One host synchronisation (the table is sized from the count). */
+int spsp_batch_text_reserve(spsp_ctx *ctx, int slot, uint64_t text_bytes);
+int spsp_batch_text_upload(spsp_ctx *ctx, int slot, int lane, uint64_t byte_off, const uint8_t *host_text,
+                           uint64_t n_bytes);
+/* Waits until the copies queued on copy lane `lane` (0 / 1; < 0: both) have finished: lets a caller keep a
+ * bounded number of uploads in flight. */
+int spsp_batch_upload_wait(spsp_ctx *ctx, int slot, int lane);
+int spsp_batch_text_pack(spsp_ctx *ctx, int slot, uint32_t n_text, const uint64_t *text_off, const uint64_t *text_len,
+                         const uint64_t *word_off, const uint32_t *input_index, uint64_t *n_bases_out,
+                         uint64_t *n_rec_out);
+/* CUDA-event time of the last pack's kernels (milliseconds). */
+int spsp_batch_text_last_ms(spsp_ctx *ctx, int slot, float *ms);
+/* Diagnostics / tests: the record table the last pack left on the slot (cap
+ * entries per array, -2 with *n_rec set when too small), and a copy of words of
+ * the slot's staged batch buffer. */
+int spsp_batch_text_records(spsp_ctx *ctx, int slot, uint64_t *rec_begin, uint64_t *rec_end, uint32_t *rec_input,
+                            uint64_t cap, uint64_t *n_rec);
+int spsp_batch_download(spsp_ctx *ctx, int slot, uint64_t word_off, uint32_t *host_words, uint64_t n_words);
+
 /* Load the compare stage with the elements the last batch on `slot` left on the
  * device (one sketch per input): the sketch -> compare hand-off without files. */
 int spsp_cmp_load_batch(spsp_ctx *ctx, int slot);

@@ -109,11 +109,18 @@ int spsph_pipeline_destroy(spsph_pipeline *p);
 spsp_ctx *spsph_pipeline_ctx(spsph_pipeline *p);
 /* Upper bound of one device batch in bases (default 2^30); larger jobs run as several batches. */
 int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t bases);
+/* Who cleans + packs the inputs (csrc/host/pipeline.h, enum Ingest): 0 = host threads (default, or what the
+ * environment variable SPSP_INGEST = host|device|auto names), 1 = the device (raw text over PCIe, ingest kernels),
+ * 2 = both on one work queue (pack workers from the front, one upload lane from the back).  In modes 1 / 2 text
+ * held in PINNED memory is copied asynchronously and must stay valid until the job's device half has run
+ * (spsph_pipeline_sketch / _finish returned); pageable text is staged by the copy call itself. */
+int spsph_pipeline_set_ingest(spsph_pipeline *p, int mode);
 /* Input i is fasta[i]/len[i] (FASTA text in memory) or, when fasta is NULL or
  * fasta[i] is NULL, the FASTA(.gz) file paths[i].  out/out_len as in
  * spsph_sketch_buffers; ok[i] = 0 for an unopenable file (may be NULL).
- * stats (may be NULL, 12 doubles): prep s, pack s, device s, assemble s, scan ms,
- * post-pass ms, hits, compare elements, H2D bytes, D2H bytes, batches, bases. */
+ * stats (may be NULL, 14 doubles): prep s, pack s, device s, assemble s, scan ms,
+ * post-pass ms, hits, compare elements, H2D bytes, D2H bytes, batches, bases,
+ * inputs ingested on the device, ingest kernel ms. */
 int spsph_pipeline_sketch(spsph_pipeline *p, uint32_t n, const uint8_t *const *fasta, const size_t *len,
                           const char *const *paths, uint8_t **out, size_t *out_len, int *ok, double *stats,
                           uint64_t *launches);

@@ -92,6 +92,19 @@ def device_lib():
                                         C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
         L.spsp_sketch_batch_device.argtypes = L.spsp_sketch_batch.argtypes
         L.spsp_cmp_load_batch.argtypes = [C.c_void_p, C.c_int]
+        L.spsp_batch_reserve.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.spsp_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.spsp_sketch_batch_staged.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(BatchResult)]
+        L.spsp_batch_text_reserve.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.spsp_batch_text_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.spsp_batch_upload_wait.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.spsp_batch_text_pack.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.spsp_batch_text_last_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        L.spsp_batch_text_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                              C.POINTER(C.c_uint64)]
+        L.spsp_batch_download.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
         L.spsp_dense_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.spsp_dense_stats_device.argtypes = L.spsp_dense_stats.argtypes
@@ -164,10 +177,11 @@ def host_lib():
         L.spsph_pipeline_ctx.restype = C.c_void_p
         L.spsph_pipeline_ctx.argtypes = [C.c_void_p]
         L.spsph_pipeline_set_max_batch_bases.argtypes = [C.c_void_p, C.c_uint64]
-        L.spsph_pipeline_sketch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+        L.spsph_pipeline_set_ingest.argtypes = [C.c_void_p, C.c_int]
+        L.spsph_pipeline_sketch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                             C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                             C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
-        L.spsph_pipeline_pack.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+        L.spsph_pipeline_pack.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                           C.POINTER(C.c_char_p)]
         L.spsph_pipeline_finish.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                             C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -329,16 +343,21 @@ class Pipeline:
     elements.  Inputs are FASTA texts (bytes) or file paths (str)."""
 
     STAT_NAMES = ("prep_s", "pack_s", "device_s", "assemble_s", "scan_ms", "post_ms", "hits", "elems", "h2d_bytes",
-                  "d2h_bytes", "batches", "bases")
+                  "d2h_bytes", "batches", "bases", "text_inputs", "ingest_ms")
+    INGEST = {"host": 0, "device": 1, "auto": 2}
 
     def __init__(self, k: int = 31, m: int = 11, s: float = 1000.0, abundance: int = 1, device: int = 0,
-                 threads: int = 8, max_batch_bases: Optional[int] = None):
+                 threads: int = 8, max_batch_bases: Optional[int] = None, ingest: Optional[str] = None):
+        """ingest: who cleans + packs the FASTA text -- "host" (host threads, the default unless SPSP_INGEST says
+        otherwise), "device" (raw text over PCIe + ingest kernels) or "auto" (both, on one work queue)."""
         self.L = host_lib()
         self.h = C.c_void_p()
         self.k, self.m, self.s = k, m, s
         _hcheck(self.L.spsph_pipeline_create(device, k, m, _f32(s), abundance, threads, C.byref(self.h)), "pipeline_create")
         if max_batch_bases is not None:
             _hcheck(self.L.spsph_pipeline_set_max_batch_bases(self.h, max_batch_bases), "pipeline_set_max_batch_bases")
+        if ingest is not None:
+            _hcheck(self.L.spsph_pipeline_set_ingest(self.h, self.INGEST[ingest]), "pipeline_set_ingest")
         self.n_last = 0
 
     def close(self):
@@ -354,10 +373,13 @@ class Pipeline:
 
     @staticmethod
     def _marshal(inputs):
+        """inputs: FASTA text as bytes / PinnedBuffer, or a path (str / os.PathLike)."""
         n = len(inputs)
-        data = (C.c_char_p * n)(*[x if isinstance(x, (bytes, bytearray)) else None for x in inputs])
-        lens = (C.c_size_t * n)(*[len(x) if isinstance(x, (bytes, bytearray)) else 0 for x in inputs])
-        paths = (C.c_char_p * n)(*[os.fsencode(x) if not isinstance(x, (bytes, bytearray)) else None for x in inputs])
+        mem = lambda x: isinstance(x, (bytes, PinnedBuffer))
+        addr = lambda x: x.ptr if isinstance(x, PinnedBuffer) else C.cast(C.c_char_p(x), C.c_void_p).value
+        data = (C.c_void_p * n)(*[addr(x) if mem(x) else None for x in inputs])
+        lens = (C.c_size_t * n)(*[len(x) if mem(x) else 0 for x in inputs])
+        paths = (C.c_char_p * n)(*[os.fsencode(x) if not mem(x) else None for x in inputs])
         return n, data, lens, paths
 
     def _collect(self, n, outs, olens, ok, st, nl, info):
@@ -375,7 +397,7 @@ class Pipeline:
         """-> sketch bytes (before gzip) per input; None for a file that cannot be opened."""
         n, data, lens, paths = self._marshal(inputs)
         outs, olens, ok = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
-        st, nl = (C.c_double * 12)(), C.c_uint64()
+        st, nl = (C.c_double * 14)(), C.c_uint64()
         _hcheck(self.L.spsph_pipeline_sketch(self.h, n, data, lens, paths, outs, olens, ok, st, C.byref(nl)),
                 "pipeline_sketch")
         return self._collect(n, outs, olens, ok, st, nl, info)
@@ -390,7 +412,7 @@ class Pipeline:
         """Second half of sketch(): device phase of the job pack() started."""
         n = self._n_packed
         outs, olens, ok = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
-        st, nl = (C.c_double * 12)(), C.c_uint64()
+        st, nl = (C.c_double * 14)(), C.c_uint64()
         _hcheck(self.L.spsph_pipeline_finish(self.h, n, outs, olens, ok, st, C.byref(nl)), "pipeline_finish")
         return self._collect(n, outs, olens, ok, st, nl, info)
 
@@ -417,6 +439,36 @@ class Pipeline:
 
     def device_context(self) -> "DeviceContext":
         return DeviceContext._borrow(self.L.spsph_pipeline_ctx(self.h), self.k, self.m)
+
+
+class PinnedBuffer:
+    """Bytes in page-locked host memory (cudaHostAlloc through the C ABI): FASTA text that the device-side ingest
+    can copy asynchronously, straight from where it lies.  Keep it alive until the job that uses it has finished."""
+
+    def __init__(self, data: bytes):
+        self.L = device_lib()
+        self.n = len(data)
+        p = C.c_void_p()
+        _dcheck(self.L.spsp_host_alloc(C.byref(p), max(1, self.n)), "spsp_host_alloc")
+        self.ptr = p.value
+        C.memmove(self.ptr, data, self.n)
+
+    def __len__(self):
+        return self.n
+
+    def tobytes(self) -> bytes:
+        return C.string_at(self.ptr, self.n)
+
+    def close(self):
+        if self.ptr:
+            self.L.spsp_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BatchStream:
@@ -666,6 +718,9 @@ class DeviceContext:
                                                  rec_end.ctypes.data, rec_input.ctypes.data, rec_begin.size, n_inputs,
                                                  abundance, C.byref(res))
         _dcheck(rc, "spsp_sketch_batch")
+        return self._batch_out(res, n_inputs, s, info)
+
+    def _batch_out(self, res, n_inputs: int, s: float, info: Optional[dict]):
         total = int(res.body_off[n_inputs])
         body = C.string_at(res.body, total) if total else b""
         hdr = f"{2 * self.k - self.m} {self.m} "
@@ -677,6 +732,59 @@ class DeviceContext:
             info.update(n_hits=int(res.n_hits), n_elems=int(res.n_elems), scan_ms=float(res.scan_ms),
                         post_ms=float(res.post_ms), elem_off=[int(res.elem_off[i]) for i in range(n_inputs + 1)])
         return out
+
+    def ingest_texts(self, texts: Sequence[bytes], slot: int = 0, info: Optional[dict] = None):
+        """Device-side ingest of FASTA texts, the C ABI calls one by one (tests / diagnostics): every text gets a
+        region of a staged batch sized for its byte length, the raw bytes are uploaded, spsp_batch_text_pack cleans
+        and packs them.  -> (n_bases[i], words[i] (the region's packed words), base offset of every region,
+        (rec_begin, rec_end, rec_input) in batch coordinates, total bases of the batch)."""
+        n = len(texts)
+        lens = np.array([len(t) for t in texts], np.uint64)
+        w_off = np.zeros(n, np.uint64); t_off = np.zeros(n, np.uint64)
+        tw = tt = 0
+        for i in range(n):
+            w_off[i], t_off[i] = tw, tt
+            tw += packed_words(int(lens[i])); tt += (int(lens[i]) + 15) & ~15
+        n_total = 16 * tw
+        _dcheck(self.L.spsp_batch_reserve(self.h, slot, packed_words(n_total)), "spsp_batch_reserve")
+        _dcheck(self.L.spsp_batch_text_reserve(self.h, slot, tt), "spsp_batch_text_reserve")
+        for i, t in enumerate(texts):
+            if len(t):
+                _dcheck(self.L.spsp_batch_text_upload(self.h, slot, -1, int(t_off[i]), C.cast(C.c_char_p(t), C.c_void_p), len(t)),
+                        "spsp_batch_text_upload")
+        idx = np.arange(n, dtype=np.uint32)
+        nb = np.zeros(max(n, 1), np.uint64); nr = np.zeros(max(n, 1), np.uint64)
+        _dcheck(self.L.spsp_batch_text_pack(self.h, slot, n, t_off.ctypes.data, lens.ctypes.data, w_off.ctypes.data,
+                                            idx.ctypes.data, nb.ctypes.data, nr.ctypes.data), "spsp_batch_text_pack")
+        n_rec = int(nr[:n].sum())
+        rb = np.zeros(max(n_rec, 1), np.uint64); re_ = np.zeros(max(n_rec, 1), np.uint64); ri = np.zeros(max(n_rec, 1), np.uint32)
+        got = C.c_uint64()
+        _dcheck(self.L.spsp_batch_text_records(self.h, slot, rb.ctypes.data, re_.ctypes.data, ri.ctypes.data, max(n_rec, 1),
+                                               C.byref(got)), "spsp_batch_text_records")
+        assert got.value == n_rec
+        words = []
+        for i in range(n):
+            w = np.zeros(packed_words(int(nb[i])), np.uint32)
+            _dcheck(self.L.spsp_batch_download(self.h, slot, int(w_off[i]), w.ctypes.data, w.size), "spsp_batch_download")
+            words.append(w)
+        if info is not None:
+            ms = C.c_float()
+            _dcheck(self.L.spsp_batch_text_last_ms(self.h, slot, C.byref(ms)), "spsp_batch_text_last_ms")
+            info["ingest_ms"] = float(ms.value)
+        return nb[:n].copy(), words, 16 * w_off, (rb[:n_rec], re_[:n_rec], ri[:n_rec]), n_total
+
+    def sketch_staged(self, n_bases: int, rec_begin, rec_end, rec_input, n_inputs: int, s: float, abundance: int = 1,
+                      slot: int = 0, info: Optional[dict] = None):
+        """spsp_sketch_batch_staged on what was uploaded / ingested on the slot; the record arrays describe the
+        host-packed inputs only (may be empty).  Returns the sketch bytes of every input."""
+        rec_begin = np.ascontiguousarray(rec_begin, np.uint64)
+        rec_end = np.ascontiguousarray(rec_end, np.uint64)
+        rec_input = np.ascontiguousarray(rec_input, np.uint32)
+        res = BatchResult()
+        _dcheck(self.L.spsp_sketch_batch_staged(self.h, slot, n_bases, rec_begin.ctypes.data, rec_end.ctypes.data,
+                                                rec_input.ctypes.data, rec_begin.size, n_inputs, abundance, C.byref(res)),
+                "spsp_sketch_batch_staged")
+        return self._batch_out(res, n_inputs, s, info)
 
     def dense_stats(self, words, n_bases: int, rec_begin, rec_end, rec_input, n_inputs: int, slot: int = 0,
                     device_ptr: Optional[int] = None, info: Optional[dict] = None):

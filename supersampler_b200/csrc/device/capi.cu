@@ -16,6 +16,7 @@
 #include "../../../include/spsp.h"
 #include "compare.cuh"
 #include "dense.cuh"
+#include "ingest.cuh"
 #include "postpass.cuh"
 #include "scan.cuh"
 
@@ -89,6 +90,15 @@ struct Slot {
     PostpassOut last_batch{};
     uint32_t last_batch_inputs = 0;
     bool has_batch = false;
+    // device-side ingest (raw FASTA text -> regions of d_packed + record table)
+    DevBuf b_text, b_ing_in, b_ing_tiles, b_ing_carry, b_ing_tot, b_ing_grand;
+    DevBuf t_rec_begin, t_rec_end, t_rec_input;      // records of the text inputs of the staged batch
+    DevBuf m_rec_begin, m_rec_end, m_rec_input;      // ... merged with the host-packed inputs' records
+    PinBuf p_ing;
+    uint64_t n_trec = 0;
+    uint32_t text_rr = 0;
+    cudaEvent_t ing0 = nullptr, ing1 = nullptr;
+    bool ing_timed = false;
 };
 
 struct spsp_ctx {
@@ -257,6 +267,14 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
         return fail(-1, "spsp_create: no CUDA device (this library has no CPU path)");
     if (device < 0 || device >= cnt) return fail(-3, "spsp_create: bad device index");
     CK(cudaSetDevice(device));
+    // How host threads wait for the device (SPSP_SCHED=spin|yield|block): spinning is fastest when every waiting
+    // thread has a core of its own; with several ranks per box and few cores per rank the waiters must yield.
+    if (const char *sch = getenv("SPSP_SCHED")) {
+        unsigned fl = !strcmp(sch, "yield") ? cudaDeviceScheduleYield : !strcmp(sch, "block") ? cudaDeviceScheduleBlockingSync
+                    : !strcmp(sch, "spin") ? cudaDeviceScheduleSpin : cudaDeviceScheduleAuto;
+        cudaSetDeviceFlags(fl);
+        cudaGetLastError();
+    }
     spsp_ctx *c = new spsp_ctx();
     c->device = device; c->k = k; c->m = m; c->thr = threshold;
     c->slots.resize(n_slots);
@@ -267,6 +285,8 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
         CK(cudaEventCreate(&s.ev0));
         CK(cudaEventCreate(&s.ev1));
         CK(cudaEventCreate(&s.ev2));
+        CK(cudaEventCreate(&s.ing0));
+        CK(cudaEventCreate(&s.ing1));
         for (int u = 0; u < 2; u++) {
             CK(cudaStreamCreateWithFlags(&s.up_stream[u], cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&s.up_event[u], cudaEventDisableTiming));
@@ -301,6 +321,8 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
         if (s.ev2) cudaEventDestroy(s.ev2);
+        if (s.ing0) cudaEventDestroy(s.ing0);
+        if (s.ing1) cudaEventDestroy(s.ing1);
         for (int u = 0; u < 2; u++) {
             if (s.up_stream[u]) { cudaStreamSynchronize(s.up_stream[u]); cudaStreamDestroy(s.up_stream[u]); }
             if (s.up_event[u]) cudaEventDestroy(s.up_event[u]);
@@ -308,6 +330,9 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         if (s.pp) postpass_buffers_destroy(s.pp);
         if (s.dn) dense_buffers_destroy(s.dn);
         s.b_rec_begin.release(); s.b_rec_end.release(); s.b_rec_input.release();
+        s.b_text.release(); s.b_ing_in.release(); s.b_ing_tiles.release(); s.b_ing_carry.release(); s.b_ing_tot.release();
+        s.b_ing_grand.release(); s.t_rec_begin.release(); s.t_rec_end.release(); s.t_rec_input.release();
+        s.m_rec_begin.release(); s.m_rec_end.release(); s.m_rec_input.release(); s.p_ing.release();
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     free_cmp(c);
@@ -809,7 +834,179 @@ extern "C" int spsp_sketch_batch_staged(spsp_ctx *c, int slot, uint64_t n_bases,
         CK(cudaEventRecord(s.up_event[u], s.up_stream[u]));
         CK(cudaStreamWaitEvent(s.stream, s.up_event[u], 0));
     }
+    if (s.n_trec) {
+        // part of the batch was ingested on the device (spsp_batch_text_pack): its records are there already
+        const uint64_t nt = s.n_trec;
+        s.n_trec = 0;
+        const uint64_t *tb = static_cast<const uint64_t *>(s.t_rec_begin.p), *te = static_cast<const uint64_t *>(s.t_rec_end.p);
+        const uint32_t *ti = static_cast<const uint32_t *>(s.t_rec_input.p);
+        if (!n_rec) return batch_impl(c, s, s.d_packed, n_bases, tb, te, ti, nt, n_inputs, abundance, res);
+        if (is_device_ptr(rec_begin)) return fail(-3, "spsp_sketch_batch_staged: host record arrays expected next to ingested text");
+        { int rc_ = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_sketch_batch_staged"); if (rc_) return rc_; }
+        CK(s.b_rec_begin.ensure(n_rec * 8)); CK(s.b_rec_end.ensure(n_rec * 8)); CK(s.b_rec_input.ensure(n_rec * 4));
+        CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, s.stream));
+        const uint64_t n_all = n_rec + nt;
+        CK(s.m_rec_begin.ensure(n_all * 8)); CK(s.m_rec_end.ensure(n_all * 8)); CK(s.m_rec_input.ensure(n_all * 4));
+        CK(launch_record_merge(static_cast<const uint64_t *>(s.b_rec_begin.p), static_cast<const uint64_t *>(s.b_rec_end.p),
+                               static_cast<const uint32_t *>(s.b_rec_input.p), n_rec, tb, te, ti, nt,
+                               static_cast<uint64_t *>(s.m_rec_begin.p), static_cast<uint64_t *>(s.m_rec_end.p),
+                               static_cast<uint32_t *>(s.m_rec_input.p), s.stream));
+        { std::lock_guard<std::mutex> g(c->mu); c->launches += 1; }
+        return batch_impl(c, s, s.d_packed, n_bases, static_cast<const uint64_t *>(s.m_rec_begin.p),
+                          static_cast<const uint64_t *>(s.m_rec_end.p), static_cast<const uint32_t *>(s.m_rec_input.p), n_all,
+                          n_inputs, abundance, res);
+    }
     return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+}
+
+// ------------------------------------------------------------ device-side ingest
+//
+// Raw FASTA text goes to the device as it is (pinned host memory -> async copies on the slot's two copy streams);
+// three kernels (csrc/device/ingest.cu) do what getLineFasta + clean_dna + the 2-bit packer do on the host and
+// leave the cleaned regions in the slot's staged batch buffer plus a record table.  A batch may mix inputs packed
+// on the host (spsp_batch_upload) with inputs ingested here; spsp_sketch_batch_staged merges the record tables.
+
+extern "C" int spsp_batch_text_reserve(spsp_ctx *c, int slot, uint64_t text_bytes)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_batch_text_reserve: bad ctx/slot");
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slots[slot];
+    if (text_bytes + 64 <= s.b_text.cap) return 0;
+    CK(cudaStreamSynchronize(s.stream));          // nothing may still read the old buffer
+    for (int u = 0; u < 2; u++) CK(cudaStreamSynchronize(s.up_stream[u]));
+    CK(s.b_text.ensure(text_bytes + 64));
+    return 0;
+}
+
+extern "C" int spsp_batch_text_upload(spsp_ctx *c, int slot, int lane, uint64_t byte_off, const uint8_t *host_text,
+                                      uint64_t n_bytes)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || lane > 1) return fail(-3, "spsp_batch_text_upload: bad ctx/slot/lane");
+    Slot &s = c->slots[slot];
+    if (byte_off + n_bytes + 64 > s.b_text.cap) return fail(-3, "spsp_batch_text_upload: outside the reserved buffer");
+    if (!n_bytes) return 0;
+    if (!host_text) return fail(-3, "spsp_batch_text_upload: null input");
+    CK(cudaSetDevice(c->device));
+    // lane < 0: alternate between the two copy streams (callable from any thread)
+    cudaStream_t up = s.up_stream[lane >= 0 ? lane : (int)(__atomic_fetch_add(&s.text_rr, 1u, __ATOMIC_RELAXED) & 1u)];
+    CK(cudaMemcpyAsync(static_cast<uint8_t *>(s.b_text.p) + byte_off, host_text, n_bytes, cudaMemcpyHostToDevice, up));
+    return 0;
+}
+
+extern "C" int spsp_batch_upload_wait(spsp_ctx *c, int slot, int lane)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || lane > 1) return fail(-3, "spsp_batch_upload_wait: bad ctx/slot/lane");
+    Slot &s = c->slots[slot];
+    CK(cudaSetDevice(c->device));
+    for (int u = 0; u < 2; u++)
+        if (lane < 0 || lane == u) CK(cudaStreamSynchronize(s.up_stream[u]));
+    return 0;
+}
+
+extern "C" int spsp_batch_text_pack(spsp_ctx *c, int slot, uint32_t n_text, const uint64_t *text_off, const uint64_t *text_len,
+                                    const uint64_t *word_off, const uint32_t *input_index, uint64_t *n_bases_out,
+                                    uint64_t *n_rec_out)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_batch_text_pack: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    s.n_trec = 0;
+    if (!n_text) return 0;
+    if (!text_off || !text_len || !word_off || !input_index) return fail(-3, "spsp_batch_text_pack: null arrays");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = s.stream;
+    // ---- the inputs, validated: aligned text, ascending disjoint regions inside the staged buffer
+    const size_t in_bytes = (size_t)n_text * sizeof(IngestInput), tot_bytes = (size_t)n_text * sizeof(IngestTotals);
+    CK(s.p_ing.ensure(in_bytes + tot_bytes + 16));
+    CK(cudaStreamSynchronize(st));                // p_ing / the ingest scratch of the previous call
+    IngestInput *h_in = static_cast<IngestInput *>(s.p_ing.p);
+    IngestTotals *h_tot = reinterpret_cast<IngestTotals *>(static_cast<uint8_t *>(s.p_ing.p) + in_bytes);
+    uint64_t *h_grand = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(s.p_ing.p) + in_bytes + tot_bytes);
+    uint64_t n_tiles = 0;
+    for (uint32_t i = 0; i < n_text; i++) {
+        if (text_off[i] & 15) return fail(-3, "spsp_batch_text_pack: text offsets must be multiples of 16");
+        if (text_off[i] + text_len[i] + 64 > s.b_text.cap) return fail(-3, "spsp_batch_text_pack: text outside the reserved buffer");
+        if (word_off[i] + spsp_packed_words(text_len[i]) > s.d_packed_words || (word_off[i] & 3))
+            return fail(-3, "spsp_batch_text_pack: region outside the reserved batch buffer");
+        if (i && (word_off[i] < word_off[i - 1] + spsp_packed_words(text_len[i - 1]) || input_index[i] <= input_index[i - 1]))
+            return fail(-3, "spsp_batch_text_pack: inputs must be ascending with disjoint regions");
+        h_in[i] = IngestInput{text_off[i], text_len[i], word_off[i], n_tiles, input_index[i], 0};
+        n_tiles += (text_len[i] + ING_TILE - 1) / ING_TILE;
+    }
+    CK(s.b_ing_in.ensure(in_bytes)); CK(s.b_ing_tot.ensure(tot_bytes)); CK(s.b_ing_grand.ensure(16));
+    CK(s.b_ing_tiles.ensure((n_tiles + 1) * sizeof(IngestTile))); CK(s.b_ing_carry.ensure((n_tiles + 1) * sizeof(IngestCarry)));
+    for (int u = 0; u < 2; u++) {                 // the kernels wait for every upload queued so far
+        CK(cudaEventRecord(s.up_event[u], s.up_stream[u]));
+        CK(cudaStreamWaitEvent(st, s.up_event[u], 0));
+    }
+    const IngestInput *d_in = static_cast<const IngestInput *>(s.b_ing_in.p);
+    IngestTotals *d_tot = static_cast<IngestTotals *>(s.b_ing_tot.p);
+    const uint8_t *d_text = static_cast<const uint8_t *>(s.b_text.p);
+    CK(cudaMemcpyAsync(s.b_ing_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(s.ing0, st));
+    CK(launch_ingest_summary(d_text, d_in, n_text, n_tiles, static_cast<IngestTile *>(s.b_ing_tiles.p), st));
+    CK(launch_ingest_carry(d_in, n_text, static_cast<const IngestTile *>(s.b_ing_tiles.p), static_cast<IngestCarry *>(s.b_ing_carry.p),
+                           d_tot, static_cast<uint64_t *>(s.b_ing_grand.p), st));
+    CK(cudaMemcpyAsync(h_tot, d_tot, tot_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_grand, s.b_ing_grand.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));                // the record table is sized from the count
+    const uint64_t n_rec = h_grand[1];
+    CK(s.t_rec_begin.ensure((n_rec + 1) * 8)); CK(s.t_rec_end.ensure((n_rec + 1) * 8)); CK(s.t_rec_input.ensure((n_rec + 1) * 4));
+    CK(launch_ingest_write(d_text, d_in, n_text, n_tiles, static_cast<const IngestCarry *>(s.b_ing_carry.p), d_tot, s.d_packed,
+                           static_cast<uint64_t *>(s.t_rec_begin.p), static_cast<uint64_t *>(s.t_rec_end.p),
+                           static_cast<uint32_t *>(s.t_rec_input.p), st));
+    CK(cudaEventRecord(s.ing1, st));
+    s.ing_timed = true;
+    s.n_trec = n_rec;
+    for (uint32_t i = 0; i < n_text; i++) {
+        if (n_bases_out) n_bases_out[i] = h_tot[i].n_bases;
+        if (n_rec_out) n_rec_out[i] = h_tot[i].n_rec;
+    }
+    { std::lock_guard<std::mutex> g(c->mu); c->launches += 5; }
+    return 0;
+}
+
+extern "C" int spsp_batch_text_last_ms(spsp_ctx *c, int slot, float *ms)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !ms) return fail(-3, "spsp_batch_text_last_ms: bad args");
+    Slot &s = c->slots[slot];
+    *ms = 0;
+    if (!s.ing_timed) return 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(s.ing1));
+    CK(cudaEventElapsedTime(ms, s.ing0, s.ing1));
+    return 0;
+}
+
+/* Copy of the record table spsp_batch_text_pack left on the slot (tests, diagnostics): n entries each. */
+extern "C" int spsp_batch_text_records(spsp_ctx *c, int slot, uint64_t *rec_begin, uint64_t *rec_end, uint32_t *rec_input,
+                                       uint64_t cap, uint64_t *n_rec)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !n_rec) return fail(-3, "spsp_batch_text_records: bad args");
+    Slot &s = c->slots[slot];
+    *n_rec = s.n_trec;
+    if (s.n_trec > cap) return fail(-2, "spsp_batch_text_records: arrays too small");
+    CK(cudaSetDevice(c->device));
+    if (s.n_trec) {
+        if (rec_begin) CK(cudaMemcpyAsync(rec_begin, s.t_rec_begin.p, s.n_trec * 8, cudaMemcpyDeviceToHost, s.stream));
+        if (rec_end) CK(cudaMemcpyAsync(rec_end, s.t_rec_end.p, s.n_trec * 8, cudaMemcpyDeviceToHost, s.stream));
+        if (rec_input) CK(cudaMemcpyAsync(rec_input, s.t_rec_input.p, s.n_trec * 4, cudaMemcpyDeviceToHost, s.stream));
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+/* Copy of words [word_off, word_off + n_words) of the slot's staged batch buffer (tests, diagnostics). */
+extern "C" int spsp_batch_download(spsp_ctx *c, int slot, uint64_t word_off, uint32_t *host_words, uint64_t n_words)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return fail(-3, "spsp_batch_download: bad ctx/slot");
+    Slot &s = c->slots[slot];
+    if (word_off + n_words > s.d_packed_words) return fail(-3, "spsp_batch_download: outside the reserved buffer");
+    CK(cudaSetDevice(c->device));
+    if (n_words) CK(cudaMemcpyAsync(host_words, s.d_packed + word_off, n_words * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return 0;
 }
 
 // ------------------------------------------------------------ dense totals
@@ -1108,7 +1305,13 @@ static int exchange_impl(spsp_ctx *c, uint64_t n_local, uint64_t q_local, const 
         CK(c->x_tiles.ensure(tile_words * 4));
         uint32_t *d_dims = static_cast<uint32_t *>(c->x_dims.p);
         uint2 *d_units = static_cast<uint2 *>(c->x_units.p);
-        uint32_t *d_tiles = static_cast<uint32_t *>(c->x_tiles.p);
+        // rank 0 keeps the tiles of every rank side by side (its own in slot 0) and assembles the matrix on the device
+        uint32_t *d_recv = nullptr;
+        if (R == 0) {
+            CK(c->x_recv.ensure((size_t)W * tile_words * 4));
+            d_recv = static_cast<uint32_t *>(c->x_recv.p);
+        }
+        uint32_t *d_tiles = R == 0 ? d_recv : static_cast<uint32_t *>(c->x_tiles.p);
         CK(cudaMemsetAsync(d_tiles, 0, tile_words * 4, st));
         CK(launch_exchange_plan(d_hs, W, R, n_cap, e_cap, symmetric ? 1 : 0, rt, (uint32_t)u_cap,
                                 static_cast<uint64_t *>(c->x_begin.p), static_cast<uint64_t *>(c->x_end.p),
@@ -1135,15 +1338,13 @@ static int exchange_impl(spsp_ctx *c, uint64_t n_local, uint64_t q_local, const 
         CK(cudaEventRecord(c->cev1, st));
         c->cmp_timed = true;
         c->launches += 3;
-        // ---- owned tiles to rank 0, everything the host needs in one sweep, ONE synchronisation
+        // ---- owned tiles to rank 0, matrix assembled there on the device; everything the host needs in one sweep,
+        // ONE synchronisation
+        const uint64_t rows_cap = symmetric ? N_cap : W * q_cap;
         const size_t meta_bytes = W * stride * 8 + N_cap * 8 + 32;
-        CK(c->xp_out.ensure(meta_bytes + (R == 0 ? (size_t)W * tile_words * 4 : 0)));
+        const size_t mat_bytes = R == 0 ? (size_t)rows_cap * N_cap * 4 : 0;
+        CK(c->xp_out.ensure(meta_bytes + mat_bytes));
         uint8_t *h_out = static_cast<uint8_t *>(c->xp_out.p);
-        uint32_t *d_recv = nullptr;
-        if (R == 0 && W > 1) {
-            CK(c->x_recv.ensure((size_t)W * tile_words * 4));
-            d_recv = static_cast<uint32_t *>(c->x_recv.p);
-        }
         if (W > 1) {
             NK(n->GroupStart());
             if (R == 0) {
@@ -1157,10 +1358,13 @@ static int exchange_impl(spsp_ctx *c, uint64_t n_local, uint64_t q_local, const 
         CK(cudaMemcpyAsync(h_out + W * stride * 8, c->x_compact.p, N_cap * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_out + W * stride * 8 + N_cap * 8, d_dims, 32, cudaMemcpyDeviceToHost, st));
         if (R == 0) {
-            CK(cudaMemcpyAsync(h_out + meta_bytes, d_tiles, tile_words * 4, cudaMemcpyDeviceToHost, st));
-            if (W > 1)
-                CK(cudaMemcpyAsync(h_out + meta_bytes + tile_words * 4, d_recv + tile_words, (size_t)(W - 1) * tile_words * 4,
-                                   cudaMemcpyDeviceToHost, st));
+            CK(c->x_tiles.ensure(mat_bytes));                              // (rank 0 has no other use for it)
+            uint32_t *d_mat = static_cast<uint32_t *>(c->x_tiles.p);
+            CK(cudaMemsetAsync(d_mat, 0, mat_bytes, st));
+            CK(launch_exchange_assemble(d_recv, tile_words, d_dims, W, symmetric ? 1 : 0, rt, rt_max, (uint32_t)rows_cap,
+                                        (uint32_t)N_cap, d_mat, N_cap, st));
+            c->launches += 1;
+            CK(cudaMemcpyAsync(h_out + meta_bytes, d_mat, mat_bytes, cudaMemcpyDeviceToHost, st));
         }
         CK(cudaStreamSynchronize(st));
         const double t2 = now();
@@ -1191,19 +1395,8 @@ static int exchange_impl(spsp_ctx *c, uint64_t n_local, uint64_t q_local, const 
         if (sizes_out) memcpy(sizes_out, h_out + W * stride * 8, (size_t)N * 8);
         if (R == 0) {
             if (ld < N) return fail(-3, "spsp_cmp_exchange: ld too small");
-            const uint32_t *tiles = reinterpret_cast<const uint32_t *>(h_out + meta_bytes);
-            for (uint64_t i = 0; i < rows; i++) memset(inter_out + i * ld, 0, (size_t)N * 4);
-            const uint32_t nJ = (N + 31) / 32, nI = (rows + 31) / 32;
-            for_each_unit(nI, nJ, symmetric, rt, [&](uint64_t idx, uint32_t jb, uint32_t ib0, uint32_t n_ib) {
-                const uint32_t *src = tiles + (size_t)(idx % W) * tile_words + (size_t)(idx / W) * rt_max * 1024;
-                for (uint32_t t = 0; t < n_ib; t++)
-                    for (uint32_t rr = 0; rr < 32; rr++) {
-                        const uint64_t i = (uint64_t)(ib0 + t) * 32 + rr;
-                        if (i >= rows) break;
-                        const uint32_t cols = std::min<uint32_t>(32, N - jb * 32);
-                        memcpy(inter_out + i * ld + (uint64_t)jb * 32, src + (size_t)t * 1024 + rr * 32, cols * 4);
-                    }
-            });
+            const uint32_t *mat = reinterpret_cast<const uint32_t *>(h_out + meta_bytes);
+            for (uint64_t i = 0; i < rows; i++) memcpy(inter_out + i * ld, mat + i * N_cap, (size_t)N * 4);
         }
         if (timing && R == 0)
             fprintf(stderr, "[xchg] enqueue gather %.0f us | plan+join+collect+sync %.0f | scatter %.0f (N=%u rows=%u units/rank<=%llu)\n",

@@ -329,6 +329,49 @@ cudaError_t launch_exchange_plan(const uint64_t *d_hdrsz, uint32_t world, uint32
     return cudaGetLastError();
 }
 
+// Rank 0, after the owned tiles of every rank have arrived: one CTA per unit (column tile x run of row tiles)
+// copies its compact 32 x 32 tiles to their place in the rows x columns matrix (leading dimension ld, zeroed by
+// the caller).  Same unit enumeration as exchange_plan_kernel: unit idx belongs to rank idx % world, slot idx / world.
+__global__ void __launch_bounds__(256)
+exchange_assemble_kernel(const uint32_t *__restrict__ tiles, uint64_t tile_words, const uint32_t *__restrict__ dims,
+                         uint32_t world, int symmetric, uint32_t rt, uint32_t rt_max, uint32_t *__restrict__ out, uint64_t ld)
+{
+    const uint32_t rows = dims[0], N = dims[1];
+    const uint32_t nI = (rows + 31) / 32, nJ = (N + 31) / 32;
+    const uint32_t jb = blockIdx.x, run = blockIdx.y;
+    if (jb >= nJ) return;
+    const uint32_t lim = symmetric ? min(jb + 1, nI) : nI;
+    const uint32_t ib0 = run * rt;
+    if (ib0 >= lim) return;
+    uint64_t first;
+    if (symmetric) {
+        const uint64_t full = jb / rt, rem = jb % rt;
+        first = rt * full * (full + 1) / 2 + rem * (full + 1);
+    } else {
+        first = (uint64_t)jb * ((nI + rt - 1) / rt);
+    }
+    const uint64_t idx = first + run;
+    const uint32_t *src = tiles + (idx % world) * tile_words + (idx / world) * (uint64_t)rt_max * 1024;
+    const uint32_t n_ib = min(rt, lim - ib0);
+    for (uint32_t i = threadIdx.x; i < n_ib * 1024; i += blockDim.x) {
+        const uint32_t t = i >> 10, rr = (i >> 5) & 31, cc = i & 31;
+        const uint32_t r = (ib0 + t) * 32 + rr, c = jb * 32 + cc;
+        if (r < rows && c < N) out[(uint64_t)r * ld + c] = src[i];
+    }
+}
+
+cudaError_t launch_exchange_assemble(const uint32_t *d_tiles, uint64_t tile_words, const uint32_t *dev_dims, uint32_t world,
+                                     int symmetric, uint32_t rt, uint32_t rt_max, uint32_t rows_cap, uint32_t cols_cap,
+                                     uint32_t *d_out, uint64_t ld, cudaStream_t st)
+{
+    const uint32_t nJ = (cols_cap + 31) / 32, nI = (rows_cap + 31) / 32;
+    const uint32_t runs = (nI + rt - 1) / rt;
+    if (!nJ || !runs) return cudaSuccess;
+    if (runs > 65535) return cudaErrorInvalidValue;
+    exchange_assemble_kernel<<<dim3(nJ, runs), 256, 0, st>>>(d_tiles, tile_words, dev_dims, world, symmetric, rt, rt_max, d_out, ld);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chunk_offsets(const CmpData &d, uint32_t n_sketches, const uint32_t *dev_dims, uint32_t n_chunks, int m,
                                  cudaStream_t st)
 {

@@ -28,6 +28,12 @@ constexpr int XHDR_WORDS = 4;         // exchange header per rank: {sketches, qu
 cudaError_t launch_exchange_plan(const uint64_t *d_hdrsz, uint32_t world, uint32_t rank, uint64_t n_cap, uint64_t e_cap,
                                  int symmetric, uint32_t rt, uint32_t units_cap, uint64_t *sk_begin, uint64_t *sk_end,
                                  uint64_t *sizes_compact, uint2 *units, uint32_t *dims, cudaStream_t st);
+// Rank 0: the compact tiles of every rank ([world][tile_words], unit idx at rank idx % world, slot idx / world, rt_max
+// tile slots per unit) -> the rows x columns matrix d_out (zeroed by the caller, leading dimension ld); grid sized
+// from the capacities, dimensions read from dev_dims.
+cudaError_t launch_exchange_assemble(const uint32_t *d_tiles, uint64_t tile_words, const uint32_t *dev_dims, uint32_t world,
+                                     int symmetric, uint32_t rt, uint32_t rt_max, uint32_t rows_cap, uint32_t cols_cap,
+                                     uint32_t *d_out, uint64_t ld, cudaStream_t st);
 // n_sketches is the capacity when dev_dims (device: dims[1] = sketches) is given.
 cudaError_t launch_chunk_offsets(const CmpData &d, uint32_t n_sketches, const uint32_t *dev_dims, uint32_t n_chunks, int m,
                                  cudaStream_t st);

@@ -324,6 +324,13 @@ extern "C" int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t ba
     return 0;
 }
 
+extern "C" int spsph_pipeline_set_ingest(spsph_pipeline *p, int mode)
+{
+    if (!p || mode < 0 || mode > 2) return hfail("bad arguments");
+    p->bs->ingest = mode == 1 ? Ingest::DEVICE : mode == 2 ? Ingest::AUTO : Ingest::HOST;
+    return 0;
+}
+
 static int pipeline_sources(uint32_t n, const uint8_t *const *fasta, const size_t *len, const char *const *paths,
                             std::vector<BatchSource> &src)
 {
@@ -349,7 +356,7 @@ static void pipeline_deliver(spsph_pipeline *p, uint32_t n, std::vector<std::vec
         stats[0] = st.prep_s; stats[1] = st.pack_s; stats[2] = st.device_s; stats[3] = st.assemble_s;
         stats[4] = st.scan_ms; stats[5] = st.post_ms; stats[6] = (double)st.hits; stats[7] = (double)st.elems;
         stats[8] = (double)st.h2d_bytes; stats[9] = (double)st.d2h_bytes; stats[10] = (double)st.batches;
-        stats[11] = (double)st.bases;
+        stats[11] = (double)st.bases; stats[12] = (double)st.text_inputs; stats[13] = st.ingest_ms;
     }
 }
 

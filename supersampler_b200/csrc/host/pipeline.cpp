@@ -134,6 +134,10 @@ struct BatchSketcher::Prepared {
     // filled by the pack phase
     uint64_t word_off = 0, n_bases = 0;
     std::vector<uint64_t> rec_off;
+    // device-side ingest
+    bool raw = false;                  // went to the device as text
+    uint64_t text_off = 0;             // where in the device text buffer (multiple of 16)
+    uint64_t file_off = 0;             // files: where in the pinned text staging
 };
 
 struct BatchSketcher::Job {
@@ -150,11 +154,14 @@ BatchSketcher::BatchSketcher(std::shared_ptr<DeviceSession> session, int k, int 
     : session_(std::move(session)), pool_(threads), k_(k), m_(m), threads_(threads < 1 ? 1 : threads), s_(s),
       abundance_(abundance)
 {
+    if (const char *e = getenv("SPSP_INGEST"))
+        ingest = !strcmp(e, "device") ? Ingest::DEVICE : !strcmp(e, "auto") ? Ingest::AUTO : Ingest::HOST;
 }
 
 BatchSketcher::~BatchSketcher()
 {
     if (stage_) spsp_host_free(stage_);
+    if (tstage_) spsp_host_free(tstage_);
 }
 
 static bool file_is_gzip(int fd)
@@ -267,14 +274,23 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
     const size_t nb = last - first;
     dbg_no_upload_ = getenv("SPSP_PIPE_NO_UPLOAD") != nullptr;      // measurement aid: pack only (results are garbage)
     auto t0 = clk::now();
-    uint64_t total_words = 0;
+    const Ingest mode = dense_stats ? Ingest::HOST : ingest;   // the dense totals take host record tables
+    uint64_t total_words = 0, total_text = 0, file_text = 0;
     for (size_t i = first; i < last; i++) {
-        prep[i].word_off = total_words;
-        total_words += spsp_packed_words(prep[i].ok ? prep[i].len : 0);
+        Prepared &p = prep[i];
+        p.word_off = total_words;
+        p.raw = false;
+        total_words += spsp_packed_words(p.ok ? p.len : 0);
+        p.text_off = total_text;
+        if (p.ok) {
+            total_text += (p.len + 15) & ~(uint64_t)15;
+            p.file_off = file_text;
+            if (p.from_file) file_text += (p.len + 15) & ~(uint64_t)15;
+        }
     }
     const uint64_t n_total = 16 * total_words;               // one scan covers every region
     const uint64_t need_words = spsp_packed_words(n_total);
-    if (need_words > stage_words_) {
+    if (mode != Ingest::DEVICE && need_words > stage_words_) {
         if (stage_) spsp_host_free(stage_);
         stage_ = nullptr; stage_words_ = 0;
         void *v = nullptr;
@@ -284,9 +300,22 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
         stage_words_ = cap;
     }
     if (spsp_batch_reserve(ctx, 0, need_words) != 0) throw_spsp("spsp_batch_reserve");
+    if (mode != Ingest::HOST) {
+        if (spsp_batch_text_reserve(ctx, 0, total_text) != 0) throw_spsp("spsp_batch_text_reserve");
+        // text read from files passes through pinned memory (sources in memory are copied from where they are)
+        if (file_text > tstage_bytes_) {
+            if (tstage_) spsp_host_free(tstage_);
+            tstage_ = nullptr; tstage_bytes_ = 0;
+            void *v = nullptr;
+            const uint64_t cap = file_text + file_text / 8 + 64;
+            if (spsp_host_alloc(&v, cap) != 0) throw_spsp("spsp_host_alloc");
+            tstage_ = static_cast<uint8_t *>(v);
+            tstage_bytes_ = cap;
+        }
+    }
 
-    // ---- pack: every worker cleans + packs whole inputs into their regions and queues the copy
-    pool_.run(nb, [&](size_t j) {
+    // ---- host lane: clean + pack one whole input into its region and queue the copy
+    auto pack_input = [&](size_t j) {
         Prepared &p = prep[first + j];
         const BatchSource &sc = src[first + j];
         PackedInput in(false);
@@ -332,7 +361,66 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
         upload_to(spsp_packed_words(p.n_bases));
         in.words.detach();
         std::vector<uint8_t>().swap(p.text);
-    });
+    };
+    // ---- device lane: the raw text of one input goes to the device text buffer (copy lane `lane`)
+    auto send_input = [&](size_t j, int lane) {
+        Prepared &p = prep[first + j];
+        const BatchSource &sc = src[first + j];
+        p.raw = true;
+        if (!p.ok || !p.len) return;
+        const size_t SLICE = 4u << 20;
+        if (!p.from_file) {
+            const uint8_t *d = sc.data ? sc.data : p.text.data();
+            for (uint64_t off = 0; off < p.len; off += SLICE)
+                if (spsp_batch_text_upload(ctx, 0, lane, p.text_off + off, d + off, std::min<uint64_t>(SLICE, p.len - off)) != 0)
+                    throw_spsp("spsp_batch_text_upload");
+            if (!sc.data) {                                  // inflated text: must outlive the copy
+                if (spsp_batch_upload_wait(ctx, 0, lane) != 0) throw_spsp("spsp_batch_upload_wait");
+                std::vector<uint8_t>().swap(p.text);
+            }
+            return;
+        }
+        int fd = open(sc.path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot reopen " + sc.path);
+        uint8_t *dst = tstage_ + p.file_off;
+        uint64_t got = 0;
+        while (got < p.len) {
+            ssize_t r = read(fd, dst + got, (size_t)std::min<uint64_t>(SLICE, p.len - got));
+            if (r <= 0) break;
+            if (spsp_batch_text_upload(ctx, 0, lane, p.text_off + got, dst + got, (uint64_t)r) != 0)
+                throw_spsp("spsp_batch_text_upload");
+            got += (uint64_t)r;
+        }
+        close(fd);
+        p.len = got;                                         // (a file that shrank since it was measured)
+    };
+
+    if (mode == Ingest::HOST) {
+        pool_.run(nb, pack_input);
+    } else if (mode == Ingest::DEVICE) {
+        pool_.run(nb, [&](size_t j) { send_input(j, -1); });
+    } else {
+        // one queue, two ends: task 0 is the upload lane (inputs from the back, two in flight: one per copy lane),
+        // every other worker packs inputs from the front until the two ends meet
+        std::mutex qmu;
+        size_t lo = 0, hi = nb;
+        auto take_front = [&](size_t &j) { std::lock_guard<std::mutex> g(qmu); if (lo >= hi) return false; j = lo++; return true; };
+        auto take_back = [&](size_t &j) { std::lock_guard<std::mutex> g(qmu); if (lo >= hi) return false; j = --hi; return true; };
+        const size_t workers = (size_t)std::max(2, pool_.size());
+        pool_.run(workers, [&](size_t w) {
+            size_t j;
+            if (w == 0) {
+                int lane = 0;
+                while (take_back(j)) {
+                    if (spsp_batch_upload_wait(ctx, 0, lane) != 0) throw_spsp("spsp_batch_upload_wait");
+                    send_input(j, lane);
+                    lane ^= 1;
+                }
+            } else {
+                while (take_front(j)) pack_input(j);
+            }
+        });
+    }
     auto t1 = clk::now();
     stats.pack_s += secs(t0, t1);
     job_->total_words = total_words;
@@ -347,18 +435,43 @@ void BatchSketcher::device_batch(std::vector<Prepared> &prep, size_t first, size
     const uint64_t total_words = job_->total_words, n_total = 16 * total_words;
     auto t1 = clk::now();                                 // (not t_packed: the caller may have waited in between)
 
-    // ---- records of the batch, ascending
+    // ---- inputs that went over as text: clean + pack them on the device (their records stay there)
+    {
+        std::vector<uint64_t> t_off, t_len, w_off, nb_out;
+        std::vector<uint32_t> idx;
+        for (size_t i = first; i < last; i++) {
+            const Prepared &p = prep[i];
+            if (!p.raw || !p.ok) continue;
+            t_off.push_back(p.text_off); t_len.push_back(p.len); w_off.push_back(p.word_off); idx.push_back((uint32_t)(i - first));
+        }
+        if (!idx.empty()) {
+            nb_out.resize(idx.size());
+            if (spsp_batch_text_pack(ctx, 0, (uint32_t)idx.size(), t_off.data(), t_len.data(), w_off.data(), idx.data(),
+                                     nb_out.data(), nullptr) != 0)
+                throw_spsp("spsp_batch_text_pack");
+            for (size_t j = 0; j < idx.size(); j++) {
+                prep[first + idx[j]].n_bases = nb_out[j];
+                stats.h2d_bytes += t_len[j];
+            }
+            float ms = 0;
+            spsp_batch_text_last_ms(ctx, 0, &ms);
+            stats.ingest_ms += ms;
+            stats.text_inputs += idx.size();
+        }
+    }
+    // ---- records of the host-packed inputs, ascending
     std::vector<uint64_t> rb, re;
     std::vector<uint32_t> ri;
     for (size_t i = first; i < last; i++) {
         const Prepared &p = prep[i];
         const uint64_t base = 16 * p.word_off;
+        stats.bases += p.n_bases;
+        if (p.raw) continue;
         for (size_t r = 0; r + 1 < p.rec_off.size(); r++) {
             rb.push_back(base + p.rec_off[r]);
             re.push_back(base + p.rec_off[r + 1]);
             ri.push_back((uint32_t)(i - first));
         }
-        stats.bases += p.n_bases;
         stats.h2d_bytes += spsp_packed_words(p.n_bases) * 4;
     }
     spsp_batch_result res{};

@@ -29,7 +29,17 @@ struct BatchStats {
     double prep_s = 0, pack_s = 0, device_s = 0, assemble_s = 0;   // wall seconds, summed over batches
     double scan_ms = 0, post_ms = 0;                               // CUDA events
     uint64_t hits = 0, elems = 0, bases = 0, batches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    uint64_t text_inputs = 0;                                      // inputs that went to the device as raw text
+    double ingest_ms = 0;                                          // their clean + pack kernels (CUDA events)
 };
+
+// Who cleans + packs an input (getLineFasta / clean_dna, utils.cpp:675-718):
+//   HOST    host threads (AVX2 / AVX-512 packer) -> 2-bit words -> H2D (0.25 B per base over PCIe)
+//   DEVICE  raw text -> H2D -> ingest kernels (csrc/device/ingest.cu); the host only moves bytes
+//   AUTO    both at once on one work queue: the pack workers take inputs from the front, one upload lane takes
+//           inputs from the back and keeps two raw inputs in flight, so the split follows what the box can do
+//           (many cores per GPU: mostly HOST; few cores per GPU or short reads: mostly DEVICE)
+enum class Ingest { HOST = 0, DEVICE = 1, AUTO = 2 };
 
 // Persistent worker threads (the pack phase runs every few milliseconds: no thread start-up per batch).
 class WorkerPool {
@@ -83,6 +93,7 @@ public:
     // print_stat totals that need every k-mer (SubSampler.cpp:633-665): filled by run() when dense_stats is
     // set, by the dense minimizer machine on the batch still staged on the device (spsp_dense_stats_staged).
     bool dense_stats = false;
+    Ingest ingest = Ingest::HOST;              // set from SPSP_INGEST (host|device|auto) by the constructor when present
     std::vector<uint64_t> total_kmers, total_superkmers;
     double dense_ms = 0;
 
@@ -101,6 +112,8 @@ private:
     bool dbg_no_upload_ = false;
     uint32_t *stage_ = nullptr;                // pinned staging buffer (grow-only)
     uint64_t stage_words_ = 0;
+    uint8_t *tstage_ = nullptr;                // pinned staging of raw text read from files (grow-only)
+    uint64_t tstage_bytes_ = 0;
     // elements of the last run
     bool elems_on_device_ = false;
     uint32_t n_last_ = 0;
