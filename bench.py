@@ -654,6 +654,9 @@ def b200_arm(args, rank, world, local_rank):
     import supersampler_b200 as S
     from supersampler_b200 import distributed as D
 
+    # host threads that wait for the device yield their core instead of spinning: measured equal to spinning with a
+    # core per waiter (N=1, 16 cores) and ahead of it with 4 cores per rank (8 GPUs on a 32-core box)
+    os.environ.setdefault("SPSP_SCHED", "yield")
     torch.cuda.set_device(local_rank)
     dist = None
     saved_stdout = None
@@ -687,7 +690,10 @@ def b200_arm(args, rank, world, local_rank):
     w_req = args.warmup
     args.warmup = max(args.warmup, rdepth)      # every context has run (tables, buffers) before the clock starts
     # host-buffer path: the public pipeline (pack on host threads -> pinned -> H2D -> scan -> post-pass -> compare)
-    pipes = [S.Pipeline(k, m, s, device=local_rank, threads=threads) for _ in range(depth)]
+    pipes = [S.Pipeline(k, m, s, device=local_rank, threads=threads, ingest=args.ingest) for _ in range(depth)]
+    # host buffers of the e2e path: page-locked when part of the text goes to the device as it is (asynchronous
+    # copies straight from where it lies); plain bytes when host threads pack all of it
+    fastas_e2e = [S.PinnedBuffer(fa) for fa in fastas] if args.ingest != "host" else fastas
     pctxs = [p_.device_context() for p_ in pipes]
     # device-resident path: contexts of their own; all genomes packed back to back, R replicas in HBM
     dctxs = [S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank) for _ in range(rdepth)]
@@ -800,7 +806,7 @@ def b200_arm(args, rank, world, local_rank):
             return sks, res
 
         def step(self, i, record):
-            out = self._note(self.stream.submit(fastas), record)
+            out = self._note(self.stream.submit(fastas_e2e), record)
             if depth == 1:
                 out = self._note(self.stream.drain(), record)
             return out
@@ -967,6 +973,10 @@ def b200_arm(args, rank, world, local_rank):
         "e2e": {"value": val(t_e2e), "unit": UNIT,
                 "h2d_bytes_per_step": int(mean("h2d_bytes")), "d2h_bytes_per_step": int(mean("d2h_bytes")),
                 "ms_per_step": t_e2e / args.steps * 1e3, "host_threads": threads,
+                "ingest": {"mode": args.ingest, "inputs_cleaned_on_device_per_step": mean("text_inputs"),
+                           "of": n_in, "ingest_kernels_ms": mean("ingest_ms"),
+                           "note": "host = host threads clean + pack to 2-bit (0.25 B per base over PCIe); device = raw FASTA "
+                                   "text over PCIe, clean + pack kernels (csrc/device/ingest.cu); auto = both on one work queue"},
                 "phases_ms": {"pack_and_h2d": mean("pack_s") * 1e3, "device": mean("device_s") * 1e3,
                               "assemble": mean("assemble_s") * 1e3, "scan_kernel": mean("scan_ms"),
                               "postpass_device": mean("post_ms"), "compare_kernel": mean("cmp_kernel_ms")},
@@ -1036,6 +1046,8 @@ def main():
     ap.add_argument("--no-pipelining", action="store_true", help="run sketch and compare of a step back to back")
     ap.add_argument("--depth", type=int, default=4, help="device-resident path: batches in flight")
     ap.add_argument("--cmp-depth", type=int, default=2, help="device-resident path: compare stages in flight")
+    ap.add_argument("--ingest", default=os.environ.get("SPSP_INGEST", "auto"), choices=["host", "device", "auto"],
+                    help="e2e path: who cleans + packs the FASTA text (host threads, the device, or both on one work queue)")
     ap.add_argument("--threads", type=int, default=0, help="host packing threads per rank (default: cores / ranks)")
     ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step timed region until this much was measured")
     ap.add_argument("--extras", default="c3,c4,c5", help="full-size BASELINE configs run once after the headline ('' = none)")

@@ -734,7 +734,10 @@ static int batch_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n
         cudaError_t e = postpass_run(s.pp, in, &s.last_batch, st);
         if (e != cudaSuccess) {
             s.has_batch = false;
-            return fail(e == cudaErrorInvalidValue ? -4 : -1, std::string("device post-pass: ") + cudaGetErrorString(e));
+            if (e == cudaErrorInvalidValue)
+                return fail(-4, "device post-pass: batch too large (>= 2^32 bases, or >= 2^31 k-mer entries expected at this "
+                                "sampling rate); cut the job into smaller batches");
+            return fail(-1, std::string("device post-pass: ") + cudaGetErrorString(e));
         }
         launched += s.last_batch.kernels_launched;
         n_hits = s.last_batch.n_hits;

@@ -129,7 +129,7 @@ void WorkerPool::run(size_t n, const std::function<void(size_t)> &fn)
 
 struct BatchSketcher::Prepared {
     uint64_t len = 0;                  // upper bound of the number of bases (= text bytes)
-    bool ok = true, from_file = false;
+    bool ok = true, from_file = false, gz = false;
     std::vector<uint8_t> text;         // inflated gzip input
     // filled by the pack phase
     uint64_t word_off = 0, n_bases = 0;
@@ -196,7 +196,9 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
     n_last_ = (uint32_t)n;
     if (n == 0) return;
 
-    // ---- prepare: sizes; gzip inputs are inflated here (their size is unknown before)
+    // ---- prepare: sizes.  A gzip input's size is unknown before it is inflated: its ISIZE trailer (exact for a
+    // single-member file below 4 GB) or a multiple of the compressed size stands in until its batch is cut;
+    // inflating happens batch by batch, so host memory holds the text of about one batch, not of the whole job
     auto t0 = clk::now();
     prep.assign(n, Prepared());
     pool_.run(n, [&](size_t i) {
@@ -210,15 +212,16 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
             p.ok = false;
             return;
         }
-        const bool gz = file_is_gzip(fd);
-        close(fd);
-        if (gz) {
-            if (!read_file_maybe_gz(src[i].path, p.text)) { p.ok = false; return; }
-            p.from_file = false;
-            p.len = p.text.size();
-        } else {
-            p.len = (uint64_t)st.st_size;
+        p.len = (uint64_t)st.st_size;
+        if (file_is_gzip(fd)) {
+            p.gz = true;
+            unsigned char t4[4] = {0, 0, 0, 0};
+            uint64_t isize = 0;
+            if (st.st_size >= 18 && pread(fd, t4, 4, st.st_size - 4) == 4)
+                isize = (uint64_t)t4[0] | ((uint64_t)t4[1] << 8) | ((uint64_t)t4[2] << 16) | ((uint64_t)t4[3] << 24);
+            p.len = std::max<uint64_t>(isize, 3 * (uint64_t)st.st_size);
         }
+        close(fd);
     });
     stats.prep_s = secs(t0, clk::now());
     for (size_t i = 0; i < n; i++) ok[i] = prep[i].ok ? 1 : 0;
@@ -230,29 +233,43 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
     const double occ_per_base = std::min(1.0, 1.5 * (double)(k_ - m_ + 1) * p_hit);
     const uint64_t occ_limit_bases = (uint64_t)std::min(9.0e18, (double)max_batch_occurrences / std::max(occ_per_base, 1e-12));
     const uint64_t batch_limit = std::max<uint64_t>(4096, std::min(max_batch_bases, occ_limit_bases));
-    std::vector<std::pair<size_t, size_t>> batches;
-    size_t first = 0;
-    uint64_t acc = 0;
-    for (size_t i = 0; i < n; i++) {
-        const uint64_t need = 16 * spsp_packed_words(prep[i].len);
-        if (i > first && acc + need > batch_limit) {
-            batches.emplace_back(first, i);
-            first = i; acc = 0;
+    auto cut = [&](size_t first) {                              // end of the batch that starts at `first`
+        uint64_t acc = 0;
+        size_t i = first;
+        for (; i < n; i++) {
+            const uint64_t need = 16 * spsp_packed_words(prep[i].ok ? prep[i].len : 0);
+            if (i > first && acc + need > batch_limit) break;
+            acc += need;
         }
-        acc += need;
-    }
-    batches.emplace_back(first, n);
-    stats.batches = batches.size();
-    if (batches.size() == 1) {
-        // the usual case: host half now, device half in finish()
-        pack_batch(src, prep, 0, n);
-        job_->first = 0; job_->last = n;
-        job_->device_pending = true;
-        return;
-    }
-    for (auto &b : batches) {
-        pack_batch(src, prep, b.first, b.second);
-        device_batch(prep, b.first, b.second, sketches, true);
+        return i;
+    };
+    size_t first = 0;
+    while (first < n) {
+        size_t last = cut(first);
+        // inflate this batch's gzip inputs (now their sizes are exact), then cut again
+        auto ti = clk::now();
+        pool_.run(last - first, [&](size_t j) {
+            Prepared &p = prep[first + j];
+            if (!p.ok || !p.gz) return;
+            p.gz = false;
+            if (!read_file_maybe_gz(src[first + j].path, p.text)) { p.ok = false; p.len = 0; return; }
+            p.from_file = false;
+            p.len = p.text.size();
+        });
+        stats.prep_s += secs(ti, clk::now());
+        for (size_t i = first; i < last; i++) ok[i] = prep[i].ok ? 1 : 0;
+        last = std::min(last, cut(first));                      // (inputs cut off here keep their text for the next batch)
+        stats.batches++;
+        if (first == 0 && last == n) {
+            // the usual case: host half now, device half in finish()
+            pack_batch(src, prep, 0, n);
+            job_->first = 0; job_->last = n;
+            job_->device_pending = true;
+            return;
+        }
+        pack_batch(src, prep, first, last);
+        device_batch(prep, first, last, sketches, true);
+        first = last;
     }
 }
 

@@ -381,12 +381,15 @@ bool pack_fasta_file(const std::string &path, uint32_t min_len, PackedInput &out
         gzFile gz = gzdopen(fd, "rb");
         if (!gz) { close(fd); return false; }
         gzbuffer(gz, 1u << 20);
+        bool bad = false;
         for (;;) {
             int r = gzread(gz, buf.data(), (unsigned)CH);
+            if (r < 0) bad = true;                 // truncated / corrupt stream: the reference's zstr throws here
             if (r <= 0) break;
             pk.feed(buf.data(), (size_t)r);
         }
-        gzclose(gz);
+        if (gzclose(gz) != Z_OK) bad = true;
+        if (bad) return false;
     } else {
         out.words.reserve((uint64_t)st.st_size / 16 + 64);
         for (;;) {
@@ -424,10 +427,11 @@ bool read_file_maybe_gz(const std::string &path, std::vector<uint8_t> &out)
         for (;;) {
             if (n == out.size()) out.resize(out.size() * 2);
             int r = gzread(gz, out.data() + n, (unsigned)std::min<size_t>(out.size() - n, 1u << 30));
-            if (r <= 0) break;
+            if (r < 0) { gzclose(gz); out.clear(); return false; }     // truncated / corrupt: not a partial success
+            if (r == 0) break;
             n += (size_t)r;
         }
-        gzclose(gz);
+        if (gzclose(gz) != Z_OK) { out.clear(); return false; }
         out.resize(n);
     } else {
         out.resize((size_t)st.st_size);

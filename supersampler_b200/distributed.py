@@ -70,23 +70,44 @@ def local_elements(sketches: Sequence[bytes]):
     return k, m, np.array(sizes, np.int64), cat(mn, np.uint32), cat(lo, np.uint64), (cat(hi, np.uint64) if hi else None)
 
 
-def exchange_elements(sizes: np.ndarray, mn: np.ndarray, lo: np.ndarray, hi: Optional[np.ndarray], device):
-    """All-gather variable-length element lists.  Returns torch tensors on
-    `device`: (sizes_all[world*G] int64 (cpu numpy), minim int32, klo int64, khi int64|None),
-    elements of rank 0's sketches first."""
+def _gather_sizes(sizes: np.ndarray, device) -> List[np.ndarray]:
+    """Per-rank size lists of ranks that may hold different numbers of sketches: the counts go first, the lists
+    are padded to the longest one (collectives need equal shapes on every rank)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
-    t_sizes = torch.from_numpy(sizes.copy()).to(device)
-    all_sizes = [torch.empty_like(t_sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, t_sizes)
-    all_sizes = [x.cpu().numpy() for x in all_sizes]
+    sizes = np.ascontiguousarray(sizes, np.int64)
+    cnt = torch.tensor([sizes.size], dtype=torch.int64, device=device)
+    cnts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(cnts, cnt)
+    cnts = cnts.cpu().numpy()
+    n_max = max(int(cnts.max()), 1)
+    pad = np.zeros(n_max, np.int64)
+    pad[: sizes.size] = sizes
+    out = torch.empty(world * n_max, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, torch.from_numpy(pad).to(device))
+    out = out.cpu().numpy().reshape(world, n_max)
+    return [out[r, : int(cnts[r])].copy() for r in range(world)]
+
+
+def exchange_elements(sizes: np.ndarray, mn: np.ndarray, lo: np.ndarray, hi: Optional[np.ndarray], device,
+                      has_hi: Optional[bool] = None):
+    """All-gather variable-length element lists (ranks may hold different numbers of sketches, or none).
+    Returns torch tensors on `device`: (sizes_all int64 (cpu numpy, rank-major), minim int32, klo int64,
+    khi int64|None), elements of rank 0's sketches first.  has_hi (k > 32) must be the same on every rank: it is
+    taken from `hi` only when not given."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    if has_hi is None:
+        has_hi = hi is not None
+    all_sizes = _gather_sizes(sizes, device)
     e_rank = [int(x.sum()) for x in all_sizes]
     e_max = max(max(e_rank), 1)
 
-    def gather(arr: np.ndarray, np_view, t_dtype):
+    def gather(arr: Optional[np.ndarray], np_view, t_dtype):
         buf = torch.zeros(e_max, dtype=t_dtype, device=device)
-        if arr.size:
+        if arr is not None and arr.size:
             buf[: arr.size] = torch.from_numpy(arr.view(np_view).copy()).to(device)
         outs = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(outs, buf)
@@ -94,7 +115,7 @@ def exchange_elements(sizes: np.ndarray, mn: np.ndarray, lo: np.ndarray, hi: Opt
 
     d_mn = gather(mn, np.int32, torch.int32)
     d_lo = gather(lo, np.int64, torch.int64)
-    d_hi = gather(hi, np.int64, torch.int64) if hi is not None else None
+    d_hi = gather(hi, np.int64, torch.int64) if has_hi else None
     return np.concatenate(all_sizes), d_mn, d_lo, d_hi
 
 
@@ -123,10 +144,7 @@ def exchange_tensors(sizes: np.ndarray, t_mn, t_lo, t_hi, has_hi: bool, device):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
-    t_sizes = torch.from_numpy(np.ascontiguousarray(sizes, np.int64)).to(device)
-    all_sizes = torch.empty(world * t_sizes.numel(), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(all_sizes, t_sizes)
-    all_sizes = all_sizes.cpu().numpy().reshape(world, -1)
+    all_sizes = _gather_sizes(sizes, device)
     e_rank = [int(x.sum()) for x in all_sizes]
     e_mine = int(np.asarray(sizes).sum())
     e_max = (max(max(e_rank), 1) + 1) & ~1                    # even: the 4-byte section stays 8-byte aligned
@@ -149,7 +167,7 @@ def exchange_tensors(sizes: np.ndarray, t_mn, t_lo, t_hi, has_hi: bool, device):
     g_lo = section(0, 8, torch.int64)
     g_hi = section(e_max * 8, 8, torch.int64) if has_hi else None
     g_mn = section(e_max * 8 * n64, 4, torch.int32)
-    return all_sizes.reshape(-1), g_mn, g_lo, g_hi
+    return np.concatenate(all_sizes), g_mn, g_lo, g_hi
 
 
 def compare_gathered(all_sizes, d_mn, d_lo, d_hi, rank: int, world: int, dctx, info: Optional[dict] = None):
@@ -213,7 +231,7 @@ def allgather_compare(sketches: Sequence[bytes], k: int, m: int, rank: int, worl
     import torch.distributed as dist
     dev = torch.device("cuda", torch.cuda.current_device())
     _, _, sizes, mn, lo, hi = local_elements(sketches)
-    all_sizes, d_mn, d_lo, d_hi = exchange_elements(sizes, mn, lo, hi, dev)
+    all_sizes, d_mn, d_lo, d_hi = exchange_elements(sizes, mn, lo, hi, dev, has_hi=k > 32)
     n = int(all_sizes.size)
     sk_off = np.concatenate([[0], np.cumsum(all_sizes)]).astype(np.uint64)
     d_out = torch.zeros(n * n, dtype=torch.int32, device=dev)

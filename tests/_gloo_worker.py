@@ -27,8 +27,8 @@ def main():
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['MASTER_PORT']}", rank=rank,
                             world_size=world)
     k, m, s = 31, 11, 100
-    # 70 sketches in total (3 tiles per side), unevenly split: sketching shards by input file
-    n_total = 70
+    # 71 sketches in total (3 tiles per side), unevenly split (36 / 35): sketching shards by input file
+    n_total = 71
     mine = [i for i in range(n_total) if i % world == rank]
     names = ([f"fam12_{i % 12}" for i in range(n_total)])
     sks = []

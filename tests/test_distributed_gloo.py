@@ -34,4 +34,4 @@ def test_allgather_compare_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     res = json.load(open(tmp_path / "result.json"))
-    assert res["ok"] and res["n"] == 70 and res["pairs_nonzero"] > 1000
+    assert res["ok"] and res["n"] == 71 and res["pairs_nonzero"] > 1000
