@@ -290,6 +290,39 @@ def reference_parity(wd, names, sketches, cmp_res, S):
     return out
 
 
+def cli_end_to_end(paths, names, args, wd, cores, ref_seconds):
+    """The drop-in executables as PROCESSES (cold start: driver + context initialisation included) on the files the
+    reference binaries just processed: bin/sub_sampler -f + bin/comparator, wall clock, outputs compared byte for
+    byte (after gunzip) with the reference's."""
+    import gzip
+    from supersampler_b200 import capi
+    d = os.path.join(wd, "cli")
+    os.makedirs(d, exist_ok=True)
+    fof = os.path.join(d, "in.txt")
+    with open(fof, "w") as f:
+        f.write("\n".join(paths) + "\n")
+    t0 = time.perf_counter()
+    subprocess.run([os.path.join(capi.BIN_DIR, "sub_sampler"), "-f", fof, "-k", str(args.k), "-m", str(args.m), "-s", str(args.s),
+                    "-t", str(cores), "-v", "0"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, check=True)
+    t1 = time.perf_counter()
+    sk = ["subsampled_" + n_ + ".gz" for n_ in names]
+    with open(os.path.join(d, "mine.txt"), "w") as f:
+        f.write("\n".join(os.path.join(d, x) for x in sk) + "\n")
+    subprocess.run([os.path.join(capi.BIN_DIR, "comparator"), "-f", os.path.join(d, "mine.txt"), "-o", "res"], cwd=d,
+                   stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, check=True)
+    t2 = time.perf_counter()
+    gun = lambda p_: gzip.open(p_, "rb").read()
+    same_sk = sum(gun(os.path.join(d, x)) == gun(os.path.join(wd, x)) for x in sk)
+    strip = lambda b_: b_.replace((d + "/").encode(), b"").replace((wd + "/").encode(), b"")       # header row = file names
+    same_csv = all(strip(gun(os.path.join(d, f"res_{t}.csv.gz"))) == strip(gun(os.path.join(wd, f"res_{t}.csv.gz")))
+                   for t in ("containment", "jaccard"))
+    ours = t2 - t0
+    return {"workload": f"C2 files on tmpfs: {len(paths)} x {args.bases} bp, sub_sampler -f -t {cores} -v 0 + comparator, as processes",
+            "ours_s": ours, "ours_sub_sampler_s": t1 - t0, "ours_comparator_s": t2 - t1, "reference_s": ref_seconds,
+            "ratio": ref_seconds / ours, "sketches_identical": int(same_sk), "sketches": len(sk), "csv_identical": bool(same_csv),
+            "note": "cold processes: CUDA driver + context start-up (about 1 s each) is inside ours_s"}
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation on the SAME job as the B200 arm at this N: 64 x N genomes
     sketched with every host core and compared all-vs-all (single-threaded by construction)."""
@@ -430,8 +463,12 @@ def extra_c3(S, SD, rank, world, dist, local_rank, cores, quick):
     ctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
     rs = ResidentSet(ctx, k, m, s)
     bsz = max(1, min(200, (1 << 30) // (SD.words_per_input(nb) * 16)))
-    b0 = fam.packed_batch(g0, 1)
-    ctx.sketch_batch(None, *b0[1:], 1, s, device_ptr=b0[0].data_ptr())      # tables, buffers: outside the timed calls
+    # warm context, as in a long-running job: tables built and buffers grown to this job's batch shape by one untimed
+    # batch (the first one) before the clock starts
+    nw = min(bsz, per)
+    b0 = fam.packed_batch(g0, nw)
+    ctx.sketch_batch(None, *b0[1:], nw, s, device_ptr=b0[0].data_ptr())
+    del b0
     for a in range(g0, g0 + per, bsz):
         cnt = min(bsz, g0 + per - a)
         buf, n_total, rb, re_, ri = fam.packed_batch(a, cnt)
@@ -460,7 +497,8 @@ def extra_c3(S, SD, rank, world, dist, local_rank, cores, quick):
     pairs = G * (G - 1) // 2
     t_sk = float(t_sk.item())
     keycmp = float((sizes.astype(np.float64).sum() * (G - 1)))          # sum over pairs of |K_i| + |K_j|
-    out = {"workload": f"C3: {G} x {nb} bp genomes, k{k} m{m} s{int(s)}, all-vs-all, one fixed job over {world} GPU(s)",
+    out = {"workload": f"C3: {G} x {nb} bp genomes, k{k} m{m} s{int(s)}, all-vs-all, one fixed job over {world} GPU(s); warm context "
+                       f"(one untimed batch of the job's shape first)",
            "scaling": "strong", "value_gbp_per_s": G * nb / (t_sk + t_cmp) / 1e9, "sketch_gbp_per_s": G * nb / t_sk / 1e9,
            "sketch_s": t_sk, "compare_s": t_cmp, "scan_ms": rs.scan_ms, "postpass_ms": rs.post_ms,
            "compare_kernel_ms": cmp_ms, "batches_per_rank": rs.batches, "kernel": _kernel_name(ctx.filter_info()),
@@ -570,8 +608,10 @@ def extra_c5(S, SD, local_rank, cores, quick):
     ctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
     rs = ResidentSet(ctx, k, m, s)
     bsz = max(1, min(200, (1 << 30) // (SD.words_per_input(nb) * 16)))
-    b0 = fam.packed_batch(0, 1)
-    ctx.sketch_batch(None, *b0[1:], 1, s, device_ptr=b0[0].data_ptr())
+    nw = min(bsz, N)                                     # warm context: one untimed batch of the job's shape
+    b0 = fam.packed_batch(0, nw)
+    ctx.sketch_batch(None, *b0[1:], nw, s, device_ptr=b0[0].data_ptr())
+    del b0
     for a in range(0, N, bsz):
         cnt = min(bsz, N - a)
         buf, n_total, rb, re_, ri = fam.packed_batch(a, cnt)
@@ -687,6 +727,8 @@ def b200_arm(args, rank, world, local_rank):
     from concurrent.futures import ThreadPoolExecutor
     depth = 1 if args.no_pipelining else 2
     rdepth = 1 if args.no_pipelining else max(2, args.depth)     # device-resident path: batches in flight
+    if args.cmp_depth <= 0:
+        args.cmp_depth = 2 if world < 4 else min(4, rdepth)
     w_req = args.warmup
     args.warmup = max(args.warmup, rdepth)      # every context has run (tables, buffers) before the clock starts
     # host-buffer path: the public pipeline (pack on host threads -> pinned -> H2D -> scan -> post-pass -> compare)
@@ -888,7 +930,7 @@ def b200_arm(args, rank, world, local_rank):
     # ---- parity against the unmodified reference at this N (checker only, outside every timed region):
     # every rank's FASTA files go to one scratch directory, rank 0 runs oracle/_ref over the 64 x N genomes and
     # holds every sketch of the job and the N x N matrix of the last step against the reference's files.
-    parity, cpu_base = None, None
+    parity, cpu_base, cli_e2e = None, None, None
     from oracle import oracle as O
     if not args.no_cpu_baseline and (O.have_ref() or world == 1):
         wd_box = [scratch_dir() if rank == 0 else None]
@@ -912,6 +954,8 @@ def b200_arm(args, rank, world, local_rank):
                     parity["n_gpus"] = world
                     parity["checked"] = (f"all {len(names_all)} sketches of the {world}-GPU job and the "
                                          f"{len(names_all)} x {len(names_all)} matrix of the last timed step")
+                if kind == "reference" and world == 1:
+                    cli_e2e = cli_end_to_end(paths, names_all, args, wd, cores, a + b)
                 tb = args.bases * len(names_all)
                 prs = len(names_all) * (len(names_all) - 1) // 2
                 cpu_base = {"value": tb / (a + b) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
@@ -1021,6 +1065,8 @@ def b200_arm(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_base
     elif cpu_base is not None:
         line["reference_same_job"] = cpu_base
+    if cli_e2e is not None:
+        line["cli_e2e"] = cli_e2e
     if extra:
         line["extra"] = extra
     if saved_stdout is not None:
@@ -1045,7 +1091,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run (cpu_baseline + parity)")
     ap.add_argument("--no-pipelining", action="store_true", help="run sketch and compare of a step back to back")
     ap.add_argument("--depth", type=int, default=4, help="device-resident path: batches in flight")
-    ap.add_argument("--cmp-depth", type=int, default=2, help="device-resident path: compare stages in flight")
+    ap.add_argument("--cmp-depth", type=int, default=0,
+                    help="device-resident path: compare stages in flight (0 = 2 on one or two GPUs, 4 from four ranks on: an "
+                         "exchange is latency-bound and every context has its own communicator)")
     ap.add_argument("--ingest", default=os.environ.get("SPSP_INGEST", "auto"), choices=["host", "device", "auto"],
                     help="e2e path: who cleans + packs the FASTA text (host threads, the device, or both on one work queue)")
     ap.add_argument("--threads", type=int, default=0, help="host packing threads per rank (default: cores / ranks)")

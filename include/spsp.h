@@ -56,6 +56,9 @@ enum {
 int spsp_abi_version(void);
 const char *spsp_last_error(void);
 int spsp_device_count(int *n);
+/* Initialise the driver and the device's primary context now (~1 s in a fresh process): a CLI calls it on a
+ * background thread while it reads its inputs, so that the first spsp_create does not pay for it. */
+int spsp_warmup(int device);
 
 /* Words (uint32) a packed buffer of n_bases must provide to the scan,
  * including the zero padding the kernels may read. */
@@ -216,6 +219,8 @@ int spsp_batch_text_upload(spsp_ctx *ctx, int slot, int lane, uint64_t byte_off,
 /* Waits until the copies queued on copy lane `lane` (0 / 1; < 0: both) have finished: lets a caller keep a
  * bounded number of uploads in flight. */
 int spsp_batch_upload_wait(spsp_ctx *ctx, int slot, int lane);
+/* *idle = 1 when nothing is queued or running on copy lane `lane` (0 / 1): the PCIe link has room for more. */
+int spsp_batch_upload_idle(spsp_ctx *ctx, int slot, int lane, int *idle);
 int spsp_batch_text_pack(spsp_ctx *ctx, int slot, uint32_t n_text, const uint64_t *text_off, const uint64_t *text_len,
                          const uint64_t *word_off, const uint32_t *input_index, uint64_t *n_bases_out,
                          uint64_t *n_rec_out);

@@ -55,6 +55,13 @@ int spsph_format_csv(const char *const *names, uint32_t n, uint32_t query_size, 
                      const uint64_t *sizes, int jaccard, unsigned precision, double min_threshold, uint8_t **out,
                      size_t *out_len);
 
+/* [cpu] The same text written to `path` as a gzip file, streamed: row blocks are formatted and compressed by
+ * `threads` workers and written in order as consecutive gzip members (memory holds one wave of blocks, not the
+ * whole matrix as text).  text_bytes (may be NULL) = CSV size before compression. */
+int spsph_write_csv_gz(const char *path, const char *const *names, uint32_t n, uint32_t query_size, const uint32_t *inter,
+                       int full_rows, const uint64_t *sizes, int jaccard, unsigned precision, double min_threshold,
+                       int threads, uint64_t *text_bytes);
+
 /* GPU: sketch n FASTA texts held in memory with `threads` host workers on
  * `device`; out[i]/out_len[i] receive the sketch bytes (before gzip).
  * timings (may be NULL): [0]=pack s, [1]=scan s (submit..collect), [2]=post-pass s,

@@ -9,6 +9,6 @@ There is no CPU fallback: GPU entry points raise when no CUDA device exists.
 """
 from .capi import (  # noqa: F401
     SpspError, build, device_lib, host_lib, threshold, pack_fasta, postpass, decode_sketch,
-    format_csv, sketch_buffers, compare_buffers, run_sub_sampler, run_comparator, run_sort_csv, DeviceContext,
+    format_csv, write_csv_gz, sketch_buffers, compare_buffers, run_sub_sampler, run_comparator, run_sort_csv, DeviceContext,
     HIT_DTYPE, packed_words, batch_layout, Sketcher, Comparer, Pipeline, BatchStream, PinnedBuffer, postpass_batch, SCAN_AUTO, SCAN_DENSE, SCAN_FILTER,
 )

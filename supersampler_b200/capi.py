@@ -66,7 +66,8 @@ def _need(path: str) -> str:
 def device_lib():
     global _dev
     if _dev is None:
-        L = C.CDLL(_need(os.path.join(LIB_DIR, "libspsp_b200.so")), mode=C.RTLD_GLOBAL)
+        # SPSP_DEVICE_LIB: another build of the device layer (kernel experiments); the default is the in-tree library
+        L = C.CDLL(_need(os.environ.get("SPSP_DEVICE_LIB") or os.path.join(LIB_DIR, "libspsp_b200.so")), mode=C.RTLD_GLOBAL)
         L.spsp_last_error.restype = C.c_char_p
         L.spsp_packed_words.restype = C.c_uint64
         L.spsp_packed_words.argtypes = [C.c_uint64]
@@ -269,6 +270,22 @@ def format_csv(names: Sequence[str], query_size: int, inter: np.ndarray, full_ro
     _hcheck(L.spsph_format_csv(arr, n, query_size, inter.ctypes.data, int(full_rows), sizes.ctypes.data, int(jaccard),
                                precision, min_threshold, C.byref(out), C.byref(ln)), "format_csv")
     return _take(out, ln.value, np.uint8).tobytes()
+
+
+def write_csv_gz(path: str, names: Sequence[str], query_size: int, inter: np.ndarray, full_rows: bool, sizes: np.ndarray,
+                 jaccard: bool, precision: int = 6, min_threshold: float = 0.0, threads: int = 4) -> int:
+    """format_csv streamed into a gzip file (parallel row blocks, consecutive gzip members) -> CSV bytes before compression."""
+    L = host_lib()
+    n = len(names)
+    arr = (C.c_char_p * n)(*[x.encode() for x in names])
+    inter = np.ascontiguousarray(inter, np.uint32)
+    sizes = np.ascontiguousarray(sizes, np.uint64)
+    tb = C.c_uint64()
+    L.spsph_write_csv_gz.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_int, C.c_uint, C.c_double, C.c_int, C.POINTER(C.c_uint64)]
+    _hcheck(L.spsph_write_csv_gz(os.fsencode(path), arr, n, query_size, inter.ctypes.data, int(full_rows), sizes.ctypes.data,
+                                 int(jaccard), precision, min_threshold, threads, C.byref(tb)), "write_csv_gz")
+    return int(tb.value)
 
 
 def sketch_buffers(fastas: Sequence[bytes], k: int = 31, m: int = 11, s: float = 1000.0, abundance: int = 1,

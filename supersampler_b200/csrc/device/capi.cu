@@ -154,6 +154,13 @@ extern "C" int spsp_device_count(int *n)
     return 0;
 }
 
+extern "C" int spsp_warmup(int device)
+{
+    CK(cudaSetDevice(device));
+    CK(cudaFree(nullptr));                       // creates the primary context
+    return 0;
+}
+
 extern "C" uint64_t spsp_packed_words(uint64_t n_bases) { return 4 * ((n_bases + 4 + 63) / 64) + 8; }
 
 extern "C" int spsp_host_alloc(void **p, size_t bytes)
@@ -895,6 +902,16 @@ extern "C" int spsp_batch_text_upload(spsp_ctx *c, int slot, int lane, uint64_t 
     // lane < 0: alternate between the two copy streams (callable from any thread)
     cudaStream_t up = s.up_stream[lane >= 0 ? lane : (int)(__atomic_fetch_add(&s.text_rr, 1u, __ATOMIC_RELAXED) & 1u)];
     CK(cudaMemcpyAsync(static_cast<uint8_t *>(s.b_text.p) + byte_off, host_text, n_bytes, cudaMemcpyHostToDevice, up));
+    return 0;
+}
+
+extern "C" int spsp_batch_upload_idle(spsp_ctx *c, int slot, int lane, int *idle)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || lane < 0 || lane > 1 || !idle)
+        return fail(-3, "spsp_batch_upload_idle: bad ctx/slot/lane");
+    const cudaError_t e = cudaStreamQuery(c->slots[slot].up_stream[lane]);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(-1, std::string("cudaStreamQuery: ") + cudaGetErrorString(e));
+    *idle = e == cudaSuccess ? 1 : 0;
     return 0;
 }
 

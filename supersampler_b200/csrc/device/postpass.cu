@@ -111,11 +111,22 @@ enum { OVF_PIECES = 1, OVF_BODY = 2, OVF_ELEMS = 4, OVF_BIG = 8, OVF_SORT = 16 }
 
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
 constexpr int RP_THREADS = 256;      // replay kernels
-constexpr int BK_THREADS = 256;      // bucket-group kernel
+// Bucket-group kernel: CTA size and group size go together (a group's phases are separated by CTA barriers and
+// several of them keep only a few lanes busy -- the chain walk has one lane per bucket -- so what fills an SM is the
+// number of resident groups, which shared memory bounds).  SPSP_BK_SCALE = 1, 2, 4 (compile time) divides both;
+// measured on B200 (profiles/README.md): 1 is best -- a group's phases cost about the same cycles whatever its
+// size (each is a chain of dependent shared-memory accesses per thread), so smaller groups only add groups:
+// 64 x 5 Mbp batch 0.27 / 0.27 / 0.40 ms, 1 Gbp batch at s=100 3.7 / 4.2 / 7.6 ms for scale 1 / 2 / 4.
+#ifndef SPSP_BK_SCALE
+#define SPSP_BK_SCALE 1
+#endif
+constexpr int BK_THREADS = 256 / SPSP_BK_SCALE;      // bucket-group kernel
 constexpr int BK_WARPS = BK_THREADS / 32;
-constexpr int BK_ECAP = 1024;        // entries of a group staged in shared memory
-constexpr int BK_PMAX = 128;         // pieces of such a group
-constexpr int BK_SLOTS = 2048;       // its open-addressing table (load <= 0.5)
+constexpr int BK_ECAP = 1024 / SPSP_BK_SCALE;        // entries of a group staged in shared memory
+constexpr int BK_PMAX = 128 / SPSP_BK_SCALE;         // pieces of such a group
+constexpr int BK_SLOTS = 2048 / SPSP_BK_SCALE;       // its open-addressing table (load <= 0.5)
+constexpr int BK_PP_ENTRIES = 600 / SPSP_BK_SCALE;   // entries a group aims at (pieces per group = this / (k - m + 1))
+static_assert(BK_WARPS >= 2, "the bucket kernel needs a look-back warp and at least one writer warp");
 constexpr int RC_SK = 192;           // 2-bit codes of a super-k-mer (2k-m <= 123, grows both ways from 64)
 constexpr uint32_t H_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t VIS_START = 0, VIS_LEFT = 1, VIS_RIGHT = 2;
@@ -131,6 +142,7 @@ constexpr uint32_t VIS_START = 0, VIS_LEFT = 1, VIS_RIGHT = 2;
 // permutation.
 constexpr int SS_THREADS = 1024, SS_CAP = 32768, SS_BIN_BITS = 13, SS_BINS = 1 << SS_BIN_BITS;
 constexpr size_t SS_SMEM = (size_t)SS_CAP * 4 + (size_t)SS_CAP * 2 + (size_t)(SS_BINS + 32) * 4;
+constexpr int SS_MLP = 4;            // keys a thread handles at a time (their loads are in flight together)
 
 template <bool HITS>
 __global__ void __launch_bounds__(SS_THREADS, 1)
@@ -154,24 +166,74 @@ pp_sort_small_kernel(const spsp_hit *__restrict__ hits, const unsigned long long
     const uint32_t n = (uint32_t)n64;
     const int shift = key_bits > SS_BIN_BITS ? key_bits - SS_BIN_BITS : 0;
     for (uint32_t b = threadIdx.x; b <= SS_BINS; b += SS_THREADS) s_off[b] = 0;
+    // One CTA means one memory latency per dependent load: every loop below works on SS_MLP keys per thread at a
+    // time, with their loads issued together, and the record look-up of a hit starts in a sampled copy of
+    // rec_begin in shared memory (complete when the batch has at most 256 records: whole genomes).
+    __shared__ uint64_t s_coarse[256];
+    uint64_t c_stride = 1;
+    uint32_t c_n = 0;
+    if (HITS && n_rec) {
+        c_stride = (n_rec + 255) / 256;
+        c_n = (uint32_t)((n_rec + c_stride - 1) / c_stride);
+        for (uint32_t j = threadIdx.x; j < c_n; j += SS_THREADS) s_coarse[j] = rec_begin[(uint64_t)j * c_stride];
+    }
     __syncthreads();
     // pass 1: keys (kept in key_out, unsorted, for pass 2) and the histogram
-    for (uint32_t i = threadIdx.x; i < n; i += SS_THREADS) {
-        uint32_t key = KEY_INVALID;
+    for (uint32_t base = 0; base < n; base += SS_THREADS * SS_MLP) {
+        uint32_t key[SS_MLP];
         if (HITS) {
-            const uint64_t pos = hits[i].pos;
-            if (n_rec) {
-                const long long r = find_rec(rec_begin, n_rec, pos);
-                if (r >= 0) {
-                    const uint64_t b = rec_begin[r], e = rec_end[r];
-                    if (pos + (uint64_t)m <= e && e - b >= (uint64_t)k) key = (uint32_t)pos;
+            uint64_t pos[SS_MLP], rb[SS_MLP], re[SS_MLP];
+            long long r[SS_MLP];
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) {
+                const uint32_t i = base + j * SS_THREADS + threadIdx.x;
+                pos[j] = i < n ? hits[i].pos : ~0ULL;
+            }
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) {
+                // last record whose begin is <= pos: coarse step in shared memory, the rest (if any) in global memory
+                uint32_t lo = 0, hi = c_n;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_coarse[mid] <= pos[j]) lo = mid + 1; else hi = mid;
+                }
+                long long rr = -1;
+                if (lo) {
+                    uint64_t a = (uint64_t)(lo - 1) * c_stride, b = min(a + c_stride, n_rec);   // begin[a] <= pos
+                    a++;
+                    while (a < b) {
+                        const uint64_t mid = (a + b) >> 1;
+                        if (rec_begin[mid] <= pos[j]) a = mid + 1; else b = mid;
+                    }
+                    rr = (long long)a - 1;
+                }
+                r[j] = rr;
+            }
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) {
+                const bool ok = r[j] >= 0 && pos[j] != ~0ULL;
+                rb[j] = ok ? rec_begin[r[j]] : 0;
+                re[j] = ok ? rec_end[r[j]] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) {
+                const uint32_t i = base + j * SS_THREADS + threadIdx.x;
+                key[j] = KEY_INVALID;
+                if (i < n) {
+                    if (r[j] >= 0 && pos[j] + (uint64_t)m <= re[j] && re[j] - rb[j] >= (uint64_t)k) key[j] = (uint32_t)pos[j];
+                    key_out[i] = key[j];
                 }
             }
-            key_out[i] = key;
         } else {
-            key = key_in[i];
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) {
+                const uint32_t i = base + j * SS_THREADS + threadIdx.x;
+                key[j] = i < n ? key_in[i] : KEY_INVALID;
+            }
         }
-        if (key != KEY_INVALID) atomicAdd(&s_off[min(key >> shift, (uint32_t)SS_BINS - 1)], 1u);
+#pragma unroll
+        for (int j = 0; j < SS_MLP; j++)
+            if (key[j] != KEY_INVALID) atomicAdd(&s_off[min(key[j] >> shift, (uint32_t)SS_BINS - 1)], 1u);
     }
     __syncthreads();
     // exclusive scan of the histogram (8 bins per thread)
@@ -207,31 +269,58 @@ pp_sort_small_kernel(const spsp_hit *__restrict__ hits, const unsigned long long
     }
     __syncthreads();
     // pass 2: scatter into the bins (cursor = running end of the bin)
-    for (uint32_t i = threadIdx.x; i < n; i += SS_THREADS) {
-        const uint32_t key = HITS ? key_out[i] : key_in[i];
-        if (key != KEY_INVALID) {
-            const uint32_t d = atomicAdd(&s_off[min(key >> shift, (uint32_t)SS_BINS - 1)], 1u);
-            s_key[d] = key;
-            s_idx[d] = (uint16_t)i;
+    for (uint32_t base = 0; base < n; base += SS_THREADS * SS_MLP) {
+        uint32_t key[SS_MLP];
+#pragma unroll
+        for (int j = 0; j < SS_MLP; j++) {
+            const uint32_t i = base + j * SS_THREADS + threadIdx.x;
+            key[j] = i < n ? (HITS ? key_out[i] : key_in[i]) : KEY_INVALID;
+        }
+#pragma unroll
+        for (int j = 0; j < SS_MLP; j++) {
+            if (key[j] != KEY_INVALID) {
+                const uint32_t d = atomicAdd(&s_off[min(key[j] >> shift, (uint32_t)SS_BINS - 1)], 1u);
+                s_key[d] = key[j];
+                s_idx[d] = (uint16_t)(base + j * SS_THREADS + threadIdx.x);
+            }
         }
     }
     __syncthreads();
     // order inside the bins (s_off[b] is now the END of bin b): every key counts the keys of its bin that sort before
     // it -- (key, original index), which makes the sort stable -- and goes straight to its final place
-    for (uint32_t r = threadIdx.x; r < total; r += SS_THREADS) {
-        const uint32_t kx = s_key[r];
-        const uint16_t ix = s_idx[r];
-        const uint32_t b = min(kx >> shift, (uint32_t)SS_BINS - 1);
-        const uint32_t lo = b ? s_off[b - 1] : 0, hi = s_off[b];
-        uint32_t rank = 0;
-        for (uint32_t q = lo; q < hi; q++) rank += (s_key[q] < kx || (s_key[q] == kx && s_idx[q] < ix)) ? 1u : 0u;
-        key_out[lo + rank] = kx;
-        if (HITS) {
-            const spsp_hit h = hits[ix];
-            val_out[lo + rank] = (h.canon << 1) | (h.rev & 1u);
-        } else {
-            val_out[lo + rank] = ix;
+    for (uint32_t base = 0; base < total; base += SS_THREADS * SS_MLP) {
+        uint32_t dst[SS_MLP], kxs[SS_MLP], val[SS_MLP];
+        uint16_t ixs[SS_MLP];
+#pragma unroll
+        for (int j = 0; j < SS_MLP; j++) {
+            const uint32_t r = base + j * SS_THREADS + threadIdx.x;
+            dst[j] = 0xFFFFFFFFu; kxs[j] = 0; ixs[j] = 0;
+            if (r < total) {
+                const uint32_t kx = s_key[r];
+                const uint16_t ix = s_idx[r];
+                const uint32_t b = min(kx >> shift, (uint32_t)SS_BINS - 1);
+                const uint32_t lo = b ? s_off[b - 1] : 0, hi = s_off[b];
+                uint32_t rank = 0;
+                for (uint32_t q = lo; q < hi; q++) rank += (s_key[q] < kx || (s_key[q] == kx && s_idx[q] < ix)) ? 1u : 0u;
+                dst[j] = lo + rank; kxs[j] = kx; ixs[j] = ix;
+            }
         }
+        if (HITS) {
+            uint32_t cn[SS_MLP], rv[SS_MLP];
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) {
+                cn[j] = dst[j] != 0xFFFFFFFFu ? hits[ixs[j]].canon : 0;
+                rv[j] = dst[j] != 0xFFFFFFFFu ? hits[ixs[j]].rev : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) val[j] = (cn[j] << 1) | (rv[j] & 1u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SS_MLP; j++) val[j] = ixs[j];
+        }
+#pragma unroll
+        for (int j = 0; j < SS_MLP; j++)
+            if (dst[j] != 0xFFFFFFFFu) { key_out[dst[j]] = kxs[j]; val_out[dst[j]] = val[j]; }
     }
     if (HITS && threadIdx.x == 0) cnt->n_valid = total;
 }
@@ -1090,11 +1179,10 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
     if (warp == 0) {
         const unsigned long long x = lookback(a.lb_bytes, grp, bytes_total);
         if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 2) = x; }
-    } else if (warp == 1) {
-        const unsigned long long x = lookback(a.lb_elems, grp, NE);
-        if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 4) = x; }
+        const unsigned long long y = lookback(a.lb_elems, grp, NE);
+        if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 4) = y; }
     } else if (staged) {
-        emit_buckets(stage, (uint32_t)warp - 2, BK_WARPS - 2);
+        emit_buckets(stage, (uint32_t)warp - 1, BK_WARPS - 1);
     }
     __syncthreads();
     const unsigned long long byte_base = *reinterpret_cast<unsigned long long *>(s_misc + 2);
@@ -1160,8 +1248,7 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
     auto bucket_key = [&](uint32_t i) -> uint64_t { return a.skey64 ? a.skey64[i] : (uint64_t)a.skey32[i]; };
     auto is_head = [&](uint32_t i) { return i == 0 || bucket_key(i) != bucket_key(i - 1); };
     auto publish_empty = [&]() {
-        if (warp == 0) lookback(a.lb_bytes, grp, 0);
-        else if (warp == 1) lookback(a.lb_elems, grp, 0);
+        if (warp == 0) { lookback(a.lb_bytes, grp, 0); lookback(a.lb_elems, grp, 0); }
     };
     const uint64_t lo64 = (uint64_t)grp * a.pp;
     if (lo64 >= n_pieces) {                                      // nothing looks back at groups behind the data
@@ -1321,7 +1408,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     const int a_bits = input_shift + bits_for(in.n_inputs ? in.n_inputs - 1 : 0);
     const bool key64 = a_bits > 31;                                  // 32-bit keys keep one value above every bucket for the padding
     const size_t nin = in.n_inputs ? in.n_inputs : 1;
-    const uint32_t pp = (uint32_t)std::min(32, std::max(4, 600 / (d + 1)));
+    const uint32_t pp = (uint32_t)std::min(32 / SPSP_BK_SCALE, std::max(2, BK_PP_ENTRIES / (d + 1)));
     out->retry = 0;
 
     const uint64_t p_cap = std::max<uint64_t>(H + H / 8 + 1024, b->pieces_cap_min);

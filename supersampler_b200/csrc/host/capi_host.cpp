@@ -172,6 +172,20 @@ extern "C" int spsph_sketcher_run(spsph_sketcher *sk, uint32_t n, const uint8_t 
     } catch (const std::exception &e) { return hfail(e.what()); }
 }
 
+extern "C" int spsph_write_csv_gz(const char *path, const char *const *names, uint32_t n, uint32_t query_size,
+                                  const uint32_t *inter, int full_rows, const uint64_t *sizes, int jaccard, unsigned precision,
+                                  double min_threshold, int threads, uint64_t *text_bytes)
+{
+    try {
+        std::vector<std::string> nm(names, names + n);
+        std::vector<uint64_t> sz(sizes, sizes + n);
+        if (!write_csv_gz(path, nm, query_size, inter, n, full_rows != 0, sz, jaccard != 0, precision, min_threshold, threads,
+                          text_bytes))
+            return hfail(std::string("cannot write ") + path);
+        return 0;
+    } catch (const std::exception &e) { return hfail(e.what()); }
+}
+
 extern "C" int spsph_sketch_buffers(int device, int k, int m, double s, unsigned abundance, int scan_mode, uint32_t n,
                                     const uint8_t *const *fasta, const size_t *len, int threads, uint8_t **out,
                                     size_t *out_len, double *timings, uint64_t *launches)

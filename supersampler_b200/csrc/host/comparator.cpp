@@ -84,7 +84,9 @@ void Comparator::compare_sketches(unsigned size_query)
     files_names = names;      // keeps the CSV aligned with the sketches that were compared
     query_size = q;
     t_load = secs(t0, clk::now());
+    trace("sketches read + decoded");
     run_device(kept);
+    trace("compared");
     std::cout << "kmers evaluated are of length: " << k << " minimizer size is " << m << std::endl;
     std::cout << "Comparisons done" << std::endl;
 }
@@ -205,17 +207,19 @@ void Comparator::csv(bool jaccard, std::vector<uint8_t> &out) const
 void Comparator::print_containment(const std::string &outfile)
 {
     std::cout << "Containement index dump " << std::endl;
-    std::vector<uint8_t> out;
-    csv(false, out);
-    if (!write_gz(outfile, out.data(), out.size(), 1)) std::cout << "Can't write " << outfile << std::endl;
+    const int nt = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    if (!write_csv_gz(outfile, files_names, (uint32_t)query_size, score.data(), nb_files, full_rows, nb_kmer_seen_infile, false,
+                      (unsigned)precision, min_threshold, nt, nullptr))
+        std::cout << "Can't write " << outfile << std::endl;
 }
 
 void Comparator::print_jaccard(const std::string &outfile)
 {
     std::cout << "Jackard index dump" << std::endl;
-    std::vector<uint8_t> out;
-    csv(true, out);
-    if (!write_gz(outfile, out.data(), out.size(), 1)) std::cout << "Can't write " << outfile << std::endl;
+    const int nt = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    if (!write_csv_gz(outfile, files_names, (uint32_t)query_size, score.data(), nb_files, full_rows, nb_kmer_seen_infile, true,
+                      (unsigned)precision, min_threshold, nt, nullptr))
+        std::cout << "Can't write " << outfile << std::endl;
 }
 
 int comparator_main(int argc, char **argv)
@@ -252,11 +256,21 @@ int comparator_main(int argc, char **argv)
                   << "-g Number of GPUs (1)" << std::endl;
         return 0;
     }
+    if (gpus <= 1) setenv("CUDA_VISIBLE_DEVICES", "0", 0);
+    // driver + context start-up (~1 s) runs beside the reading and decoding of the sketch files
+    std::thread warm([gpus] {
+        int ndev = 0;
+        if (spsp_device_count(&ndev) != 0) return;
+        for (int d = 0; d < ndev && d < (int)std::max(1u, gpus); d++) spsp_warmup(d);
+        trace("devices warm");
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
     try {
         Comparator comp(p, min_threshold);
         comp.n_gpus = (int)gpus;
         comp.n_threads = (int)threads;
         auto start = clk::now();
+        trace("main: arguments parsed");
         if (query.empty()) {
             std::cout << "No query file, I will perform a all versus all comparison" << std::endl;
             comp.getfilesname(inputfof, comp.files_names);
@@ -274,6 +288,7 @@ int comparator_main(int argc, char **argv)
         comp.print_containment(output_name + "_containment.csv.gz");
         comp.print_jaccard(output_name + "_jaccard.csv.gz");
         std::cout << "Jaccard output lasted " << secs(middle, clk::now()) << " sec" << std::endl;
+        trace("CSV files written");
     } catch (const std::exception &e) {
         std::cerr << "comparator: " << e.what() << std::endl;
         return 2;

@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <functional>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -331,6 +332,32 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
         }
     }
 
+    // AUTO: called by the pack workers between slices -- a copy lane with nothing queued means the link has room:
+    // send an input from the back of the queue as raw text (asynchronous; the worker goes on packing)
+    std::mutex qmu;
+    size_t q_lo = 0, q_hi = nb;
+    std::atomic<int> lane_claim[2];
+    lane_claim[0] = 0; lane_claim[1] = 0;
+    std::function<void(size_t, int)> send_input_fn;
+    auto feed_link = [&]() {
+        if (mode != Ingest::AUTO) return;
+        for (int lane = 0; lane < 2; lane++) {
+            int idle = 0;
+            if (lane_claim[lane].load(std::memory_order_relaxed)) continue;
+            if (spsp_batch_upload_idle(ctx, 0, lane, &idle) != 0) throw_spsp("spsp_batch_upload_idle");
+            if (!idle || lane_claim[lane].exchange(1)) continue;
+            size_t j = 0;
+            bool got = false;
+            {
+                // (text that still sits in a file would have to be read into pinned memory by this worker first,
+                // which costs about what packing it costs: files go over as text in DEVICE mode only)
+                std::lock_guard<std::mutex> g(qmu);
+                if (q_lo < q_hi && !prep[first + q_hi - 1].from_file) { j = --q_hi; got = true; }
+            }
+            if (got) send_input_fn(j, lane);
+            lane_claim[lane].store(0);
+        }
+    };
     // ---- host lane: clean + pack one whole input into its region and queue the copy
     auto pack_input = [&](size_t j) {
         Prepared &p = prep[first + j];
@@ -356,6 +383,7 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
                 for (size_t off = 0; off < len; off += SLICE) {
                     pk.feed(d + off, std::min(SLICE, len - off));
                     if (off + SLICE < len) upload_to(pk.commit());
+                    feed_link();
                 }
             } else {
                 int fd = open(sc.path.c_str(), O_RDONLY);
@@ -368,6 +396,7 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
                     pk.feed(buf.data(), (size_t)r);
                     got += (uint64_t)r;
                     if (got < p.len) upload_to(pk.commit());
+                    feed_link();
                 }
                 close(fd);
             }
@@ -412,29 +441,23 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
         p.len = got;                                         // (a file that shrank since it was measured)
     };
 
+    send_input_fn = send_input;
     if (mode == Ingest::HOST) {
         pool_.run(nb, pack_input);
     } else if (mode == Ingest::DEVICE) {
         pool_.run(nb, [&](size_t j) { send_input(j, -1); });
     } else {
-        // one queue, two ends: task 0 is the upload lane (inputs from the back, two in flight: one per copy lane),
-        // every other worker packs inputs from the front until the two ends meet
-        std::mutex qmu;
-        size_t lo = 0, hi = nb;
-        auto take_front = [&](size_t &j) { std::lock_guard<std::mutex> g(qmu); if (lo >= hi) return false; j = lo++; return true; };
-        auto take_back = [&](size_t &j) { std::lock_guard<std::mutex> g(qmu); if (lo >= hi) return false; j = --hi; return true; };
-        const size_t workers = (size_t)std::max(2, pool_.size());
-        pool_.run(workers, [&](size_t w) {
-            size_t j;
-            if (w == 0) {
-                int lane = 0;
-                while (take_back(j)) {
-                    if (spsp_batch_upload_wait(ctx, 0, lane) != 0) throw_spsp("spsp_batch_upload_wait");
-                    send_input(j, lane);
-                    lane ^= 1;
+        // one queue, two ends: every worker packs inputs from the front; raw sends take inputs from the back
+        pool_.run((size_t)std::max(1, pool_.size()), [&](size_t) {
+            for (;;) {
+                feed_link();
+                size_t j;
+                {
+                    std::lock_guard<std::mutex> g(qmu);
+                    if (q_lo >= q_hi) break;
+                    j = q_lo++;
                 }
-            } else {
-                while (take_front(j)) pack_input(j);
+                pack_input(j);
             }
         });
     }

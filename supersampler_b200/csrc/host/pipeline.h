@@ -36,9 +36,10 @@ struct BatchStats {
 // Who cleans + packs an input (getLineFasta / clean_dna, utils.cpp:675-718):
 //   HOST    host threads (AVX2 / AVX-512 packer) -> 2-bit words -> H2D (0.25 B per base over PCIe)
 //   DEVICE  raw text -> H2D -> ingest kernels (csrc/device/ingest.cu); the host only moves bytes
-//   AUTO    both at once on one work queue: the pack workers take inputs from the front, one upload lane takes
-//           inputs from the back and keeps two raw inputs in flight, so the split follows what the box can do
-//           (many cores per GPU: mostly HOST; few cores per GPU or short reads: mostly DEVICE)
+//   AUTO    both at once on one work queue: the workers pack inputs from the front; whenever one of them finds a
+//           copy lane idle (the PCIe link has room) it first sends an input from the back of the queue as raw
+//           text, so the split follows what the box can do (many cores per GPU: mostly HOST; few cores per GPU
+//           or short records: mostly DEVICE)
 enum class Ingest { HOST = 0, DEVICE = 1, AUTO = 2 };
 
 // Persistent worker threads (the pack phase runs every few milliseconds: no thread start-up per batch).

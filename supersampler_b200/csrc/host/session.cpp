@@ -1,8 +1,20 @@
 #include "session.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace spsp_host {
+
+static const std::chrono::steady_clock::time_point g_loaded = std::chrono::steady_clock::now();
+void trace(const char *what)
+{
+    static const bool on = getenv("SPSP_TRACE") != nullptr;
+    if (!on) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_loaded).count();
+    fprintf(stderr, "[spsp %9.1f ms] %s\n", ms, what);
+}
 
 void throw_spsp(const std::string &what) { throw std::runtime_error(what + ": " + spsp_last_error()); }
 

@@ -29,5 +29,7 @@ private:
 };
 
 [[noreturn]] void throw_spsp(const std::string &what);
+// SPSP_TRACE=1: milliseconds since the library was loaded + a label, on stderr (where a CLI run spends its time).
+void trace(const char *what);
 
 }  // namespace spsp_host

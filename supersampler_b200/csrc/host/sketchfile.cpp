@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+
+#include <zlib.h>
 
 namespace spsp_host {
 
@@ -128,19 +131,23 @@ bool decode_sketch(const uint8_t *p, size_t n, SketchElems &out, std::string *er
     return true;
 }
 
-void format_csv(const std::vector<std::string> &names, uint32_t query_size, const uint32_t *inter, uint64_t ld,
-                bool row_major_full, const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision,
-                double min_threshold, std::vector<uint8_t> &out)
+static void csv_header(const std::vector<std::string> &names, bool jaccard, std::vector<uint8_t> &out)
 {
     const uint32_t n = (uint32_t)names.size();
-    auto put = [&](const char *s, size_t l) { out.insert(out.end(), s, s + l); };
     for (uint32_t i = 0; i < n; i++) {
-        put(names[i].data(), names[i].size());
+        out.insert(out.end(), names[i].begin(), names[i].end());
         out.push_back(i + 1 == n ? '\n' : ',');
     }
     if (!jaccard) out.push_back('\n');                    // Comparator.cpp:373
+}
+
+// rows [i0, i1) of the matrix as text (Comparator.cpp:375-407, :425-459)
+static void csv_rows(uint32_t n, uint32_t i0, uint32_t i1, const uint32_t *inter, uint64_t ld, bool row_major_full,
+                     const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision, double min_threshold,
+                     std::vector<uint8_t> &out)
+{
     char tmp[64];
-    for (uint32_t i = 0; i < n && i < query_size; i++)
+    for (uint32_t i = i0; i < i1; i++)
         for (uint32_t j = 0; j < n; j++) {
             if (i == j) out.push_back('1');
             else {
@@ -151,11 +158,104 @@ void format_csv(const std::vector<std::string> &names, uint32_t query_size, cons
                 else {
                     double sc = jaccard ? (double)c / (double)(sizes[i] + sizes[j] - c) : (double)c / (double)sizes[i];
                     if (sc < min_threshold) out.push_back('0');
-                    else put(tmp, (size_t)snprintf(tmp, sizeof tmp, "%.*g", (int)precision, sc));
+                    else {
+                        const int l = snprintf(tmp, sizeof tmp, "%.*g", (int)precision, sc);
+                        out.insert(out.end(), tmp, tmp + l);
+                    }
                 }
             }
             out.push_back(j + 1 == n ? '\n' : ',');
         }
+}
+
+void format_csv(const std::vector<std::string> &names, uint32_t query_size, const uint32_t *inter, uint64_t ld,
+                bool row_major_full, const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision,
+                double min_threshold, std::vector<uint8_t> &out)
+{
+    const uint32_t n = (uint32_t)names.size();
+    csv_header(names, jaccard, out);
+    csv_rows(n, 0, std::min(n, query_size), inter, ld, row_major_full, sizes, jaccard, precision, min_threshold, out);
+}
+
+// One complete gzip member holding p[0, n).
+static bool gzip_member(const uint8_t *p, size_t n, int level, std::vector<uint8_t> &out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, (uLong)n) + 64);
+    size_t off = 0, produced = 0;
+    int rc = Z_OK;
+    do {                                                   // (avail_in is 32 bits wide)
+        const size_t piece = std::min<size_t>(n - off, (size_t)1 << 30);
+        zs.next_in = const_cast<Bytef *>(p + off);
+        zs.avail_in = (uInt)piece;
+        off += piece;
+        const int flush = off == n ? Z_FINISH : Z_NO_FLUSH;
+        do {
+            zs.next_out = out.data() + produced;
+            zs.avail_out = (uInt)std::min<size_t>(out.size() - produced, (size_t)1 << 30);
+            const size_t before = zs.avail_out;
+            rc = deflate(&zs, flush);
+            produced += before - zs.avail_out;
+            if (rc == Z_STREAM_ERROR) { deflateEnd(&zs); return false; }
+            if (produced == out.size()) out.resize(out.size() * 2);
+        } while (zs.avail_in || (flush == Z_FINISH && rc != Z_STREAM_END));
+    } while (off < n);
+    deflateEnd(&zs);
+    out.resize(produced);
+    return rc == Z_STREAM_END;
+}
+
+bool write_csv_gz(const std::string &path, const std::vector<std::string> &names, uint32_t query_size, const uint32_t *inter,
+                  uint64_t ld, bool row_major_full, const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision,
+                  double min_threshold, int threads, uint64_t *text_bytes)
+{
+    const uint32_t n = (uint32_t)names.size(), rows = std::min(n, query_size);
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    uint64_t total = 0;
+    bool ok = true;
+    auto put_member = [&](const std::vector<uint8_t> &text) {
+        std::vector<uint8_t> z;
+        if (!gzip_member(text.data(), text.size(), 1, z) || fwrite(z.data(), 1, z.size(), f) != z.size()) ok = false;
+        total += text.size();
+    };
+    {
+        std::vector<uint8_t> hdr;
+        csv_header(names, jaccard, hdr);
+        put_member(hdr);                                   // (an empty matrix still yields a valid gzip file)
+    }
+    // blocks of about 4 MB of text, `threads` of them formatted and compressed at a time, written in order: the
+    // file is a sequence of gzip members (what `zcat`, zlib's gzread and the reference's zstr all read as one
+    // stream) and host memory holds one wave of blocks, never the whole matrix as text
+    const unsigned nw = (unsigned)std::max(1, std::min(threads, 64));
+    const uint32_t per_block = (uint32_t)std::max<uint64_t>(1, ((uint64_t)4 << 20) / ((uint64_t)n * 6 + 1));
+    for (uint32_t i0 = 0; i0 < rows && ok; i0 += per_block * nw) {
+        const uint32_t blocks = std::min<uint32_t>(nw, (rows - i0 + per_block - 1) / per_block);
+        std::vector<std::vector<uint8_t>> z(blocks);
+        std::vector<uint64_t> tb(blocks, 0);
+        std::vector<char> good(blocks, 1);
+        std::vector<std::thread> pool;
+        auto work = [&](uint32_t b) {
+            std::vector<uint8_t> text;
+            const uint32_t a = i0 + b * per_block, e = std::min(rows, a + per_block);
+            text.reserve((size_t)(e - a) * n * 4);
+            csv_rows(n, a, e, inter, ld, row_major_full, sizes, jaccard, precision, min_threshold, text);
+            tb[b] = text.size();
+            if (!gzip_member(text.data(), text.size(), 1, z[b])) good[b] = 0;
+        };
+        for (uint32_t b = 1; b < blocks; b++) pool.emplace_back(work, b);
+        work(0);
+        for (auto &t : pool) t.join();
+        for (uint32_t b = 0; b < blocks && ok; b++) {
+            if (!good[b] || fwrite(z[b].data(), 1, z[b].size(), f) != z[b].size()) ok = false;
+            total += tb[b];
+        }
+    }
+    if (fclose(f) != 0) ok = false;
+    if (text_bytes) *text_bytes = total;
+    return ok;
 }
 
 }  // namespace spsp_host

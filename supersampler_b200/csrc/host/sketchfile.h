@@ -25,5 +25,11 @@ bool decode_sketch(const uint8_t *p, size_t n, SketchElems &out, std::string *er
 void format_csv(const std::vector<std::string> &names, uint32_t query_size, const uint32_t *inter, uint64_t ld,
                 bool row_major_full, const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision,
                 double min_threshold, std::vector<uint8_t> &out);
+// The same text streamed into a gzip file: row blocks are formatted and compressed by `threads` workers and written
+// in order as consecutive gzip members, so memory holds one wave of blocks instead of the whole matrix as text
+// (10^4 sketches all-vs-all are ~10^8 cells).  text_bytes (may be null) = size of the CSV before compression.
+bool write_csv_gz(const std::string &path, const std::vector<std::string> &names, uint32_t query_size, const uint32_t *inter,
+                  uint64_t ld, bool row_major_full, const std::vector<uint64_t> &sizes, bool jaccard, unsigned precision,
+                  double min_threshold, int threads, uint64_t *text_bytes);
 
 }  // namespace spsp_host

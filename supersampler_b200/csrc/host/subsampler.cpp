@@ -97,9 +97,11 @@ void Subsampler::parse_fasta_test(const std::string &input_file, const std::stri
         return;
     }
     t_pack = secs(t0, clk::now());
+    trace("input packed");
     subsampled_file = get_out_name(input_file, output_prefix) + ".gz";
     std::vector<uint8_t> sketch;
     sketch_packed(sketch);
+    trace("scan + post-pass done");
     auto t1 = clk::now();
     if (!write_gz(subsampled_file, sketch.data(), sketch.size(), gzip_level))
         std::cout << "Can't write file: " << subsampled_file << std::endl;
@@ -212,16 +214,22 @@ int sub_sampler_main(int argc, char **argv)
     std::cout << "Maximal super kmer are of length " << 2 * k - m1 << " or " << k - m1 + 1 << " kmers" << std::endl;
     if (c < 1) c = 1;
     if (gpus < 1) gpus = 1;
+    // a process that uses one GPU need not enumerate the others (driver start-up grows with the number of devices)
+    if (gpus == 1) setenv("CUDA_VISIBLE_DEVICES", "0", 0);
     try {
         int ndev = 0;
+        trace("main: arguments parsed");
         if (spsp_device_count(&ndev) != 0 || ndev == 0) throw std::runtime_error("no CUDA device available");
+        trace("device count (driver initialised)");
         if ((int)gpus > ndev) gpus = (unsigned)ndev;
         const uint64_t thr = compute_threshold((int)k, (int)m1, s);
         if (!input.empty()) {
             auto session = std::make_shared<DeviceSession>(0, (int)k, (int)m1, thr, 1);
+            trace("device context created");
             Subsampler ss(k, m1, s, c, type, abundance, session, 0);
             ss.want_dense_stats = verbose;
             ss.parse_fasta_test(input, output);
+            trace("sketch written");
             if (verbose) ss.print_stat();
             return 0;
         }
@@ -256,6 +264,7 @@ int sub_sampler_main(int argc, char **argv)
                 for (size_t i = g; i < files.size(); i += gpus) mine.push_back(i);
                 if (mine.empty()) return;
                 auto session = std::make_shared<DeviceSession>((int)g, (int)k, (int)m1, thr, 1);
+                trace("device context created");
                 BatchSketcher bs(session, (int)k, (int)m1, s, abundance, (int)per_gpu);
                 bs.dense_stats = verbose;
                 std::vector<BatchSource> src(mine.size());
@@ -263,6 +272,7 @@ int sub_sampler_main(int argc, char **argv)
                 std::vector<std::vector<uint8_t>> sk;
                 std::vector<char> ok;
                 bs.run(src, sk, ok);
+                trace("batches sketched");
                 parallel_for((int)per_gpu, mine.size(), [&](size_t j) {
                     const std::string &f = files[mine[j]];
                     if (!ok[j]) {
@@ -309,6 +319,7 @@ int sub_sampler_main(int argc, char **argv)
         for (unsigned g = 1; g < gpus; g++) pool.emplace_back(gpu_work, g);
         gpu_work(0);
         for (auto &t : pool) t.join();
+        trace("sketch files written");
         for (const auto &e : errors)
             if (!e.empty()) throw std::runtime_error(e);
     } catch (const std::exception &e) {

@@ -1,5 +1,5 @@
 #!/bin/bash
-# e2e with the three ingest modes, all cores and 4 cores (what a rank of an 8-GPU job gets on a 32-core box)
+# e2e with the ingest modes, all cores and 4 cores (what a rank of an 8-GPU job gets on a 32-core box)
 run() {
   tag=$1; shift
   "$@" > gpurun_out/ing_$tag.json 2> gpurun_out/ing_$tag.err
@@ -16,9 +16,7 @@ PY
 }
 nproc
 B="python bench.py --steps 20 --warmup 5 --extras= --no-cpu-baseline"
-run host $B --ingest host
-run auto $B --ingest auto
-run device $B --ingest device
-run c4_host taskset -c 0-3 $B --threads 4 --ingest host
-run c4_auto taskset -c 0-3 $B --threads 4 --ingest auto
-run c4_device taskset -c 0-3 $B --threads 4 --ingest device
+for mode in ${MODES:-host auto}; do
+  run $mode $B --ingest $mode
+  run c4_$mode taskset -c 0-3 $B --threads 4 --ingest $mode
+done
