@@ -809,7 +809,7 @@ def b200_arm(args, rank, world, local_rank):
                 stats["hits"] = info["n_hits"]
                 stats["launches"] += nl + cinfo.get("launches", 0)
                 stats["sketch_s"].append(t_sk); stats["compare_s"].append(cinfo["seconds"])
-                stats["d2h"] = sum(len(x) for x in sks) + (res[0].size * 4 if res[0] is not None else 0)
+                stats["d2h"] = sks.nbytes + (res[0].size * 4 if res[0] is not None else 0)
             return sks, res
 
         def step(self, i, record):
@@ -939,10 +939,10 @@ def b200_arm(args, rank, world, local_rank):
         wd = wd_box[0]
         try:
             my_paths = write_files(fastas, names, wd)
-            all_sks, all_names = [sks_res], [names]
+            all_sks, all_names = [list(sks_res)], [names]
             if dist is not None:
                 all_sks, all_names = [None] * world, [None] * world
-                dist.all_gather_object(all_sks, sks_res)
+                dist.all_gather_object(all_sks, list(sks_res))
                 dist.all_gather_object(all_names, names)
                 barrier()
             if rank == 0:

@@ -201,8 +201,9 @@ int spsp_sketch_batch_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const ui
  *
  *   reserve : device text buffer of text_bytes (grow-only; synchronises when it grows)
  *   upload  : async H2D of a slice of text to byte offset byte_off (host_text
- *             pinned for true overlap; callable from any thread) on copy lane
- *             `lane` (0 / 1; < 0: the lanes alternate)
+ *             pinned for true overlap; callable from any thread) on text lane
+ *             `lane` (0 / 1; < 0: the lanes alternate).  Text has two copy streams
+ *             of its own, beside the two that carry packed words.
  *   pack    : for n_text inputs -- text [text_off[i], +text_len[i]) (text_off a
  *             multiple of 16), region of the staged batch buffer starting at
  *             word word_off[i] (spsp_batch_reserve'd, spsp_packed_words(text_len[i])
@@ -216,10 +217,10 @@ int spsp_sketch_batch_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const ui
 int spsp_batch_text_reserve(spsp_ctx *ctx, int slot, uint64_t text_bytes);
 int spsp_batch_text_upload(spsp_ctx *ctx, int slot, int lane, uint64_t byte_off, const uint8_t *host_text,
                            uint64_t n_bytes);
-/* Waits until the copies queued on copy lane `lane` (0 / 1; < 0: both) have finished: lets a caller keep a
- * bounded number of uploads in flight. */
+/* Waits until the copies queued on text lane `lane` (0 / 1; < 0: both) have finished: lets a caller keep a
+ * bounded number of text uploads in flight. */
 int spsp_batch_upload_wait(spsp_ctx *ctx, int slot, int lane);
-/* *idle = 1 when nothing is queued or running on copy lane `lane` (0 / 1): the PCIe link has room for more. */
+/* *idle = 1 when nothing is queued or running on text lane `lane` (0 / 1): the previous raw input has arrived. */
 int spsp_batch_upload_idle(spsp_ctx *ctx, int slot, int lane, int *idle);
 int spsp_batch_text_pack(spsp_ctx *ctx, int slot, uint32_t n_text, const uint64_t *text_off, const uint64_t *text_len,
                          const uint64_t *word_off, const uint32_t *input_index, uint64_t *n_bases_out,

@@ -84,6 +84,10 @@ struct Slot {
     // staged uploads alternate between two copy streams: one copy engine moves ~27 GB/s on this platform, two 55
     cudaStream_t up_stream[2] = {nullptr, nullptr};
     cudaEvent_t up_event[2] = {nullptr, nullptr};
+    // raw FASTA text (device-side ingest) travels on two streams of its own: its long copies must not hold back the
+    // short packed pieces queued behind them, and "lane idle" then means "the previous raw input has arrived"
+    cudaStream_t raw_stream[2] = {nullptr, nullptr};
+    cudaEvent_t raw_event[2] = {nullptr, nullptr};
     PostpassBuffers *pp = nullptr;
     DenseBuffers *dn = nullptr;
     DevBuf b_rec_begin, b_rec_end, b_rec_input;
@@ -297,6 +301,8 @@ extern "C" int spsp_create(int device, int k, int m, uint64_t threshold, int n_s
         for (int u = 0; u < 2; u++) {
             CK(cudaStreamCreateWithFlags(&s.up_stream[u], cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&s.up_event[u], cudaEventDisableTiming));
+            CK(cudaStreamCreateWithFlags(&s.raw_stream[u], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s.raw_event[u], cudaEventDisableTiming));
         }
     }
     CK(cudaEventCreate(&c->cev0));
@@ -333,6 +339,8 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         for (int u = 0; u < 2; u++) {
             if (s.up_stream[u]) { cudaStreamSynchronize(s.up_stream[u]); cudaStreamDestroy(s.up_stream[u]); }
             if (s.up_event[u]) cudaEventDestroy(s.up_event[u]);
+            if (s.raw_stream[u]) { cudaStreamSynchronize(s.raw_stream[u]); cudaStreamDestroy(s.raw_stream[u]); }
+            if (s.raw_event[u]) cudaEventDestroy(s.raw_event[u]);
         }
         if (s.pp) postpass_buffers_destroy(s.pp);
         if (s.dn) dense_buffers_destroy(s.dn);
@@ -885,7 +893,7 @@ extern "C" int spsp_batch_text_reserve(spsp_ctx *c, int slot, uint64_t text_byte
     Slot &s = c->slots[slot];
     if (text_bytes + 64 <= s.b_text.cap) return 0;
     CK(cudaStreamSynchronize(s.stream));          // nothing may still read the old buffer
-    for (int u = 0; u < 2; u++) CK(cudaStreamSynchronize(s.up_stream[u]));
+    for (int u = 0; u < 2; u++) CK(cudaStreamSynchronize(s.raw_stream[u]));
     CK(s.b_text.ensure(text_bytes + 64));
     return 0;
 }
@@ -900,7 +908,7 @@ extern "C" int spsp_batch_text_upload(spsp_ctx *c, int slot, int lane, uint64_t 
     if (!host_text) return fail(-3, "spsp_batch_text_upload: null input");
     CK(cudaSetDevice(c->device));
     // lane < 0: alternate between the two copy streams (callable from any thread)
-    cudaStream_t up = s.up_stream[lane >= 0 ? lane : (int)(__atomic_fetch_add(&s.text_rr, 1u, __ATOMIC_RELAXED) & 1u)];
+    cudaStream_t up = s.raw_stream[lane >= 0 ? lane : (int)(__atomic_fetch_add(&s.text_rr, 1u, __ATOMIC_RELAXED) & 1u)];
     CK(cudaMemcpyAsync(static_cast<uint8_t *>(s.b_text.p) + byte_off, host_text, n_bytes, cudaMemcpyHostToDevice, up));
     return 0;
 }
@@ -909,7 +917,7 @@ extern "C" int spsp_batch_upload_idle(spsp_ctx *c, int slot, int lane, int *idle
 {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || lane < 0 || lane > 1 || !idle)
         return fail(-3, "spsp_batch_upload_idle: bad ctx/slot/lane");
-    const cudaError_t e = cudaStreamQuery(c->slots[slot].up_stream[lane]);
+    const cudaError_t e = cudaStreamQuery(c->slots[slot].raw_stream[lane]);
     if (e != cudaSuccess && e != cudaErrorNotReady) return fail(-1, std::string("cudaStreamQuery: ") + cudaGetErrorString(e));
     *idle = e == cudaSuccess ? 1 : 0;
     return 0;
@@ -921,7 +929,7 @@ extern "C" int spsp_batch_upload_wait(spsp_ctx *c, int slot, int lane)
     Slot &s = c->slots[slot];
     CK(cudaSetDevice(c->device));
     for (int u = 0; u < 2; u++)
-        if (lane < 0 || lane == u) CK(cudaStreamSynchronize(s.up_stream[u]));
+        if (lane < 0 || lane == u) CK(cudaStreamSynchronize(s.raw_stream[u]));
     return 0;
 }
 
@@ -956,9 +964,9 @@ extern "C" int spsp_batch_text_pack(spsp_ctx *c, int slot, uint32_t n_text, cons
     }
     CK(s.b_ing_in.ensure(in_bytes)); CK(s.b_ing_tot.ensure(tot_bytes)); CK(s.b_ing_grand.ensure(16));
     CK(s.b_ing_tiles.ensure((n_tiles + 1) * sizeof(IngestTile))); CK(s.b_ing_carry.ensure((n_tiles + 1) * sizeof(IngestCarry)));
-    for (int u = 0; u < 2; u++) {                 // the kernels wait for every upload queued so far
-        CK(cudaEventRecord(s.up_event[u], s.up_stream[u]));
-        CK(cudaStreamWaitEvent(st, s.up_event[u], 0));
+    for (int u = 0; u < 2; u++) {                 // the kernels wait for every text upload queued so far
+        CK(cudaEventRecord(s.raw_event[u], s.raw_stream[u]));
+        CK(cudaStreamWaitEvent(st, s.raw_event[u], 0));
     }
     const IngestInput *d_in = static_cast<const IngestInput *>(s.b_ing_in.p);
     IngestTotals *d_tot = static_cast<IngestTotals *>(s.b_ing_tot.p);

@@ -292,7 +292,12 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
     const size_t nb = last - first;
     dbg_no_upload_ = getenv("SPSP_PIPE_NO_UPLOAD") != nullptr;      // measurement aid: pack only (results are garbage)
     auto t0 = clk::now();
-    const Ingest mode = dense_stats ? Ingest::HOST : ingest;   // the dense totals take host record tables
+    // AUTO with many pack workers is HOST: measured on B200 boxes, 16 workers already run into the host's memory
+    // bandwidth and raw text then only competes for the PCIe link (96.7 vs 95.3 Gbp/s); with 4 workers per GPU
+    // (8 GPUs on a 32-core box) the mixed queue takes 33 to 63 Gbp/s.  SPSP_AUTO_MAX_WORKERS moves the switch.
+    static const int auto_max_workers = getenv("SPSP_AUTO_MAX_WORKERS") ? atoi(getenv("SPSP_AUTO_MAX_WORKERS")) : 11;
+    Ingest mode = dense_stats ? Ingest::HOST : ingest;         // the dense totals take host record tables
+    if (mode == Ingest::AUTO && pool_.size() > auto_max_workers) mode = Ingest::HOST;
     uint64_t total_words = 0, total_text = 0, file_text = 0;
     for (size_t i = first; i < last; i++) {
         Prepared &p = prep[i];

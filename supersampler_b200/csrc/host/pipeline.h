@@ -37,9 +37,10 @@ struct BatchStats {
 //   HOST    host threads (AVX2 / AVX-512 packer) -> 2-bit words -> H2D (0.25 B per base over PCIe)
 //   DEVICE  raw text -> H2D -> ingest kernels (csrc/device/ingest.cu); the host only moves bytes
 //   AUTO    both at once on one work queue: the workers pack inputs from the front; whenever one of them finds a
-//           copy lane idle (the PCIe link has room) it first sends an input from the back of the queue as raw
-//           text, so the split follows what the box can do (many cores per GPU: mostly HOST; few cores per GPU
-//           or short records: mostly DEVICE)
+//           text lane idle (the previous raw input has arrived) it first sends an input from the back of the
+//           queue as raw text, so the split follows what the box can do (few cores per GPU: about half of the
+//           inputs go over as text).  With more than 11 workers AUTO is HOST: the host lane then runs into the
+//           host's memory bandwidth and raw text only competes for the PCIe link (measured, see pipeline.cpp)
 enum class Ingest { HOST = 0, DEVICE = 1, AUTO = 2 };
 
 // Persistent worker threads (the pack phase runs every few milliseconds: no thread start-up per batch).

@@ -267,3 +267,16 @@ def test_streamed_csv_equals_in_memory_csv(tmp_path):
             with gzip.open(p, "rb") as f:
                 got = f.read()
             assert got == want and nbytes == len(want), (n, q, jac)
+
+
+def test_batch_sketches_sequence():
+    """The lazy per-batch sketch list assembles header line + body on access and compares like a list."""
+    from supersampler_b200.capi import BatchSketches
+    body = b"AAAABBBCC"
+    bs = BatchSketches(body, np.array([0, 4, 4, 7, 9], np.uint64), np.array([5, 0, 7, 9], np.uint64), "51 11 ", " 1000.000000\n")
+    want = [b"51 11 5 1000.000000\nAAAA", b"51 11 0 1000.000000\n", b"51 11 7 1000.000000\nBBB", b"51 11 9 1000.000000\nCC"]
+    assert len(bs) == 4 and list(bs) == want and bs == want and want == list(bs)
+    assert bs[-1] == want[-1] and bs[1:3] == want[1:3] and [] + bs == want
+    assert not (bs == want[:3]) and bs.nbytes == len(body) + 5 * 8 + 4 * 8
+    with pytest.raises(IndexError):
+        bs[4]
