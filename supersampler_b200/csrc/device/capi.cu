@@ -37,12 +37,18 @@ static int fail(int code, const std::string &msg)
 
 // Grow-only device / pinned buffers: steady-state calls never hit cudaMalloc / cudaFree
 // (both serialise against the whole device and against driver queries).
+static void trace_alloc(const char *what, size_t from, size_t to)
+{
+    static const bool on = getenv("SPSP_TRACE_ALLOC") != nullptr;
+    if (on) fprintf(stderr, "[alloc] %s buffer %zu -> %zu bytes\n", what, from, to);
+}
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        trace_alloc("device", cap, bytes);
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 256;
@@ -58,6 +64,7 @@ struct PinBuf {
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        trace_alloc("pinned", cap, bytes);
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 256;

@@ -1323,12 +1323,18 @@ __global__ void pp_iota_kernel(uint32_t *__restrict__ v, uint64_t n)
 
 // ---------------------------------------------------------------- driver
 
+static void trace_alloc(const char *what, size_t from, size_t to)
+{
+    static const bool on = getenv("SPSP_TRACE_ALLOC") != nullptr;
+    if (on) fprintf(stderr, "[alloc] post-pass %s buffer %zu -> %zu bytes\n", what, from, to);
+}
 struct DBuf {
     void *p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        trace_alloc("device", cap, bytes);
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 4096;
@@ -1344,9 +1350,10 @@ struct HBuf {
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        trace_alloc("pinned", cap, bytes);
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 4096;
+        size_t want = bytes + bytes / 2 + 4096;              // pinned memory is slow to allocate: grow in big steps
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -1556,6 +1563,9 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     PP_CK(b->h_small.ensure(small_bytes + 8));
     PP_CK(b->h_off.ensure((nin + 1) * 8 * 2));
     uint64_t pred = b->last_body_bytes ? std::min<uint64_t>(body_cap, b->last_body_bytes + b->last_body_bytes / 4 + 4096) : 0;
+    // the guess must not regrow pinned memory by a few bytes (cudaHostAlloc of 13 MB was measured at 16 ms, five
+    // times the whole pass): a buffer that holds the previous batch with some room is copied as far as it goes
+    if (pred > b->h_body.cap && b->h_body.cap >= b->last_body_bytes + b->last_body_bytes / 16) pred = b->h_body.cap;
     if (pred) PP_CK(b->h_body.ensure(pred));
     uint8_t *hs = b->h_small.as<uint8_t>();
     PP_CK(cudaMemcpyAsync(hs, ar.base, small_bytes, cudaMemcpyDeviceToHost, st));
@@ -1581,6 +1591,10 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     const uint64_t n_hits = *reinterpret_cast<const uint64_t *>(hs + small_bytes);
     out->n_hits = n_hits;
     out->kernels_launched = launched;
+    static const bool trace_retry = getenv("SPSP_TRACE_ALLOC") != nullptr;
+    if (trace_retry && (n_hits > H || hc.overflow))
+        fprintf(stderr, "[alloc] post-pass retry: hits %llu / cap %llu, overflow bits %u (pieces %llu body %llu big %llu)\n",
+                (unsigned long long)n_hits, (unsigned long long)H, hc.overflow, hc.n_pieces, hc.body_bytes, hc.big_top);
     if (n_hits > H) { out->retry = PP_RETRY_HITS; return cudaSuccess; }      // the caller grows the hit buffer and rescans
     if (hc.overflow) {
         if (hc.overflow & OVF_PIECES) b->pieces_cap_min = hc.n_pieces + hc.n_pieces / 8 + 1024;
