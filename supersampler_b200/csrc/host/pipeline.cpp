@@ -128,6 +128,26 @@ void WorkerPool::run(size_t n, const std::function<void(size_t)> &fn)
     if (!p.error.empty()) throw std::runtime_error(p.error);
 }
 
+// Two pinned chunks per worker thread for text read from files (device-side ingest).
+namespace {
+struct TextRing {
+    uint8_t *buf[2] = {nullptr, nullptr};
+    size_t cap = 0;
+    void ensure(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        for (auto &b : buf) {
+            if (b) spsp_host_free(b);
+            void *v = nullptr;
+            if (spsp_host_alloc(&v, bytes) != 0) throw_spsp("spsp_host_alloc");
+            b = static_cast<uint8_t *>(v);
+        }
+        cap = bytes;
+    }
+    ~TextRing() { for (auto &b : buf) if (b) spsp_host_free(b); }
+};
+}  // namespace
+
 struct BatchSketcher::Prepared {
     uint64_t len = 0;                  // upper bound of the number of bases (= text bytes)
     bool ok = true, from_file = false, gz = false;
@@ -138,7 +158,6 @@ struct BatchSketcher::Prepared {
     // device-side ingest
     bool raw = false;                  // went to the device as text
     uint64_t text_off = 0;             // where in the device text buffer (multiple of 16)
-    uint64_t file_off = 0;             // files: where in the pinned text staging
 };
 
 struct BatchSketcher::Job {
@@ -162,7 +181,6 @@ BatchSketcher::BatchSketcher(std::shared_ptr<DeviceSession> session, int k, int 
 BatchSketcher::~BatchSketcher()
 {
     if (stage_) spsp_host_free(stage_);
-    if (tstage_) spsp_host_free(tstage_);
 }
 
 static bool file_is_gzip(int fd)
@@ -298,7 +316,7 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
     static const int auto_max_workers = getenv("SPSP_AUTO_MAX_WORKERS") ? atoi(getenv("SPSP_AUTO_MAX_WORKERS")) : 11;
     Ingest mode = dense_stats ? Ingest::HOST : ingest;         // the dense totals take host record tables
     if (mode == Ingest::AUTO && pool_.size() > auto_max_workers) mode = Ingest::HOST;
-    uint64_t total_words = 0, total_text = 0, file_text = 0;
+    uint64_t total_words = 0, total_text = 0;
     for (size_t i = first; i < last; i++) {
         Prepared &p = prep[i];
         p.word_off = total_words;
@@ -307,8 +325,7 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
         p.text_off = total_text;
         if (p.ok) {
             total_text += (p.len + 15) & ~(uint64_t)15;
-            p.file_off = file_text;
-            if (p.from_file) file_text += (p.len + 15) & ~(uint64_t)15;
+
         }
     }
     const uint64_t n_total = 16 * total_words;               // one scan covers every region
@@ -325,16 +342,6 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
     if (spsp_batch_reserve(ctx, 0, need_words) != 0) throw_spsp("spsp_batch_reserve");
     if (mode != Ingest::HOST) {
         if (spsp_batch_text_reserve(ctx, 0, total_text) != 0) throw_spsp("spsp_batch_text_reserve");
-        // text read from files passes through pinned memory (sources in memory are copied from where they are)
-        if (file_text > tstage_bytes_) {
-            if (tstage_) spsp_host_free(tstage_);
-            tstage_ = nullptr; tstage_bytes_ = 0;
-            void *v = nullptr;
-            const uint64_t cap = file_text + file_text / 8 + 64;
-            if (spsp_host_alloc(&v, cap) != 0) throw_spsp("spsp_host_alloc");
-            tstage_ = static_cast<uint8_t *>(v);
-            tstage_bytes_ = cap;
-        }
     }
 
     // AUTO: called by the pack workers between slices -- a copy lane with nothing queued means the link has room:
@@ -413,6 +420,30 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
         in.words.detach();
         std::vector<uint8_t>().swap(p.text);
     };
+    // ---- device lane, text in a file: bytes [off0, off0 + len0) pass through two pinned chunks of this worker, one
+    // per text lane; chunk c is refilled once the copies queued on its lane have left (no staging buffer of the
+    // size of the file: pinned memory is slow to allocate, 13 MB were measured at 16 ms).  Pieces of one file are
+    // independent (the device needs no sequential state from the host), so a large file is read by many workers.
+    auto send_file_piece = [&](size_t j, uint64_t off0, uint64_t len0) {
+        Prepared &p = prep[first + j];
+        const size_t SLICE = 4u << 20;
+        int fd = open(src[first + j].path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot reopen " + src[first + j].path);
+        static thread_local TextRing ring;
+        ring.ensure(SLICE);
+        uint64_t got = 0;
+        for (int c = 0; got < len0; c ^= 1) {
+            if (spsp_batch_upload_wait(ctx, 0, c) != 0) { close(fd); throw_spsp("spsp_batch_upload_wait"); }
+            const ssize_t r = pread(fd, ring.buf[c], (size_t)std::min<uint64_t>(SLICE, len0 - got), (off_t)(off0 + got));
+            if (r <= 0) { close(fd); throw std::runtime_error(src[first + j].path + " changed while it was read"); }
+            if (spsp_batch_text_upload(ctx, 0, c, p.text_off + off0 + got, ring.buf[c], (uint64_t)r) != 0) {
+                close(fd);
+                throw_spsp("spsp_batch_text_upload");
+            }
+            got += (uint64_t)r;
+        }
+        close(fd);
+    };
     // ---- device lane: the raw text of one input goes to the device text buffer (copy lane `lane`)
     auto send_input = [&](size_t j, int lane) {
         Prepared &p = prep[first + j];
@@ -431,26 +462,30 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
             }
             return;
         }
-        int fd = open(sc.path.c_str(), O_RDONLY);
-        if (fd < 0) throw std::runtime_error("cannot reopen " + sc.path);
-        uint8_t *dst = tstage_ + p.file_off;
-        uint64_t got = 0;
-        while (got < p.len) {
-            ssize_t r = read(fd, dst + got, (size_t)std::min<uint64_t>(SLICE, p.len - got));
-            if (r <= 0) break;
-            if (spsp_batch_text_upload(ctx, 0, lane, p.text_off + got, dst + got, (uint64_t)r) != 0)
-                throw_spsp("spsp_batch_text_upload");
-            got += (uint64_t)r;
-        }
-        close(fd);
-        p.len = got;                                         // (a file that shrank since it was measured)
+        send_file_piece(j, 0, p.len);
     };
 
     send_input_fn = send_input;
     if (mode == Ingest::HOST) {
         pool_.run(nb, pack_input);
     } else if (mode == Ingest::DEVICE) {
-        pool_.run(nb, [&](size_t j) { send_input(j, -1); });
+        // work items: inputs in memory as they are, files in pieces of 32 MB
+        struct Item { size_t j; uint64_t off, len; bool file; };
+        std::vector<Item> items;
+        const uint64_t PIECE = 32u << 20;
+        for (size_t j = 0; j < nb; j++) {
+            Prepared &p = prep[first + j];
+            if (p.ok && p.from_file && p.len) {
+                p.raw = true;
+                for (uint64_t off = 0; off < p.len; off += PIECE) items.push_back({j, off, std::min(PIECE, p.len - off), true});
+            } else {
+                items.push_back({j, 0, 0, false});
+            }
+        }
+        pool_.run(items.size(), [&](size_t i) {
+            if (items[i].file) send_file_piece(items[i].j, items[i].off, items[i].len);
+            else send_input(items[i].j, -1);
+        });
     } else {
         // one queue, two ends: every worker packs inputs from the front; raw sends take inputs from the back
         pool_.run((size_t)std::max(1, pool_.size()), [&](size_t) {

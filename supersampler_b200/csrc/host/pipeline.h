@@ -114,8 +114,6 @@ private:
     bool dbg_no_upload_ = false;
     uint32_t *stage_ = nullptr;                // pinned staging buffer (grow-only)
     uint64_t stage_words_ = 0;
-    uint8_t *tstage_ = nullptr;                // pinned staging of raw text read from files (grow-only)
-    uint64_t tstage_bytes_ = 0;
     // elements of the last run
     bool elems_on_device_ = false;
     uint32_t n_last_ = 0;

@@ -244,3 +244,58 @@ def allgather_compare(sketches: Sequence[bytes], k: int, m: int, rank: int, worl
     dist.reduce(d_out, dst=0, op=dist.ReduceOp.SUM)
     inter = d_out.cpu().numpy().view(np.uint32).reshape(n, n)
     return inter, all_sizes.astype(np.uint64), False
+
+
+def _parse_cpulist(txt: str) -> List[int]:
+    out: List[int] = []
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_rank_to_gpu_cores(local_rank: int, local_world: int, pci_bus_ids: Optional[Sequence[str]] = None) -> dict:
+    """One process per GPU on a multi-socket box: confine this rank (and every thread it starts: pack workers,
+    pinned allocations by first touch) to its share of the cores that are LOCAL to its GPU (sysfs `local_cpulist`
+    of the GPU's PCI device = the NUMA node behind its root complex), split evenly among the ranks whose GPUs sit
+    on the same node.  Without it the ranks' packers read text and write pinned memory across the socket link.
+    Returns what it did (for the bench line); a no-op when the topology cannot be read."""
+    import os
+    info = {"bound": False}
+    try:
+        if pci_bus_ids is None:
+            import subprocess
+            q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE,
+                               stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.split()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                q = [q[int(x)] for x in vis.split(",") if x.strip().isdigit() and int(x) < len(q)]
+            pci_bus_ids = q
+        if len(pci_bus_ids) < local_world:
+            return info
+        allowed = sorted(os.sched_getaffinity(0))
+
+        def local_cpus(bus_id: str) -> List[int]:
+            b = bus_id.lower()
+            if b.count(":") == 2 and len(b.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit domain
+                b = b[4:]
+            with open(f"/sys/bus/pci/devices/{b}/local_cpulist") as f:
+                cpus = [c for c in _parse_cpulist(f.read()) if c in allowed]
+            return cpus or allowed
+
+        sets = [tuple(local_cpus(pci_bus_ids[r])) for r in range(local_world)]
+        mine = sets[local_rank]
+        peers = [r for r in range(local_world) if sets[r] == mine]            # ranks that share my node
+        share = len(mine) // len(peers)
+        if share < 1:
+            return info
+        j = peers.index(local_rank)
+        cpus = list(mine[j * share:(j + 1) * share])
+        os.sched_setaffinity(0, cpus)
+        info.update(bound=True, cpus=f"{cpus[0]}-{cpus[-1]}" if cpus == list(range(cpus[0], cpus[-1] + 1)) else cpus,
+                    n_cpus=len(cpus), ranks_on_node=len(peers), node_cpus=len(mine))
+    except Exception as ex:                      # topology not readable: stay unbound
+        info["error"] = f"{type(ex).__name__}: {ex}"
+    return info

@@ -280,3 +280,12 @@ def test_batch_sketches_sequence():
     assert not (bs == want[:3]) and bs.nbytes == len(body) + 5 * 8 + 4 * 8
     with pytest.raises(IndexError):
         bs[4]
+
+
+def test_cpulist_and_numa_binding_is_safe():
+    from supersampler_b200 import distributed as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert D._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    info = D.bind_rank_to_gpu_cores(0, 2, ["00000000:FF:1F.7", "00000000:FE:1F.7"])      # no such devices: must stay unbound
+    assert info["bound"] is False and os.sched_getaffinity(0) == before
