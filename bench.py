@@ -65,14 +65,14 @@ def log(*a):
 
 def measured_traffic(bases_per_launch):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(p) as f:
-            t = json.load(f)
-        if abs(bases_per_launch - 320012288) < 1e6:
-            return t["traffic_bytes_per_launch"], t["source"], t.get("pipes_pct_of_peak")
-    except Exception:
-        pass
+    for nm in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", nm)) as f:
+                t = json.load(f)
+            if abs(bases_per_launch - 320012288) < 1e6:
+                return t["traffic_bytes_per_launch"], t["source"], t.get("pipes_pct_of_peak")
+        except Exception:
+            continue
     return None, None, None
 
 

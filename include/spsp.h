@@ -225,6 +225,9 @@ int spsp_batch_upload_idle(spsp_ctx *ctx, int slot, int lane, int *idle);
 int spsp_batch_text_pack(spsp_ctx *ctx, int slot, uint32_t n_text, const uint64_t *text_off, const uint64_t *text_len,
                          const uint64_t *word_off, const uint32_t *input_index, uint64_t *n_bases_out,
                          uint64_t *n_rec_out);
+/* k-mers of every input of the batch just sketched on the slot (sum over its records of at least k bases of
+ * length - k + 1: read_kmer, SubSampler.cpp:343-347), from the record table the device used. */
+int spsp_batch_record_kmers(spsp_ctx *ctx, int slot, uint32_t n_inputs, uint64_t *kmers_out);
 /* CUDA-event time of the last pack's kernels (milliseconds). */
 int spsp_batch_text_last_ms(spsp_ctx *ctx, int slot, float *ms);
 /* Diagnostics / tests: the record table the last pack left on the slot (cap
@@ -261,7 +264,8 @@ int spsp_dense_stats_device(spsp_ctx *ctx, int slot, const uint32_t *d_packed, u
                             const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input,
                             uint64_t n_rec, uint32_t n_inputs, uint64_t *total_superkmers, uint64_t *selected_kmers,
                             float *kernel_ms);
-/* On what spsp_batch_upload staged on the slot (the batch just sketched). */
+/* On what spsp_batch_upload staged on the slot (the batch just sketched).  rec_begin == NULL with n_rec == 0:
+ * the record table of that batch as the device saw it (host-packed, ingested on the device, or both merged). */
 int spsp_dense_stats_staged(spsp_ctx *ctx, int slot, uint64_t n_bases, const uint64_t *rec_begin,
                             const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
                             uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms);

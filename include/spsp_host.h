@@ -116,9 +116,11 @@ int spsph_pipeline_destroy(spsph_pipeline *p);
 spsp_ctx *spsph_pipeline_ctx(spsph_pipeline *p);
 /* Upper bound of one device batch in bases (default 2^30); larger jobs run as several batches. */
 int spsph_pipeline_set_max_batch_bases(spsph_pipeline *p, uint64_t bases);
-/* Who cleans + packs the inputs (csrc/host/pipeline.h, enum Ingest): 0 = host threads (default, or what the
- * environment variable SPSP_INGEST = host|device|auto names), 1 = the device (raw text over PCIe, ingest kernels),
- * 2 = both on one work queue (pack workers from the front, one upload lane from the back).  In modes 1 / 2 text
+/* Who cleans + packs the inputs (csrc/host/pipeline.h, enum Ingest): 0 = host threads, 1 = the device (raw text
+ * over PCIe, ingest kernels), 2 = both (the default, or what the environment variable SPSP_INGEST =
+ * host|device|auto names): inputs that look like read sets go over as text, the others are packed by the workers,
+ * which -- when there are few of them -- also send inputs from the back of the queue as text whenever a text
+ * lane is idle.  In modes 1 / 2 text
  * held in PINNED memory is copied asynchronously and must stay valid until the job's device half has run
  * (spsph_pipeline_sketch / _finish returned); pageable text is staged by the copy call itself. */
 int spsph_pipeline_set_ingest(spsph_pipeline *p, int mode);

@@ -107,6 +107,11 @@ struct Slot {
     DevBuf m_rec_begin, m_rec_end, m_rec_input;      // ... merged with the host-packed inputs' records
     PinBuf p_ing;
     uint64_t n_trec = 0;
+    // record table of the last staged batch as the device saw it (host-packed, ingested or merged)
+    const uint64_t *last_rb = nullptr, *last_re = nullptr;
+    const uint32_t *last_ri = nullptr;
+    uint64_t last_nrec = 0;
+    DevBuf b_kmers;
     uint32_t text_rr = 0;
     cudaEvent_t ing0 = nullptr, ing1 = nullptr;
     bool ing_timed = false;
@@ -354,7 +359,7 @@ extern "C" int spsp_destroy(spsp_ctx *c)
         s.b_rec_begin.release(); s.b_rec_end.release(); s.b_rec_input.release();
         s.b_text.release(); s.b_ing_in.release(); s.b_ing_tiles.release(); s.b_ing_carry.release(); s.b_ing_tot.release();
         s.b_ing_grand.release(); s.t_rec_begin.release(); s.t_rec_end.release(); s.t_rec_input.release();
-        s.m_rec_begin.release(); s.m_rec_end.release(); s.m_rec_input.release(); s.p_ing.release();
+        s.m_rec_begin.release(); s.m_rec_end.release(); s.m_rec_input.release(); s.p_ing.release(); s.b_kmers.release();
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     free_cmp(c);
@@ -865,7 +870,10 @@ extern "C" int spsp_sketch_batch_staged(spsp_ctx *c, int slot, uint64_t n_bases,
         s.n_trec = 0;
         const uint64_t *tb = static_cast<const uint64_t *>(s.t_rec_begin.p), *te = static_cast<const uint64_t *>(s.t_rec_end.p);
         const uint32_t *ti = static_cast<const uint32_t *>(s.t_rec_input.p);
-        if (!n_rec) return batch_impl(c, s, s.d_packed, n_bases, tb, te, ti, nt, n_inputs, abundance, res);
+        if (!n_rec) {
+            s.last_rb = tb; s.last_re = te; s.last_ri = ti; s.last_nrec = nt;
+            return batch_impl(c, s, s.d_packed, n_bases, tb, te, ti, nt, n_inputs, abundance, res);
+        }
         if (is_device_ptr(rec_begin)) return fail(-3, "spsp_sketch_batch_staged: host record arrays expected next to ingested text");
         { int rc_ = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_sketch_batch_staged"); if (rc_) return rc_; }
         CK(s.b_rec_begin.ensure(n_rec * 8)); CK(s.b_rec_end.ensure(n_rec * 8)); CK(s.b_rec_input.ensure(n_rec * 4));
@@ -879,11 +887,36 @@ extern "C" int spsp_sketch_batch_staged(spsp_ctx *c, int slot, uint64_t n_bases,
                                static_cast<uint64_t *>(s.m_rec_begin.p), static_cast<uint64_t *>(s.m_rec_end.p),
                                static_cast<uint32_t *>(s.m_rec_input.p), s.stream));
         { std::lock_guard<std::mutex> g(c->mu); c->launches += 1; }
+        s.last_rb = static_cast<const uint64_t *>(s.m_rec_begin.p); s.last_re = static_cast<const uint64_t *>(s.m_rec_end.p);
+        s.last_ri = static_cast<const uint32_t *>(s.m_rec_input.p); s.last_nrec = n_all;
         return batch_impl(c, s, s.d_packed, n_bases, static_cast<const uint64_t *>(s.m_rec_begin.p),
                           static_cast<const uint64_t *>(s.m_rec_end.p), static_cast<const uint32_t *>(s.m_rec_input.p), n_all,
                           n_inputs, abundance, res);
     }
-    return batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+    const int rc = batch_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, abundance, res);
+    if (is_device_ptr(rec_begin)) { s.last_rb = rec_begin; s.last_re = rec_end; s.last_ri = rec_input; }
+    else {
+        s.last_rb = static_cast<const uint64_t *>(s.b_rec_begin.p); s.last_re = static_cast<const uint64_t *>(s.b_rec_end.p);
+        s.last_ri = static_cast<const uint32_t *>(s.b_rec_input.p);
+    }
+    s.last_nrec = n_rec;
+    return rc;
+}
+
+extern "C" int spsp_batch_record_kmers(spsp_ctx *c, int slot, uint32_t n_inputs, uint64_t *kmers_out)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !kmers_out) return fail(-3, "spsp_batch_record_kmers: bad args");
+    Slot &s = c->slots[slot];
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)(n_inputs ? n_inputs : 1) * 8;
+    CK(s.b_kmers.ensure(bytes));
+    CK(cudaMemsetAsync(s.b_kmers.p, 0, bytes, s.stream));
+    CK(launch_record_kmers(s.last_rb, s.last_re, s.last_ri, s.last_nrec, (uint32_t)c->k, static_cast<unsigned long long *>(s.b_kmers.p),
+                           s.stream));
+    CK(cudaMemcpyAsync(kmers_out, s.b_kmers.p, (size_t)n_inputs * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    { std::lock_guard<std::mutex> g(c->mu); c->launches += 1; }
+    return 0;
 }
 
 // ------------------------------------------------------------ device-side ingest
@@ -1062,22 +1095,25 @@ static int dense_impl(spsp_ctx *c, Slot &s, const uint32_t *d_packed, uint64_t n
                       const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec, uint32_t n_inputs,
                       uint64_t *total_superkmers, uint64_t *selected_kmers, float *kernel_ms)
 {
-    int rc = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_dense_stats");
-    if (rc) return rc;
     cudaStream_t st = s.stream;
-    const size_t nr = n_rec ? n_rec : 1;
-    CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
-    if (n_rec) {
-        CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, st));
+    const bool on_device = n_rec && is_device_ptr(rec_begin);         // a table that is on the device already is used in place
+    if (!on_device) {
+        int rc = check_records(rec_begin, rec_end, rec_input, n_rec, n_bases, n_inputs, "spsp_dense_stats");
+        if (rc) return rc;
+        const size_t nr = n_rec ? n_rec : 1;
+        CK(s.b_rec_begin.ensure(nr * 8)); CK(s.b_rec_end.ensure(nr * 8)); CK(s.b_rec_input.ensure(nr * 4));
+        if (n_rec) {
+            CK(cudaMemcpyAsync(s.b_rec_begin.p, rec_begin, n_rec * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s.b_rec_end.p, rec_end, n_rec * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s.b_rec_input.p, rec_input, n_rec * 4, cudaMemcpyHostToDevice, st));
+        }
     }
     if (!s.dn) s.dn = dense_buffers_create();
     DenseIn in{};
     in.d_packed = d_packed; in.n_bases = n_bases;
-    in.d_rec_begin = static_cast<const uint64_t *>(s.b_rec_begin.p);
-    in.d_rec_end = static_cast<const uint64_t *>(s.b_rec_end.p);
-    in.d_rec_input = static_cast<const uint32_t *>(s.b_rec_input.p);
+    in.d_rec_begin = on_device ? rec_begin : static_cast<const uint64_t *>(s.b_rec_begin.p);
+    in.d_rec_end = on_device ? rec_end : static_cast<const uint64_t *>(s.b_rec_end.p);
+    in.d_rec_input = on_device ? rec_input : static_cast<const uint32_t *>(s.b_rec_input.p);
     in.n_rec = n_rec; in.n_inputs = n_inputs; in.k = c->k; in.m = c->m; in.thr = c->thr;
     uint32_t nl = 0;
     cudaError_t e = dense_stats_run(s.dn, in, total_superkmers, selected_kmers, kernel_ms, &nl, st);
@@ -1123,6 +1159,9 @@ extern "C" int spsp_dense_stats_staged(spsp_ctx *c, int slot, uint64_t n_bases, 
     Slot &s = c->slots[slot];
     if (spsp_packed_words(n_bases) > s.d_packed_words) return fail(-3, "spsp_dense_stats_staged: nothing staged on this slot");
     CK(cudaSetDevice(c->device));
+    if (!rec_begin && !n_rec && s.last_nrec)       // the table of the batch just sketched, as the device saw it
+        return dense_impl(c, s, s.d_packed, n_bases, s.last_rb, s.last_re, s.last_ri, s.last_nrec, n_inputs, total_superkmers,
+                          selected_kmers, kernel_ms);
     return dense_impl(c, s, s.d_packed, n_bases, rec_begin, rec_end, rec_input, n_rec, n_inputs, total_superkmers,
                       selected_kmers, kernel_ms);
 }

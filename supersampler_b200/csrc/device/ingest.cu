@@ -418,7 +418,38 @@ __global__ void record_merge_kernel(const uint64_t *__restrict__ a_begin, const 
     o_input[o] = from_a ? a_input[self] : b_input[self];
 }
 
+// k-mers of every input: sum over its records of at least k bases of (length - k + 1)  (read_kmer, SubSampler.cpp:343-347)
+__global__ void record_kmers_kernel(const uint64_t *__restrict__ rec_begin, const uint64_t *__restrict__ rec_end,
+                                    const uint32_t *__restrict__ rec_input, uint64_t n_rec, uint32_t k,
+                                    unsigned long long *__restrict__ kmers)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    uint32_t in = 0xFFFFFFFFu;
+    if (r < n_rec) {
+        const uint64_t n = rec_end[r] - rec_begin[r];
+        in = rec_input[r];
+        if (n >= k) v = n - k + 1;
+    }
+    // records are grouped by input: add up the lanes that share the first lane's input, the others go alone
+    const uint32_t in0 = __shfl_sync(0xffffffffu, in, 0);
+    const bool same = in == in0;
+    unsigned long long part = same ? v : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0 && in0 != 0xFFFFFFFFu && part) atomicAdd(kmers + in0, part);
+    if (!same && in != 0xFFFFFFFFu && v) atomicAdd(kmers + in, v);
+}
+
 }  // namespace
+
+cudaError_t launch_record_kmers(const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec,
+                                uint32_t k, unsigned long long *d_kmers, cudaStream_t st)
+{
+    if (!n_rec) return cudaSuccess;
+    record_kmers_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(rec_begin, rec_end, rec_input, n_rec, k, d_kmers);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ingest_summary(const uint8_t *d_text, const IngestInput *d_in, uint32_t n_in, uint64_t n_tiles,
                                   IngestTile *d_tiles, cudaStream_t st)

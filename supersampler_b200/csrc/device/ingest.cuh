@@ -52,4 +52,8 @@ cudaError_t launch_record_merge(const uint64_t *a_begin, const uint64_t *a_end, 
                                 const uint64_t *b_begin, const uint64_t *b_end, const uint32_t *b_input, uint64_t nb,
                                 uint64_t *o_begin, uint64_t *o_end, uint32_t *o_input, cudaStream_t st);
 
+// d_kmers[input] += k-mers of the input's records (records of at least k bases: length - k + 1); d_kmers zeroed by the caller.
+cudaError_t launch_record_kmers(const uint64_t *rec_begin, const uint64_t *rec_end, const uint32_t *rec_input, uint64_t n_rec,
+                                uint32_t k, unsigned long long *d_kmers, cudaStream_t st);
+
 }  // namespace spsp

@@ -130,6 +130,16 @@ void WorkerPool::run(size_t n, const std::function<void(size_t)> &fn)
 
 // Two pinned chunks per worker thread for text read from files (device-side ingest).
 namespace {
+// Does this text look like a read set?  (header lines every few hundred bytes: the host packer's block loops
+// fall back to its byte-wise state machine at every '>', 0.6 GB/s per thread against 7-10 on genomes, while the
+// ingest kernels do not care: C4's 1 Gbp read sets go 1.7 -> 33 Gbp/s from files)
+bool looks_like_reads(const uint8_t *p, size_t n)
+{
+    n = std::min<size_t>(n, 64u << 10);
+    size_t headers = 0;
+    for (size_t i = 0; i + 1 < n; i++) headers += (p[i] == '\n') & (p[i + 1] == '>');
+    return n >= 4096 && headers * 4096 > n;              // more than one record per 4 KB
+}
 struct TextRing {
     uint8_t *buf[2] = {nullptr, nullptr};
     size_t cap = 0;
@@ -157,6 +167,7 @@ struct BatchSketcher::Prepared {
     std::vector<uint64_t> rec_off;
     // device-side ingest
     bool raw = false;                  // went to the device as text
+    bool reads = false;                // short records: AUTO sends it as text
     uint64_t text_off = 0;             // where in the device text buffer (multiple of 16)
 };
 
@@ -222,7 +233,7 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
     prep.assign(n, Prepared());
     pool_.run(n, [&](size_t i) {
         Prepared &p = prep[i];
-        if (src[i].data) { p.len = src[i].len; return; }
+        if (src[i].data) { p.len = src[i].len; p.reads = looks_like_reads(src[i].data, src[i].len); return; }
         p.from_file = true;
         int fd = open(src[i].path.c_str(), O_RDONLY);
         struct stat st;
@@ -239,6 +250,10 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
             if (st.st_size >= 18 && pread(fd, t4, 4, st.st_size - 4) == 4)
                 isize = (uint64_t)t4[0] | ((uint64_t)t4[1] << 8) | ((uint64_t)t4[2] << 16) | ((uint64_t)t4[3] << 24);
             p.len = std::max<uint64_t>(isize, 3 * (uint64_t)st.st_size);
+        } else {
+            uint8_t head[64u << 10];
+            const ssize_t r = pread(fd, head, sizeof head, 0);
+            p.reads = r > 0 && looks_like_reads(head, (size_t)r);
         }
         close(fd);
     });
@@ -274,6 +289,7 @@ void BatchSketcher::begin(const std::vector<BatchSource> &src)
             if (!read_file_maybe_gz(src[first + j].path, p.text)) { p.ok = false; p.len = 0; return; }
             p.from_file = false;
             p.len = p.text.size();
+            p.reads = looks_like_reads(p.text.data(), p.text.size());
         });
         stats.prep_s += secs(ti, clk::now());
         for (size_t i = first; i < last; i++) ok[i] = prep[i].ok ? 1 : 0;
@@ -314,8 +330,12 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
     // bandwidth and raw text then only competes for the PCIe link (96.7 vs 95.3 Gbp/s); with 4 workers per GPU
     // (8 GPUs on a 32-core box) the mixed queue takes 33 to 63 Gbp/s.  SPSP_AUTO_MAX_WORKERS moves the switch.
     static const int auto_max_workers = getenv("SPSP_AUTO_MAX_WORKERS") ? atoi(getenv("SPSP_AUTO_MAX_WORKERS")) : 11;
-    Ingest mode = dense_stats ? Ingest::HOST : ingest;         // the dense totals take host record tables
-    if (mode == Ingest::AUTO && pool_.size() > auto_max_workers) mode = Ingest::HOST;
+    Ingest mode = ingest;
+    const bool auto_mixed = mode == Ingest::AUTO && pool_.size() <= auto_max_workers;     // opportunistic raw sends
+    bool any_reads = false;
+    if (mode == Ingest::AUTO)
+        for (size_t i = first; i < last; i++) any_reads = any_reads || (prep[i].ok && prep[i].reads);
+    if (mode == Ingest::AUTO && !auto_mixed && !any_reads) mode = Ingest::HOST;
     uint64_t total_words = 0, total_text = 0;
     for (size_t i = first; i < last; i++) {
         Prepared &p = prep[i];
@@ -348,11 +368,12 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
     // send an input from the back of the queue as raw text (asynchronous; the worker goes on packing)
     std::mutex qmu;
     size_t q_lo = 0, q_hi = nb;
+    const std::vector<size_t> *q_map = nullptr;          // queue position -> input of the batch
     std::atomic<int> lane_claim[2];
     lane_claim[0] = 0; lane_claim[1] = 0;
     std::function<void(size_t, int)> send_input_fn;
     auto feed_link = [&]() {
-        if (mode != Ingest::AUTO) return;
+        if (mode != Ingest::AUTO || !auto_mixed) return;
         for (int lane = 0; lane < 2; lane++) {
             int idle = 0;
             if (lane_claim[lane].load(std::memory_order_relaxed)) continue;
@@ -364,7 +385,7 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
                 // (text that still sits in a file would have to be read into pinned memory by this worker first,
                 // which costs about what packing it costs: files go over as text in DEVICE mode only)
                 std::lock_guard<std::mutex> g(qmu);
-                if (q_lo < q_hi && !prep[first + q_hi - 1].from_file) { j = --q_hi; got = true; }
+                if (q_lo < q_hi && !prep[first + (*q_map)[q_hi - 1]].from_file) { j = (*q_map)[--q_hi]; got = true; }
             }
             if (got) send_input_fn(j, lane);
             lane_claim[lane].store(0);
@@ -487,15 +508,39 @@ void BatchSketcher::pack_batch(const std::vector<BatchSource> &src, std::vector<
             else send_input(items[i].j, -1);
         });
     } else {
-        // one queue, two ends: every worker packs inputs from the front; raw sends take inputs from the back
+        // inputs that look like read sets go over as text (files in pieces, like DEVICE); the others through one
+        // queue with two ends: every worker packs inputs from the front; raw sends take inputs from the back
+        struct Item { size_t j; uint64_t off, len; bool file; };
+        std::vector<Item> items;
+        std::vector<size_t> rest;
+        const uint64_t PIECE = 32u << 20;
+        for (size_t j = 0; j < nb; j++) {
+            Prepared &p = prep[first + j];
+            if (!(p.ok && p.reads && p.len)) { rest.push_back(j); continue; }
+            if (p.from_file) {
+                p.raw = true;
+                for (uint64_t off = 0; off < p.len; off += PIECE) items.push_back({j, off, std::min(PIECE, p.len - off), true});
+            } else {
+                items.push_back({j, 0, 0, false});
+            }
+        }
+        q_lo = 0; q_hi = rest.size();
+        q_map = &rest;
+        std::atomic<size_t> next_item{0};
         pool_.run((size_t)std::max(1, pool_.size()), [&](size_t) {
+            for (;;) {
+                const size_t i = next_item.fetch_add(1);
+                if (i >= items.size()) break;
+                if (items[i].file) send_file_piece(items[i].j, items[i].off, items[i].len);
+                else send_input(items[i].j, -1);
+            }
             for (;;) {
                 feed_link();
                 size_t j;
                 {
                     std::lock_guard<std::mutex> g(qmu);
                     if (q_lo >= q_hi) break;
-                    j = q_lo++;
+                    j = rest[q_lo++];
                 }
                 pack_input(j);
             }
@@ -559,16 +604,23 @@ void BatchSketcher::device_batch(std::vector<Prepared> &prep, size_t first, size
                                  &res) != 0)
         throw_spsp("spsp_sketch_batch_staged");
     if (dense_stats) {
-        std::vector<uint64_t> tot(nb ? nb : 1), sel(nb ? nb : 1);
+        std::vector<uint64_t> tot(nb ? nb : 1), sel(nb ? nb : 1), km(nb ? nb : 1, 0);
         float ms = 0;
-        if (spsp_dense_stats_staged(ctx, 0, n_total, rb.data(), re.data(), ri.data(), rb.size(), (uint32_t)nb, tot.data(),
-                                    sel.data(), &ms) != 0)
+        bool any_raw = false;
+        for (size_t j = 0; j < nb; j++) any_raw = any_raw || prep[first + j].raw;
+        // (a batch with inputs ingested on the device: the record table lives there, merged by the sketch call)
+        if (any_raw ? spsp_dense_stats_staged(ctx, 0, n_total, nullptr, nullptr, nullptr, 0, (uint32_t)nb, tot.data(), sel.data(), &ms)
+                    : spsp_dense_stats_staged(ctx, 0, n_total, rb.data(), re.data(), ri.data(), rb.size(), (uint32_t)nb, tot.data(),
+                                              sel.data(), &ms))
             throw_spsp("spsp_dense_stats_staged");
+        if (any_raw && spsp_batch_record_kmers(ctx, 0, (uint32_t)nb, km.data()) != 0) throw_spsp("spsp_batch_record_kmers");
         dense_ms += ms;
         for (size_t j = 0; j < nb; j++) {
             const Prepared &p = prep[first + j];
             total_superkmers[first + j] = tot[j];
-            for (size_t r = 0; r + 1 < p.rec_off.size(); r++) total_kmers[first + j] += p.rec_off[r + 1] - p.rec_off[r] - (uint64_t)k_ + 1;
+            if (any_raw) total_kmers[first + j] += km[j];
+            else
+                for (size_t r = 0; r + 1 < p.rec_off.size(); r++) total_kmers[first + j] += p.rec_off[r + 1] - p.rec_off[r] - (uint64_t)k_ + 1;
             if (sel[j] != res.selected[j])      // two independent device paths must agree on the selected k-mers
                 throw std::runtime_error("dense and sparse sketch paths disagree on the number of selected k-mers");
         }

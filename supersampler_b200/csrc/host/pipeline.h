@@ -39,8 +39,10 @@ struct BatchStats {
 //   AUTO    both at once on one work queue: the workers pack inputs from the front; whenever one of them finds a
 //           text lane idle (the previous raw input has arrived) it first sends an input from the back of the
 //           queue as raw text, so the split follows what the box can do (few cores per GPU: about half of the
-//           inputs go over as text).  With more than 11 workers AUTO is HOST: the host lane then runs into the
-//           host's memory bandwidth and raw text only competes for the PCIe link (measured, see pipeline.cpp)
+//           inputs go over as text).  With more than 11 workers the queue is host-only: the host lane then runs
+//           into the host's memory bandwidth and raw text only competes for the PCIe link (measured, see
+//           pipeline.cpp).  Inputs that look like read sets (a header line every few hundred bytes) always go over
+//           as text: the host packer crawls on them, the ingest kernels do not care.  The default.
 enum class Ingest { HOST = 0, DEVICE = 1, AUTO = 2 };
 
 // Persistent worker threads (the pack phase runs every few milliseconds: no thread start-up per batch).
@@ -95,7 +97,7 @@ public:
     // print_stat totals that need every k-mer (SubSampler.cpp:633-665): filled by run() when dense_stats is
     // set, by the dense minimizer machine on the batch still staged on the device (spsp_dense_stats_staged).
     bool dense_stats = false;
-    Ingest ingest = Ingest::HOST;              // set from SPSP_INGEST (host|device|auto) by the constructor when present
+    Ingest ingest = Ingest::AUTO;              // or what SPSP_INGEST (host|device|auto) names
     std::vector<uint64_t> total_kmers, total_superkmers;
     double dense_ms = 0;
 

@@ -157,3 +157,38 @@ def test_pipeline_ingest_genomes_and_reads(oracle):
         del pins
         pl.close()
     host.close()
+
+
+@pytest.mark.parametrize("mode", ["host", "device", "auto"])
+def test_cli_batch_stats_and_sketches_every_ingest_mode(mode, tmp_path, golden):
+    """`sub_sampler -f -v 1` on genomes, read sets and messy records in one file of files: the printed totals
+    (k-mers / super-k-mers seen: the dense machine on the record table the device used, host-packed, ingested or
+    merged) equal the reference's printed numbers and every sketch file holds the golden bytes."""
+    import json
+    import os
+    import subprocess
+    from supersampler_b200 import capi
+    from tests.conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "stats.json")) as f:
+        stats = json.load(f)
+    cases = ["c1_k31_m11_s1000", "reads_k31_m11_s1000", "nasty_k31_m11_s1000", "tiny_k31_m11_s1000", "empty_k31_m11_s1000"]
+    paths = []
+    for c in cases:
+        inp = SKETCH_CASES[c][0]
+        p = tmp_path / (inp + ".fa")
+        p.write_bytes(build_input(inp))
+        paths.append(p)
+    fof = tmp_path / "in.txt"
+    fof.write_text("\n".join(str(p) for p in paths) + "\n")
+    env = dict(os.environ, SPSP_INGEST=mode)
+    r = subprocess.run([os.path.join(capi.BIN_DIR, "sub_sampler"), "-f", str(fof), "-k", "31", "-m", "11", "-s", "1000", "-t", "3"],
+                       cwd=tmp_path, env=env, stdin=subprocess.DEVNULL, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for c in cases:
+        inp = SKETCH_CASES[c][0]
+        with gzip.open(tmp_path / f"subsampled_{inp}.gz", "rb") as f:
+            assert sha(f.read()) == golden["sketch"][c]["sha256"], (mode, c)
+        want = stats[c]
+        if want["selected_kmers"]:
+            assert f"I have seen {want['total_kmers']:,} kmers and I selected {want['selected_kmers']:,} kmers" in r.stdout, (mode, c)
+            assert f"I have seen {want['total_superkmers']:,} superkmers" in r.stdout, (mode, c)

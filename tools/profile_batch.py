@@ -9,8 +9,9 @@ from supersampler_b200 import synth
 def main():
     S.build()
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    k, m, s = 31, 11, float(sys.argv[2]) if len(sys.argv) > 2 else 1000.0
+    k, s = 31, float(sys.argv[2]) if len(sys.argv) > 2 else 1000.0
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    m = int(sys.argv[4]) if len(sys.argv) > 4 else 11
     fam = synth.Family(5_000_000, 42)
     ws, ros = [], []
     for i in range(n):
