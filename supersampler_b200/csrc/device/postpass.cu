@@ -104,6 +104,7 @@ __device__ __forceinline__ long long find_rec(const uint64_t *__restrict__ rec_b
 struct Counters {
     unsigned long long n_valid, n_pieces, n_entries, n_buckets, n_elems, body_bytes;
     unsigned long long big_top;        // bump allocator of the big-group pool (bytes)
+    unsigned long long tmp_bytes, tmp_elems;   // bump allocators of the groups' temporary output ranges
     unsigned int overflow;             // OVF_* bits: a capacity was too small, the host retries
     unsigned int pad;
 };
@@ -595,13 +596,18 @@ struct BucketArgs {
     uint64_t pieces_cap;
     int k, m, input_shift;
     unsigned abundance;
-    unsigned long long *lb_bytes, *lb_elems;   // [groups] decoupled look-back states
-    uint8_t *body;
+    // A group writes its bytes and elements to ranges it draws from two bump allocators (any order) and leaves
+    // {where, how much}; pp_offsets_kernel turns the sizes into final offsets (groups are in bucket order) and
+    // pp_gather_kernel moves every group's output to its final place.  (Round 1/2a obtained the offsets inside
+    // the group kernel by decoupled look-back: every group then waited, holding its SM slot, for all running
+    // predecessors to reach the same point -- 40 k of its 134 k cycles.)
+    unsigned long long *g_tb, *g_nb, *g_te, *g_ne;   // [groups] temp byte offset / bytes, temp element offset / elements
+    uint8_t *tmp_body;
     uint64_t body_cap;
-    uint32_t *el_min;
-    uint64_t *el_klo, *el_khi;
+    uint32_t *tmp_min;
+    uint64_t *tmp_klo, *tmp_khi;
     uint64_t elems_cap;
-    unsigned long long *in_first_byte, *in_first_elem;   // [input] offset + 1 of the input's first bucket, 0 = none
+    unsigned long long *in_first_byte, *in_first_elem;   // [input] (group + 1) << 32 | offset inside the group of the input's first bucket, 0 = none
     uint8_t *big_pool;
     uint64_t big_cap;
     Counters *cnt;
@@ -755,36 +761,6 @@ __device__ __forceinline__ K128 kmer_neighbour(const K128 &cur, bool left, int t
         nx.lo &= kmask.lo; nx.hi &= kmask.hi;
     }
     return nx;
-}
-
-// Decoupled look-back over the groups' aggregates: returns the sum of the aggregates of groups < g and
-// leaves this group's inclusive prefix for its successors.  state = flag << 62 | value (flag 1 = aggregate,
-// 2 = inclusive prefix); called by one full warp.
-__device__ unsigned long long lookback(unsigned long long *state, uint32_t g, unsigned long long agg)
-{
-    const int lane = threadIdx.x & 31;
-    volatile unsigned long long *vs = state;
-    if (lane == 0) vs[g] = ((g == 0 ? 2ULL : 1ULL) << 62) | agg;
-    unsigned long long excl = 0;
-    if (g == 0) return 0;
-    long long j = (long long)g - 1;
-    for (;;) {
-        const long long idx = j - lane;
-        unsigned long long v = 2ULL << 62;                       // before group 0: inclusive prefix 0
-        if (idx >= 0) {
-            do { v = vs[idx]; } while ((v >> 62) == 0);
-        }
-        const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-        const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;
-        unsigned long long part = (lane <= first_inc) ? (v & ((1ULL << 62) - 1)) : 0;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        excl += part;
-        if (inc_mask) break;
-        j -= 32;
-    }
-    if (lane == 0) vs[g] = (2ULL << 62) | (excl + agg);
-    return excl;
 }
 
 // Leftmost occurrence of the minimizer in codes sk[0, len), -1 if none (one thread).
@@ -998,8 +974,16 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
                 const bool left = n_left != 0;
                 if (!left && n_right == 0) break;
                 // find_next (:566-602): first neighbour in probe order that is in the bucket and unseen
+                // the four candidates of one side are one aligned 8-byte (16-byte) word: one load, not four
                 const IDX *ad = g.adj + (size_t)cur * 8 + (left ? 0 : 4);
-                const uint32_t c0 = ad[0], c1 = ad[1], c2 = ad[2], c3 = ad[3];
+                uint32_t c0, c1, c2, c3;
+                if (sizeof(IDX) == 2) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(ad);
+                    c0 = v.x & 0xFFFFu; c1 = v.x >> 16; c2 = v.y & 0xFFFFu; c3 = v.y >> 16;
+                } else {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(ad);
+                    c0 = v.x; c1 = v.y; c2 = v.z; c3 = v.w;
+                }
                 const uint32_t s0 = g.seen[c0], s1 = g.seen[c1], s2 = g.seen[c2], s3 = g.seen[c3];
                 const uint32_t found = !s0 ? c0 : !s1 ? c1 : !s2 ? c2 : !s3 ? c3 : U;
                 const bool ok = found != U;
@@ -1061,6 +1045,7 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
         g.e_slot[u] = keep ? 1u : 0u;
     }
     __syncthreads();
+    PP_PHASE(11);
     {
         const int ln = lane, wp = warp;
         uint32_t carry = 0;
@@ -1170,42 +1155,37 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
         if (lane == 0) { p_txt[0] = '\n'; p_txt[1] = '\n'; }
     }
     };
-    // ---- global offsets: decoupled look-back over the groups (bytes by warp 0, elements by warp 1).  Waiting for the
-    // predecessors is hidden behind the writer loop: the other warps assemble the group's bytes in shared memory
-    // (the entry keys are dead by now), which are then copied to their final place in one coalesced sweep.
+    // ---- the group's bytes, assembled in shared memory when they fit (the entry keys are dead by now)
     constexpr uint32_t STAGE_CAP = BK_ECAP * 8;
     const bool staged = sizeof(IDX) == 2 && bytes_total <= STAGE_CAP;
     uint8_t *stage = reinterpret_cast<uint8_t *>(g.e_lo);
-    if (warp == 0) {
-        const unsigned long long x = lookback(a.lb_bytes, grp, bytes_total);
-        if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 2) = x; }
-        const unsigned long long y = lookback(a.lb_elems, grp, NE);
-        if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 4) = y; }
-    } else if (staged) {
-        emit_buckets(stage, (uint32_t)warp - 1, BK_WARPS - 1);
+    if (staged) emit_buckets(stage, (uint32_t)warp, BK_WARPS);
+    // ---- temporary output ranges
+    if (threadIdx.x == 0) {
+        const unsigned long long tb = atomicAdd(&a.cnt->tmp_bytes, (unsigned long long)bytes_total);
+        const unsigned long long te = atomicAdd(&a.cnt->tmp_elems, (unsigned long long)NE);
+        *reinterpret_cast<unsigned long long *>(s_misc + 2) = tb;
+        *reinterpret_cast<unsigned long long *>(s_misc + 4) = te;
+        atomicAdd(&a.cnt->n_buckets, (unsigned long long)NB);
+        unsigned ovf = 0;
+        if (tb + bytes_total > a.body_cap) ovf |= OVF_BODY;
+        if (te + NE > a.elems_cap) ovf |= OVF_ELEMS;
+        if (ovf) atomicOr(&a.cnt->overflow, ovf);
+        else { a.g_tb[grp] = tb; a.g_nb[grp] = bytes_total; a.g_te[grp] = te; a.g_ne[grp] = NE; }
     }
     __syncthreads();
     const unsigned long long byte_base = *reinterpret_cast<unsigned long long *>(s_misc + 2);
     const unsigned long long elem_base = *reinterpret_cast<unsigned long long *>(s_misc + 4);
     PP_PHASE(8);
     if (a.dbg && threadIdx.x == 0) { a.dbg[(size_t)grp * 16 + 12] = E; a.dbg[(size_t)grp * 16 + 13] = U; a.dbg[(size_t)grp * 16 + 14] = NB; }
-    if (threadIdx.x == 0) {
-        atomicAdd(&a.cnt->body_bytes, (unsigned long long)bytes_total);
-        atomicAdd(&a.cnt->n_elems, (unsigned long long)NE);
-        atomicAdd(&a.cnt->n_buckets, (unsigned long long)NB);
-        unsigned ovf = 0;
-        if (byte_base + bytes_total > a.body_cap) ovf |= OVF_BODY;
-        if (elem_base + NE > a.elems_cap) ovf |= OVF_ELEMS;
-        if (ovf) atomicOr(&a.cnt->overflow, ovf);
-    }
     if (byte_base + bytes_total > a.body_cap || elem_base + NE > a.elems_cap) return;
     // ---- where every input's bytes / elements begin: buckets are sorted by input first
     for (uint32_t b = threadIdx.x; b < NB; b += BK_THREADS) {
         const uint32_t hp = first + g.b_hp[b];
         const uint64_t in = bucket_key(hp) >> a.input_shift;
         if (hp == 0 || (bucket_key(hp - 1) >> a.input_shift) != in) {
-            a.in_first_byte[in] = byte_base + g.b_bytes[b] + 1;                  // + 1: 0 means "no bucket"
-            a.in_first_elem[in] = elem_base + (g.e_slot[g.b_us[b]] >> 1) + 1;
+            a.in_first_byte[in] = ((unsigned long long)(grp + 1) << 32) | g.b_bytes[b];
+            a.in_first_elem[in] = ((unsigned long long)(grp + 1) << 32) | (g.e_slot[g.b_us[b]] >> 1);
         }
     }
     // ---- elements
@@ -1216,18 +1196,18 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
             const K128 rc = k_rc_t<HI>(key, k);
             if (k_lt(rc, key)) key = rc;
             const unsigned long long o = elem_base + (x >> 1);
-            a.el_min[o] = (uint32_t)(bucket_key(first + g.b_hp[g.u_bl[u]]) & (((uint64_t)1 << a.input_shift) - 1));
-            a.el_klo[o] = key.lo;
-            if (HI) a.el_khi[o] = key.hi;
+            a.tmp_min[o] = (uint32_t)(bucket_key(first + g.b_hp[g.u_bl[u]]) & (((uint64_t)1 << a.input_shift) - 1));
+            a.tmp_klo[o] = key.lo;
+            if (HI) a.tmp_khi[o] = key.hi;
         }
     }
     if (a.dbg) { __syncthreads(); PP_PHASE(9); }
     // ---- the sketch bytes
     if (staged) {
-        uint8_t *dst = a.body + byte_base;
+        uint8_t *dst = a.tmp_body + byte_base;
         for (uint32_t i = threadIdx.x; i < bytes_total; i += BK_THREADS) dst[i] = stage[i];
     } else {
-        emit_buckets(a.body + byte_base, (uint32_t)warp, BK_WARPS);
+        emit_buckets(a.tmp_body + byte_base, (uint32_t)warp, BK_WARPS);
     }
     if (a.dbg) { __syncthreads(); PP_PHASE(10); }
 }
@@ -1247,17 +1227,8 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
     const uint32_t n_pieces = (uint32_t)npt;
     auto bucket_key = [&](uint32_t i) -> uint64_t { return a.skey64 ? a.skey64[i] : (uint64_t)a.skey32[i]; };
     auto is_head = [&](uint32_t i) { return i == 0 || bucket_key(i) != bucket_key(i - 1); };
-    auto publish_empty = [&]() {
-        if (warp == 0) { lookback(a.lb_bytes, grp, 0); lookback(a.lb_elems, grp, 0); }
-    };
     const uint64_t lo64 = (uint64_t)grp * a.pp;
-    if (lo64 >= n_pieces) {                                      // nothing looks back at groups behind the data
-        if (threadIdx.x == 0) {
-            reinterpret_cast<volatile unsigned long long *>(a.lb_bytes)[grp] = 1ULL << 62;
-            reinterpret_cast<volatile unsigned long long *>(a.lb_elems)[grp] = 1ULL << 62;
-        }
-        return;
-    }
+    if (lo64 >= n_pieces) return;                                // behind the data (the group arrays are zeroed)
     const uint32_t lo = (uint32_t)lo64, nominal_end = (uint32_t)min((uint64_t)n_pieces, lo64 + a.pp);
     if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_end = n_pieces; }
     __syncthreads();
@@ -1265,7 +1236,7 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
         if (is_head(i)) atomicMin(&s_first, i);
     __syncthreads();
     const uint32_t first = s_first;
-    if (first == 0xFFFFFFFFu) { publish_empty(); return; }       // no bucket starts in this group's range
+    if (first == 0xFFFFFFFFu) return;                            // no bucket starts in this group's range
     // the group ends where the first bucket of a later range starts
     for (uint32_t b0 = nominal_end; b0 < n_pieces; b0 += BK_THREADS) {
         const uint32_t i = b0 + threadIdx.x;
@@ -1305,13 +1276,92 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
         __syncthreads();
         if (off + need > a.big_cap) {
             if (threadIdx.x == 0) atomicOr(&a.cnt->overflow, (unsigned)OVF_BIG);
-            publish_empty();
             return;
         }
         group_carve<uint32_t>(g, a.big_pool + off, np, E, S, HI);
         for (uint32_t p = threadIdx.x; p < np; p += BK_THREADS) g.pc[p] = a.pieces[a.order[first + p]];
         __syncthreads();
         process_group<uint32_t, HI>(a, g, grp, first, np, s_warp, s_sk, s_misc);
+    }
+}
+
+// Final offsets of the groups' outputs: exclusive prefix sums of their byte and element counts, in group (= bucket)
+// order, into g_bb / g_be; the totals go to the counters.  One CTA.
+__global__ void __launch_bounds__(1024) pp_offsets_kernel(const unsigned long long *__restrict__ g_nb, const unsigned long long *__restrict__ g_ne,
+                                                          unsigned long long *__restrict__ g_bb, unsigned long long *__restrict__ g_be,
+                                                          uint64_t n_groups, Counters *cnt)
+{
+    __shared__ unsigned long long s_w[2][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long run_b = 0, run_e = 0;
+    for (uint64_t g0 = 0; g0 < n_groups; g0 += 1024) {
+        const uint64_t g = g0 + threadIdx.x;
+        const unsigned long long vb = g < n_groups ? g_nb[g] : 0, ve = g < n_groups ? g_ne[g] : 0;
+        unsigned long long ib = vb, ie = ve;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long tb = __shfl_up_sync(0xffffffffu, ib, o), te = __shfl_up_sync(0xffffffffu, ie, o);
+            if (lane >= o) { ib += tb; ie += te; }
+        }
+        if (lane == 31) { s_w[0][warp] = ib; s_w[1][warp] = ie; }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long tb = s_w[0][lane], te = s_w[1][lane];
+            unsigned long long xb = tb, xe = te;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long ub = __shfl_up_sync(0xffffffffu, xb, o), ue = __shfl_up_sync(0xffffffffu, xe, o);
+                if (lane >= o) { xb += ub; xe += ue; }
+            }
+            s_w[0][lane] = xb - tb; s_w[1][lane] = xe - te;
+            if (lane == 31) { s_w[0][32] = xb; s_w[1][32] = xe; }
+        }
+        __syncthreads();
+        if (g < n_groups) { g_bb[g] = run_b + s_w[0][warp] + ib - vb; g_be[g] = run_e + s_w[1][warp] + ie - ve; }
+        run_b += s_w[0][32]; run_e += s_w[1][32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { cnt->body_bytes = run_b; cnt->n_elems = run_e; }
+}
+
+// Moves every group's bytes and elements from its temporary range to their final place, and turns the inputs'
+// (group, offset inside the group) markers into final offsets (+ 1).  grid.x covers the groups, the CTAs behind
+// them the inputs.
+__global__ void __launch_bounds__(256) pp_gather_kernel(const unsigned long long *__restrict__ g_tb, const unsigned long long *__restrict__ g_nb,
+                                                        const unsigned long long *__restrict__ g_te, const unsigned long long *__restrict__ g_ne,
+                                                        const unsigned long long *__restrict__ g_bb, const unsigned long long *__restrict__ g_be,
+                                                        uint64_t n_groups, const uint8_t *__restrict__ tmp_body, uint8_t *__restrict__ body,
+                                                        uint64_t body_cap, const uint32_t *__restrict__ tmp_min,
+                                                        const uint64_t *__restrict__ tmp_klo, const uint64_t *__restrict__ tmp_khi,
+                                                        uint32_t *__restrict__ el_min, uint64_t *__restrict__ el_klo, uint64_t *__restrict__ el_khi,
+                                                        uint64_t elems_cap, unsigned long long *__restrict__ in_first_byte,
+                                                        unsigned long long *__restrict__ in_first_elem, uint32_t n_inputs, const Counters *cnt)
+{
+    if (cnt->overflow) return;                                   // the host retries with larger buffers
+    const uint64_t g = blockIdx.x;
+    if (g < n_groups) {
+        const unsigned long long nb = g_nb[g], ne = g_ne[g];
+        if (nb) {
+            const uint8_t *src = tmp_body + g_tb[g];
+            uint8_t *dst = body + g_bb[g];
+            if (g_bb[g] + nb <= body_cap)
+                for (unsigned long long i = threadIdx.x; i < nb; i += blockDim.x) dst[i] = src[i];
+        }
+        if (ne && g_be[g] + ne <= elems_cap) {
+            const unsigned long long so = g_te[g], d0 = g_be[g];
+            for (unsigned long long i = threadIdx.x; i < ne; i += blockDim.x) {
+                el_min[d0 + i] = tmp_min[so + i];
+                el_klo[d0 + i] = tmp_klo[so + i];
+                if (el_khi) el_khi[d0 + i] = tmp_khi[so + i];
+            }
+        }
+        return;
+    }
+    const uint64_t in = (g - n_groups) * blockDim.x + threadIdx.x;
+    if (in < n_inputs) {
+        const unsigned long long vb = in_first_byte[in], ve = in_first_elem[in];
+        if (vb) in_first_byte[in] = g_bb[(vb >> 32) - 1] + (vb & 0xFFFFFFFFull) + 1;     // + 1: 0 means "no bucket"
+        if (ve) in_first_elem[in] = g_be[(ve >> 32) - 1] + (ve & 0xFFFFFFFFull) + 1;
     }
 }
 
@@ -1364,7 +1414,7 @@ struct HBuf {
 
 // One device arena per slot (a single allocation, grow-only) + the output buffers that must survive the call.
 struct PostpassBuffers {
-    DBuf arena, elems, body, big;
+    DBuf arena, elems, body, big, tmp_elems, tmp_body;
     HBuf h_small, h_body, h_off;
     // capacities that were found too small once (a retry raised them): kept for the next batches
     uint64_t pieces_cap_min = 0, body_cap_min = 0, big_cap_min = 0;
@@ -1446,7 +1496,8 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     }
     Arena ar{nullptr};
     Counters *cnt = nullptr;
-    unsigned long long *in_sel = nullptr, *in_fb = nullptr, *in_fe = nullptr, *lb_bytes = nullptr, *lb_elems = nullptr;
+    unsigned long long *in_sel = nullptr, *in_fb = nullptr, *in_fe = nullptr;
+    unsigned long long *g_tb = nullptr, *g_nb = nullptr, *g_te = nullptr, *g_ne = nullptr, *g_bb = nullptr, *g_be = nullptr;
     uint32_t *hkey = nullptr, *hval = nullptr, *hkey2 = nullptr, *hval2 = nullptr, *cl_np = nullptr, *cl_nk = nullptr, *cta_np = nullptr;
     uint4 *pieces = nullptr;
     uint32_t *pkey32 = nullptr, *skey32 = nullptr, *pidx = nullptr, *order = nullptr;
@@ -1461,9 +1512,10 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
         in_fb = ar.take<unsigned long long>(nin);          // first byte / element of every input (+ 1)
         in_fe = ar.take<unsigned long long>(nin);
         small_bytes = ar.off;
-        lb_bytes = ar.take<unsigned long long>(n_groups);
-        lb_elems = ar.take<unsigned long long>(n_groups);
+        g_tb = ar.take<unsigned long long>(n_groups); g_nb = ar.take<unsigned long long>(n_groups);
+        g_te = ar.take<unsigned long long>(n_groups); g_ne = ar.take<unsigned long long>(n_groups);
         zero_bytes = ar.off;
+        g_bb = ar.take<unsigned long long>(n_groups); g_be = ar.take<unsigned long long>(n_groups);
         hkey = ar.take<uint32_t>(H); hval = ar.take<uint32_t>(H);
         if (!small_hits) { hkey2 = ar.take<uint32_t>(H); hval2 = ar.take<uint32_t>(H); }
         cl_np = ar.take<uint32_t>(H); cl_nk = ar.take<uint32_t>(H);
@@ -1484,8 +1536,13 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     uint64_t *el_klo = static_cast<uint64_t *>(b->elems.p);
     uint64_t *el_khi = hi128 ? el_klo + e_cap : nullptr;
     uint32_t *el_min = reinterpret_cast<uint32_t *>(el_klo + e_cap * (hi128 ? 2 : 1));
+    PP_CK(b->tmp_elems.ensure(e_cap * (4 + 8 + (hi128 ? 8 : 0)) + 64));
+    uint64_t *tmp_klo = static_cast<uint64_t *>(b->tmp_elems.p);
+    uint64_t *tmp_khi = hi128 ? tmp_klo + e_cap : nullptr;
+    uint32_t *tmp_min = reinterpret_cast<uint32_t *>(tmp_klo + e_cap * (hi128 ? 2 : 1));
     PP_CK(b->body.ensure(body_cap));
     body_cap = b->body.cap;
+    PP_CK(b->tmp_body.ensure(body_cap));
     PP_CK(b->big.ensure(big_cap));
     big_cap = b->big.cap;
     uint32_t launched = 0;
@@ -1534,8 +1591,9 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     BucketArgs ba{};
     ba.packed = in.d_packed; ba.pieces = pieces; ba.order = order; ba.skey32 = skey32; ba.skey64 = skey64; ba.pp = pp;
     ba.pieces_cap = p_cap; ba.k = k; ba.m = m; ba.input_shift = input_shift; ba.abundance = in.abundance;
-    ba.lb_bytes = lb_bytes; ba.lb_elems = lb_elems; ba.body = static_cast<uint8_t *>(b->body.p); ba.body_cap = body_cap;
-    ba.el_min = el_min; ba.el_klo = el_klo; ba.el_khi = el_khi; ba.elems_cap = e_cap;
+    ba.g_tb = g_tb; ba.g_nb = g_nb; ba.g_te = g_te; ba.g_ne = g_ne;
+    ba.tmp_body = static_cast<uint8_t *>(b->tmp_body.p); ba.body_cap = body_cap;
+    ba.tmp_min = tmp_min; ba.tmp_klo = tmp_klo; ba.tmp_khi = tmp_khi; ba.elems_cap = e_cap;
     ba.in_first_byte = in_fb; ba.in_first_elem = in_fe; ba.big_pool = static_cast<uint8_t *>(b->big.p); ba.big_cap = big_cap;
     ba.cnt = cnt;
     static const bool pp_debug = getenv("SPSP_PP_DEBUG") != nullptr;
@@ -1556,6 +1614,16 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     if (hi128) pp_bucket_kernel<true><<<(unsigned)n_groups, BK_THREADS, bk_smem, st>>>(ba);
     else pp_bucket_kernel<false><<<(unsigned)n_groups, BK_THREADS, bk_smem, st>>>(ba);
     launched++;
+    PP_CK(cudaGetLastError());
+    // ---- final offsets (groups are in bucket order) and the move of every group's output to its final place
+    pp_offsets_kernel<<<1, 1024, 0, st>>>(g_nb, g_ne, g_bb, g_be, n_groups, cnt);
+    {
+        const uint64_t grid = n_groups + (nin + 255) / 256;
+        pp_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(g_tb, g_nb, g_te, g_ne, g_bb, g_be, n_groups, ba.tmp_body,
+                                                        static_cast<uint8_t *>(b->body.p), body_cap, tmp_min, tmp_klo, tmp_khi, el_min,
+                                                        el_klo, el_khi, e_cap, in_fb, in_fe, (uint32_t)nin, cnt);
+    }
+    launched += 2;
     PP_CK(cudaGetLastError());
     // ---- results to the host: ONE synchronisation in the steady state.  The counters and per-input arrays travel as
     // one block; the sketch bytes are copied speculatively, sized by the previous batch, and topped up if this batch
@@ -1584,9 +1652,15 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
             for (int i = 1; i <= 10; i++) ph[i] += (double)(r[i] - r[i - 1]);
         }
         fprintf(stderr, "[pp] groups %.0f  entries/grp %.0f uniques %.0f buckets %.1f | cycles per group:", n, e / n, u / n, nb / n);
-        const char *nm[11] = {"", "pieces", "entries", "insert", "unique", "adjacency", "walk", "elemflag+scan", "lookback", "publish", "emit"};
+        const char *nm[11] = {"", "pieces", "entries", "insert", "unique", "adjacency", "walk", "elemflag+scan", "stage bytes + ranges", "elements out", "bytes out"};
         for (int i = 1; i <= 10; i++) fprintf(stderr, " %s %.0f", nm[i], ph[i] / n);
-        fprintf(stderr, "\n");
+        double f11 = 0;
+        for (uint64_t g = 0; g < n_groups; g++) {
+            const long long *r = &h[g * 16];
+            if (!r[0] || !r[10]) continue;
+            f11 += (double)(r[11] - r[6]);
+        }
+        fprintf(stderr, " | element flags alone %.0f\n", f11 / n);
     }
     const uint64_t n_hits = *reinterpret_cast<const uint64_t *>(hs + small_bytes);
     out->n_hits = n_hits;
@@ -1598,7 +1672,7 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     if (n_hits > H) { out->retry = PP_RETRY_HITS; return cudaSuccess; }      // the caller grows the hit buffer and rescans
     if (hc.overflow) {
         if (hc.overflow & OVF_PIECES) b->pieces_cap_min = hc.n_pieces + hc.n_pieces / 8 + 1024;
-        if (hc.overflow & OVF_BODY) b->body_cap_min = hc.body_bytes + hc.body_bytes / 8 + 4096;
+        if (hc.overflow & OVF_BODY) b->body_cap_min = hc.tmp_bytes + hc.tmp_bytes / 8 + 4096;     // (the demand of every group)
         if (hc.overflow & OVF_BIG) b->big_cap_min = hc.big_top + hc.big_top / 8 + 4096;
         if (hc.overflow & OVF_SORT) b->force_large_sort = true;
         if (hc.overflow & OVF_ELEMS) return cudaErrorUnknown;                 // cannot happen: the bound is exact
