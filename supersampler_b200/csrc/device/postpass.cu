@@ -602,6 +602,11 @@ struct BucketArgs {
     // the group kernel by decoupled look-back: every group then waited, holding its SM slot, for all running
     // predecessors to reach the same point -- 40 k of its 134 k cycles.)
     unsigned long long *g_tb, *g_nb, *g_te, *g_ne;   // [groups] temp byte offset / bytes, temp element offset / elements
+    // Small batches (the one-CTA sort path, <= 32 K hits) keep the decoupled look-back: there the two extra launches
+    // of the two-pass form cost more than the waiting (64 x 5 Mbp batches: value 1 291 vs 1 417 Gbp/s on one box);
+    // then lb_* are the look-back states and tmp_* point at the final arrays.  Large batches: 3.70 -> 3.50 ms per
+    // 1 Gbp at s = 100, 2.3 -> 1.0 ms per 1 Gbp read set with the two-pass form.
+    unsigned long long *lb_bytes, *lb_elems;
     uint8_t *tmp_body;
     uint64_t body_cap;
     uint32_t *tmp_min;
@@ -761,6 +766,36 @@ __device__ __forceinline__ K128 kmer_neighbour(const K128 &cur, bool left, int t
         nx.lo &= kmask.lo; nx.hi &= kmask.hi;
     }
     return nx;
+}
+
+// Decoupled look-back over the groups' aggregates: returns the sum of the aggregates of groups < g and
+// leaves this group's inclusive prefix for its successors.  state = flag << 62 | value (flag 1 = aggregate,
+// 2 = inclusive prefix); called by one full warp.
+__device__ unsigned long long lookback(unsigned long long *state, uint32_t g, unsigned long long agg)
+{
+    const int lane = threadIdx.x & 31;
+    volatile unsigned long long *vs = state;
+    if (lane == 0) vs[g] = ((g == 0 ? 2ULL : 1ULL) << 62) | agg;
+    unsigned long long excl = 0;
+    if (g == 0) return 0;
+    long long j = (long long)g - 1;
+    for (;;) {
+        const long long idx = j - lane;
+        unsigned long long v = 2ULL << 62;                       // before group 0: inclusive prefix 0
+        if (idx >= 0) {
+            do { v = vs[idx]; } while ((v >> 62) == 0);
+        }
+        const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;
+        unsigned long long part = (lane <= first_inc) ? (v & ((1ULL << 62) - 1)) : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        excl += part;
+        if (inc_mask) break;
+        j -= 32;
+    }
+    if (lane == 0) vs[g] = (2ULL << 62) | (excl + agg);
+    return excl;
 }
 
 // Leftmost occurrence of the minimizer in codes sk[0, len), -1 if none (one thread).
@@ -1159,6 +1194,30 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
     constexpr uint32_t STAGE_CAP = BK_ECAP * 8;
     const bool staged = sizeof(IDX) == 2 && bytes_total <= STAGE_CAP;
     uint8_t *stage = reinterpret_cast<uint8_t *>(g.e_lo);
+    if (a.lb_bytes) {
+        // small batches: final offsets by decoupled look-back (warp 0), hidden behind the writer warps
+        if (warp == 0) {
+            const unsigned long long x = lookback(a.lb_bytes, grp, bytes_total);
+            if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 2) = x; }
+            const unsigned long long y = lookback(a.lb_elems, grp, NE);
+            if (lane == 0) { *reinterpret_cast<unsigned long long *>(s_misc + 4) = y; }
+        } else if (staged) {
+            emit_buckets(stage, (uint32_t)warp - 1, BK_WARPS - 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long bb = *reinterpret_cast<unsigned long long *>(s_misc + 2);
+            const unsigned long long eb = *reinterpret_cast<unsigned long long *>(s_misc + 4);
+            atomicAdd(&a.cnt->body_bytes, (unsigned long long)bytes_total);
+            atomicAdd(&a.cnt->n_elems, (unsigned long long)NE);
+            atomicAdd(&a.cnt->tmp_bytes, (unsigned long long)bytes_total);
+            atomicAdd(&a.cnt->n_buckets, (unsigned long long)NB);
+            unsigned ovf = 0;
+            if (bb + bytes_total > a.body_cap) ovf |= OVF_BODY;
+            if (eb + NE > a.elems_cap) ovf |= OVF_ELEMS;
+            if (ovf) atomicOr(&a.cnt->overflow, ovf);
+        }
+    } else {
     if (staged) emit_buckets(stage, (uint32_t)warp, BK_WARPS);
     // ---- temporary output ranges
     if (threadIdx.x == 0) {
@@ -1174,6 +1233,7 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
         else { a.g_tb[grp] = tb; a.g_nb[grp] = bytes_total; a.g_te[grp] = te; a.g_ne[grp] = NE; }
     }
     __syncthreads();
+    }
     const unsigned long long byte_base = *reinterpret_cast<unsigned long long *>(s_misc + 2);
     const unsigned long long elem_base = *reinterpret_cast<unsigned long long *>(s_misc + 4);
     PP_PHASE(8);
@@ -1184,8 +1244,13 @@ __device__ void process_group(const BucketArgs &a, GroupMem<IDX> &g, uint32_t gr
         const uint32_t hp = first + g.b_hp[b];
         const uint64_t in = bucket_key(hp) >> a.input_shift;
         if (hp == 0 || (bucket_key(hp - 1) >> a.input_shift) != in) {
-            a.in_first_byte[in] = ((unsigned long long)(grp + 1) << 32) | g.b_bytes[b];
-            a.in_first_elem[in] = ((unsigned long long)(grp + 1) << 32) | (g.e_slot[g.b_us[b]] >> 1);
+            if (a.lb_bytes) {
+                a.in_first_byte[in] = byte_base + g.b_bytes[b] + 1;                  // + 1: 0 means "no bucket"
+                a.in_first_elem[in] = elem_base + (g.e_slot[g.b_us[b]] >> 1) + 1;
+            } else {
+                a.in_first_byte[in] = ((unsigned long long)(grp + 1) << 32) | g.b_bytes[b];
+                a.in_first_elem[in] = ((unsigned long long)(grp + 1) << 32) | (g.e_slot[g.b_us[b]] >> 1);
+            }
         }
     }
     // ---- elements
@@ -1228,7 +1293,16 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
     auto bucket_key = [&](uint32_t i) -> uint64_t { return a.skey64 ? a.skey64[i] : (uint64_t)a.skey32[i]; };
     auto is_head = [&](uint32_t i) { return i == 0 || bucket_key(i) != bucket_key(i - 1); };
     const uint64_t lo64 = (uint64_t)grp * a.pp;
-    if (lo64 >= n_pieces) return;                                // behind the data (the group arrays are zeroed)
+    auto publish_empty = [&]() {
+        if (a.lb_bytes && warp == 0) { lookback(a.lb_bytes, grp, 0); lookback(a.lb_elems, grp, 0); }
+    };
+    if (lo64 >= n_pieces) {                                      // behind the data: nothing looks back at these groups
+        if (a.lb_bytes && threadIdx.x == 0) {
+            reinterpret_cast<volatile unsigned long long *>(a.lb_bytes)[grp] = 1ULL << 62;
+            reinterpret_cast<volatile unsigned long long *>(a.lb_elems)[grp] = 1ULL << 62;
+        }
+        return;
+    }
     const uint32_t lo = (uint32_t)lo64, nominal_end = (uint32_t)min((uint64_t)n_pieces, lo64 + a.pp);
     if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_end = n_pieces; }
     __syncthreads();
@@ -1236,7 +1310,7 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
         if (is_head(i)) atomicMin(&s_first, i);
     __syncthreads();
     const uint32_t first = s_first;
-    if (first == 0xFFFFFFFFu) return;                            // no bucket starts in this group's range
+    if (first == 0xFFFFFFFFu) { publish_empty(); return; }       // no bucket starts in this group's range
     // the group ends where the first bucket of a later range starts
     for (uint32_t b0 = nominal_end; b0 < n_pieces; b0 += BK_THREADS) {
         const uint32_t i = b0 + threadIdx.x;
@@ -1276,6 +1350,7 @@ __global__ void __launch_bounds__(BK_THREADS) pp_bucket_kernel(BucketArgs a)
         __syncthreads();
         if (off + need > a.big_cap) {
             if (threadIdx.x == 0) atomicOr(&a.cnt->overflow, (unsigned)OVF_BIG);
+            publish_empty();
             return;
         }
         group_carve<uint32_t>(g, a.big_pool + off, np, E, S, HI);
@@ -1536,13 +1611,13 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     uint64_t *el_klo = static_cast<uint64_t *>(b->elems.p);
     uint64_t *el_khi = hi128 ? el_klo + e_cap : nullptr;
     uint32_t *el_min = reinterpret_cast<uint32_t *>(el_klo + e_cap * (hi128 ? 2 : 1));
-    PP_CK(b->tmp_elems.ensure(e_cap * (4 + 8 + (hi128 ? 8 : 0)) + 64));
+    if (!small_hits) PP_CK(b->tmp_elems.ensure(e_cap * (4 + 8 + (hi128 ? 8 : 0)) + 64));
     uint64_t *tmp_klo = static_cast<uint64_t *>(b->tmp_elems.p);
     uint64_t *tmp_khi = hi128 ? tmp_klo + e_cap : nullptr;
     uint32_t *tmp_min = reinterpret_cast<uint32_t *>(tmp_klo + e_cap * (hi128 ? 2 : 1));
     PP_CK(b->body.ensure(body_cap));
     body_cap = b->body.cap;
-    PP_CK(b->tmp_body.ensure(body_cap));
+    if (!small_hits) PP_CK(b->tmp_body.ensure(body_cap));
     PP_CK(b->big.ensure(big_cap));
     big_cap = b->big.cap;
     uint32_t launched = 0;
@@ -1591,9 +1666,16 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     BucketArgs ba{};
     ba.packed = in.d_packed; ba.pieces = pieces; ba.order = order; ba.skey32 = skey32; ba.skey64 = skey64; ba.pp = pp;
     ba.pieces_cap = p_cap; ba.k = k; ba.m = m; ba.input_shift = input_shift; ba.abundance = in.abundance;
-    ba.g_tb = g_tb; ba.g_nb = g_nb; ba.g_te = g_te; ba.g_ne = g_ne;
-    ba.tmp_body = static_cast<uint8_t *>(b->tmp_body.p); ba.body_cap = body_cap;
-    ba.tmp_min = tmp_min; ba.tmp_klo = tmp_klo; ba.tmp_khi = tmp_khi; ba.elems_cap = e_cap;
+    const bool two_pass = !small_hits;                 // see BucketArgs
+    ba.g_tb = g_tb; ba.g_nb = g_nb; ba.g_te = g_te; ba.g_ne = g_ne; ba.body_cap = body_cap; ba.elems_cap = e_cap;
+    if (two_pass) {
+        ba.tmp_body = static_cast<uint8_t *>(b->tmp_body.p);
+        ba.tmp_min = tmp_min; ba.tmp_klo = tmp_klo; ba.tmp_khi = tmp_khi;
+    } else {
+        ba.lb_bytes = g_tb; ba.lb_elems = g_te;        // (zeroed with the group arrays)
+        ba.tmp_body = static_cast<uint8_t *>(b->body.p);
+        ba.tmp_min = el_min; ba.tmp_klo = el_klo; ba.tmp_khi = el_khi;
+    }
     ba.in_first_byte = in_fb; ba.in_first_elem = in_fe; ba.big_pool = static_cast<uint8_t *>(b->big.p); ba.big_cap = big_cap;
     ba.cnt = cnt;
     static const bool pp_debug = getenv("SPSP_PP_DEBUG") != nullptr;
@@ -1616,14 +1698,14 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     launched++;
     PP_CK(cudaGetLastError());
     // ---- final offsets (groups are in bucket order) and the move of every group's output to its final place
-    pp_offsets_kernel<<<1, 1024, 0, st>>>(g_nb, g_ne, g_bb, g_be, n_groups, cnt);
-    {
+    if (two_pass) {
+        pp_offsets_kernel<<<1, 1024, 0, st>>>(g_nb, g_ne, g_bb, g_be, n_groups, cnt);
         const uint64_t grid = n_groups + (nin + 255) / 256;
         pp_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(g_tb, g_nb, g_te, g_ne, g_bb, g_be, n_groups, ba.tmp_body,
                                                         static_cast<uint8_t *>(b->body.p), body_cap, tmp_min, tmp_klo, tmp_khi, el_min,
                                                         el_klo, el_khi, e_cap, in_fb, in_fe, (uint32_t)nin, cnt);
+        launched += 2;
     }
-    launched += 2;
     PP_CK(cudaGetLastError());
     // ---- results to the host: ONE synchronisation in the steady state.  The counters and per-input arrays travel as
     // one block; the sketch bytes are copied speculatively, sized by the previous batch, and topped up if this batch

@@ -5,8 +5,8 @@
 set -u
 O=gpurun_out
 NCU="ncu --set full --import-source on --clock-control none"
-python bench.py --impl reference --steps 2 --warmup 1 > $O/ev_bench_ref.json 2> $O/ev_bench_ref.err
-python bench.py > $O/ev_bench_n1.json 2> $O/ev_bench_n1.err || { tail -5 $O/ev_bench_n1.err; exit 1; }
+python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > $O/ev_bench_ref.json 2> $O/ev_bench_ref.err
+python bench.py --gpus 1 --steps 20 --warmup 5 > $O/ev_bench_n1.json 2> $O/ev_bench_n1.err || { tail -5 $O/ev_bench_n1.err; exit 1; }
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/ev_tests.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $O/ev_smoke.txt 2>&1
 for cfg in "64 1000 3 11" "64 100 3 11" "200 100 3 11" "64 200 3 13"; do
