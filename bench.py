@@ -57,6 +57,12 @@ import numpy as np  # noqa: E402
 
 METRIC = "sketch_gbp_per_s"
 UNIT = "Gbp/s"
+ALL_CORES = os.sched_getaffinity(0)          # before a rank confines itself to its share of the cores
+
+
+def _all_cores():
+    """preexec_fn of the reference's processes: they get every core of the box, whatever this rank is bound to."""
+    os.sched_setaffinity(0, ALL_CORES)
 
 
 def log(*a):
@@ -206,7 +212,8 @@ def ref_sketch(paths, k, m, s, wd, cores):
         f.write("\n".join(paths) + "\n")
     t0 = time.perf_counter()
     subprocess.run([os.path.join(O.REF_DIR, "sub_sampler"), "-f", fof, "-k", str(k), "-m", str(m), "-s", str(s),
-                    "-t", str(cores), "-v", "0"], cwd=wd, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, check=True)
+                    "-t", str(cores), "-v", "0"], cwd=wd, stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, check=True,
+                   preexec_fn=_all_cores)
     t = time.perf_counter() - t0
     return t, [os.path.join(wd, "subsampled_" + os.path.basename(p).split(".")[0] + ".gz") for p in paths]
 
@@ -224,7 +231,7 @@ def ref_compare(sketch_paths, wd, tag="res", queries=None):
             f.write("\n".join(queries) + "\n")
         cmd += ["-q", qf]
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, cwd=wd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, text=True, check=True)
+    r = subprocess.run(cmd, cwd=wd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, text=True, check=True, preexec_fn=_all_cores)
     t = time.perf_counter() - t0
     lasted = None
     for ln in r.stdout.splitlines():
