@@ -30,8 +30,9 @@ the G sketches all-vs-all.
           CSV matrices byte for byte (`parity_vs_reference`).
   extra : BASELINE configs 3, 4, 5 at their stated sizes, once, outside the
           headline regions, inputs synthesised on the device, each with its own
-          parity block against oracle/_ref (N > 1: config 3 only, as one fixed
-          job over the ranks = the strong-scaling figure).
+          parity block against oracle/_ref (N > 1: configs 3 and 5, each as one
+          fixed job over the ranks = the strong-scaling figures; config 5
+          through the query-mode exchange).
 
 Launch:  python bench.py --gpus N --steps K --warmup W        (N=1)
          python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -612,38 +613,67 @@ def extra_c4(S, SD, local_rank, cores, threads, quick):
     return out
 
 
-def extra_c5(S, SD, local_rank, cores, quick):
+def extra_c5(S, SD, rank, world, dist, local_rank, cores, quick):
     """BASELINE config 5: 100 query sketches vs 10 000 reference sketches, k31 m13 s200, `-q` mode:
-    10 100 x 5 Mbp genomes sketched from HBM in 1 Gbp batches, Q x N compare on the device.
+    10 100 x 5 Mbp genomes sketched from HBM in 1 Gbp batches, Q x N compare on the device.  On several GPUs the
+    job is dealt over the ranks (rank 0: the queries + its share of the references, the others their shares; the
+    union is in the comparator's order, queries first) and compared by the query-mode exchange of the C ABI
+    (spsp_cmp_exchange: only the Q x N rows exist anywhere).
     Parity: reference sub_sampler on the 100 queries + the first 156 references, reference
     `comparator -q` on those 256; our Q x 256 block of the full answer must give the same CSV bytes."""
     import torch
+    from supersampler_b200 import distributed as D
     from oracle import oracle as O
     k, m, s = 31, 13, 200.0
     Q, R, nb = (10, 150, 1_000_000) if quick else (100, 10_000, 5_000_000)
     N = Q + R
+    per = R // world
+    g0 = 0 if rank == 0 else Q + rank * per                       # first genome of this rank
+    n_loc = (Q + per if rank == 0 else per) + (R - per * world if rank == world - 1 else 0)
     fam = SD.DeviceFamily(nb, seed=555)
     ctx = S.DeviceContext(k, m, S.threshold(k, m, s), device=local_rank)
     rs = ResidentSet(ctx, k, m, s)
     bsz = max(1, min(200, (1 << 30) // (SD.words_per_input(nb) * 16)))
-    nw = min(bsz, N)                                     # warm context: one untimed batch of the job's shape
-    b0 = fam.packed_batch(0, nw)
+    nw = min(bsz, n_loc)                                 # warm context: one untimed batch of the job's shape
+    b0 = fam.packed_batch(g0, nw)
     ctx.sketch_batch(None, *b0[1:], nw, s, device_ptr=b0[0].data_ptr())
     del b0
-    for a in range(0, N, bsz):
-        cnt = min(bsz, N - a)
+    for a in range(g0, g0 + n_loc, bsz):
+        cnt = min(bsz, g0 + n_loc - a)
         buf, n_total, rb, re_, ri = fam.packed_batch(a, cnt)
         rs.add_batch(buf, n_total, rb, re_, ri, cnt)
         del buf
-    inter, sizes, t_cmp, cmp_ms = rs.compare(query_size=Q)
+    t_sk = rs.sketch_s
+    first_cmp = None
+    if dist is None:
+        inter, sizes, t_cmp, cmp_ms = rs.compare(query_size=Q)
+        first_cmp = rs.compare_first_call_s
+    else:
+        D.join_contexts(ctx, rank, world)
+        sizes_l, mn, lo = rs.elements()
+        for _ in range(2):                               # warm context: the first call also sizes the exchange buffers
+            cinfo = {}
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            inter, sizes = ctx.cmp_exchange(sizes_l, mn.data_ptr(), lo.data_ptr(), None, Q if rank == 0 else 0, Q, N, rank, cinfo)
+            tt = torch.tensor([time.perf_counter() - t0, cinfo.get("kernel_ms", 0.0), t_sk], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            first_cmp = float(tt[0]) if first_cmp is None else first_cmp
+        t_cmp, cmp_ms, t_sk = float(tt[0]), float(tt[1]), float(tt[2])
+        if rank != 0:
+            ctx.close()
+            return None
     pairs = Q * R
-    out = {"workload": f"C5: {Q} queries vs {R} references ({N} x {nb} bp genomes), k{k} m{m} s{int(s)}, -q mode",
-           "sketch_gbp_per_s": N * nb / rs.sketch_s / 1e9, "sketch_s": rs.sketch_s, "scan_ms": rs.scan_ms,
+    out = {"workload": f"C5: {Q} queries vs {R} references ({N} x {nb} bp genomes), k{k} m{m} s{int(s)}, -q mode"
+                       + (f", one fixed job over {world} GPUs (query-mode exchange)" if world > 1 else ""),
+           "sketch_gbp_per_s": N * nb / t_sk / 1e9, "sketch_s": t_sk, "scan_ms": rs.scan_ms,
            "postpass_ms": rs.post_ms, "batches": rs.batches, "kernel": _kernel_name(ctx.filter_info()),
-           "elements": int(sizes.sum()), "compare_s": t_cmp, "compare_first_call_s": rs.compare_first_call_s,
+           "elements": int(sizes.sum()), "compare_s": t_cmp, "compare_first_call_s": first_cmp,
            "compare_kernel_ms": cmp_ms, "query_ref_pairs": pairs,
            "pairs_per_s": pairs / t_cmp, "kernel_pairs_per_s": pairs / max(1e-9, cmp_ms * 1e-3),
-           "value_gbp_per_s": N * nb / (rs.sketch_s + t_cmp) / 1e9}
+           "value_gbp_per_s": N * nb / (t_sk + t_cmp) / 1e9}
+    if world > 1:
+        out["scaling"] = "strong"
     if O.have_ref():
         n_ref = min(156, R)
         sel = list(range(Q + n_ref))                    # queries first, then references: the comparator's order
@@ -674,13 +704,13 @@ def extra_c5(S, SD, local_rank, cores, quick):
 
 def run_extras(S, rank, world, dist, local_rank, cores, threads, args):
     """C3 / C4 / C5 of BASELINE.json at their stated sizes, run once, outside the headline timed regions.
-    N > 1: C3 only (a fixed job over the ranks: the strong-scaling figure)."""
+    N > 1: C3 and C5, each as one fixed job over the ranks (the strong-scaling figures); C4 has no exchange."""
     import torch
     from supersampler_b200 import synth_device as SD
     extra = {}
     todo = [c for c in args.extras.split(",") if c]
     for name in todo:
-        if name != "c3" and world > 1:
+        if name == "c4" and world > 1:               # (a sketch-only config: it shards by file, nothing to exchange)
             continue
         t0 = time.perf_counter()
         try:
@@ -689,7 +719,7 @@ def run_extras(S, rank, world, dist, local_rank, cores, threads, args):
             elif name == "c4":
                 r = extra_c4(S, SD, local_rank, cores, threads, args.quick_extras)
             elif name == "c5":
-                r = extra_c5(S, SD, local_rank, cores, args.quick_extras)
+                r = extra_c5(S, SD, rank, world, dist, local_rank, cores, args.quick_extras)
             else:
                 continue
         except Exception as ex:                      # an extra must not take the headline line with it
