@@ -957,6 +957,7 @@ extern "C" int spsp_batch_upload_idle(spsp_ctx *c, int slot, int lane, int *idle
 {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || lane < 0 || lane > 1 || !idle)
         return fail(-3, "spsp_batch_upload_idle: bad ctx/slot/lane");
+    CK(cudaSetDevice(c->device));
     const cudaError_t e = cudaStreamQuery(c->slots[slot].raw_stream[lane]);
     if (e != cudaSuccess && e != cudaErrorNotReady) return fail(-1, std::string("cudaStreamQuery: ") + cudaGetErrorString(e));
     *idle = e == cudaSuccess ? 1 : 0;

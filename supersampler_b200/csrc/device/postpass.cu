@@ -1611,10 +1611,14 @@ cudaError_t postpass_run(PostpassBuffers *b, const PostpassIn &in, PostpassOut *
     uint64_t *el_klo = static_cast<uint64_t *>(b->elems.p);
     uint64_t *el_khi = hi128 ? el_klo + e_cap : nullptr;
     uint32_t *el_min = reinterpret_cast<uint32_t *>(el_klo + e_cap * (hi128 ? 2 : 1));
-    if (!small_hits) PP_CK(b->tmp_elems.ensure(e_cap * (4 + 8 + (hi128 ? 8 : 0)) + 64));
-    uint64_t *tmp_klo = static_cast<uint64_t *>(b->tmp_elems.p);
-    uint64_t *tmp_khi = hi128 ? tmp_klo + e_cap : nullptr;
-    uint32_t *tmp_min = reinterpret_cast<uint32_t *>(tmp_klo + e_cap * (hi128 ? 2 : 1));
+    uint64_t *tmp_klo = nullptr, *tmp_khi = nullptr;
+    uint32_t *tmp_min = nullptr;
+    if (!small_hits) {                                 // the two-pass form's temporary element ranges
+        PP_CK(b->tmp_elems.ensure(e_cap * (4 + 8 + (hi128 ? 8 : 0)) + 64));
+        tmp_klo = static_cast<uint64_t *>(b->tmp_elems.p);
+        tmp_khi = hi128 ? tmp_klo + e_cap : nullptr;
+        tmp_min = reinterpret_cast<uint32_t *>(tmp_klo + e_cap * (hi128 ? 2 : 1));
+    }
     PP_CK(b->body.ensure(body_cap));
     body_cap = b->body.cap;
     if (!small_hits) PP_CK(b->tmp_body.ensure(body_cap));
