@@ -165,7 +165,10 @@ static int next_record(const uint8_t *txt, size_t n, size_t *pos, int *eof, buf_
     if (p < n) p++; else *eof = 1;              /* hit EOF inside getline */
     for (;;) {
         if (p >= n) { *eof = 1; break; }        /* peek() == EOF sets eofbit */
-        if (txt[p] == '>') break;
+        /* utils.cpp:709-713 holds peek() in a (signed) char and compares it with EOF: a line that starts with the
+         * byte 0xFF ends the record exactly like one that starts with '>' (and is then consumed as a header line) --
+         * verified against the reference binary, tests/golden case "ffline" */
+        if (txt[p] == '>' || txt[p] == 0xFF) break;
         size_t q = p;
         while (q < n && txt[q] != '\n') q++;
         for (size_t i = p; i < q; i++) {

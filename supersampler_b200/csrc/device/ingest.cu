@@ -2,8 +2,9 @@
 // 2-bit packing (utils.cpp:13-16) as three streaming passes over raw text resident in HBM.
 //
 //   text semantics (same as the host packer, csrc/host/seqio.cpp):
-//     * the first line of an input and every line that starts with '>' is a header line: it starts a record and
-//       none of its bytes are sequence;
+//     * the first line of an input and every line that starts with '>' -- or with the byte 0xFF, which the
+//       reference's `char c = peek(); c != EOF` (utils.cpp:709-713) cannot tell from the end of the file -- is a
+//       header line: it starts a record and none of its bytes are sequence;
 //     * on every other line the bytes ACGTacgt are bases (code (c >> 1) & 3: A0 C1 T2 G3), every other byte is
 //       deleted, so its neighbours become adjacent;
 //     * a record is the run of bases between two header lines (it may be empty; records shorter than k are kept
@@ -44,7 +45,7 @@ __device__ __forceinline__ uint32_t gather4(uint32_t m)      // 0xFF/0x00 per by
 __device__ __forceinline__ void classify_word(uint32_t w, uint32_t &nl, uint32_t &gt, uint32_t &base)
 {
     nl = gather4(__vcmpeq4(w, 0x0A0A0A0Au));
-    gt = gather4(__vcmpeq4(w, 0x3E3E3E3Eu));
+    gt = gather4(__vcmpeq4(w, 0x3E3E3E3Eu) | __vcmpeq4(w, 0xFFFFFFFFu));     // '>' or 0xFF: header when first on a line
     const uint32_t lo = w | 0x20202020u;
     const uint32_t b = __vcmpeq4(lo, 0x61616161u) | __vcmpeq4(lo, 0x63636363u) | __vcmpeq4(lo, 0x67676767u) |
                        __vcmpeq4(lo, 0x74747474u);

@@ -165,6 +165,7 @@ static inline const uint8_t *pack_blocks(const uint8_t *p, const uint8_t *end, u
     const __m256i lut = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1,
                                          -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, -1, -1);
     const __m256i up = _mm256_set1_epi8((char)0xDF), three = _mm256_set1_epi8(3), gt = _mm256_set1_epi8('>');
+    const __m256i ones = _mm256_set1_epi8((char)0xFF);
     const __m256i w14 = _mm256_set1_epi16(0x0401), w116 = _mm256_set1_epi32(0x00100001);
     const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
                                           0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
@@ -173,8 +174,8 @@ static inline const uint8_t *pack_blocks(const uint8_t *p, const uint8_t *end, u
         pack_prefetch(p);
         const uint32_t okm = (uint32_t)_mm256_movemask_epi8(
             _mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, c), _mm256_and_si256(c, up)));
-        // '>' is not a base: only a block with a deleted byte can hold one
-        if (okm != 0xFFFFFFFFu && _mm256_movemask_epi8(_mm256_cmpeq_epi8(c, gt))) break;
+        // '>' (and 0xFF, see LINE_START below) is not a base: only a block with a deleted byte can hold one
+        if (okm != 0xFFFFFFFFu && _mm256_movemask_epi8(_mm256_or_si256(_mm256_cmpeq_epi8(c, gt), _mm256_cmpeq_epi8(c, ones)))) break;
         const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(c, 1), three);
         const __m256i b4 = _mm256_madd_epi16(_mm256_maddubs_epi16(codes, w14), w116);   // byte = c0 + 4 c1 + 16 c2 + 64 c3
         const __m256i pk = _mm256_shuffle_epi8(b4, pick);
@@ -213,8 +214,8 @@ static const uint8_t *pack_blocks_avx512(const uint8_t *p, const uint8_t *end, u
         const __m512i c = _mm512_loadu_si512(p);
         pack_prefetch(p);
         const uint64_t ok = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(lut, c), _mm512_and_si512(c, up));
-        // '>' is not a base: only a block with a deleted byte can hold one
-        if (ok != ~0ULL && _mm512_cmpeq_epi8_mask(c, gt)) break;
+        // '>' (and 0xFF) is not a base: only a block with a deleted byte can hold one
+        if (ok != ~0ULL && (_mm512_cmpeq_epi8_mask(c, gt) | _mm512_cmpeq_epi8_mask(c, _mm512_set1_epi8((char)0xFF)))) break;
         const __m512i z = _mm512_maskz_compress_epi8(ok, c);                                // bases first, zeros behind
         const __m512i codes = _mm512_and_si512(_mm512_srli_epi16(z, 1), three);
         const __m512i b4 = _mm512_madd_epi16(_mm512_maddubs_epi16(codes, w14), w116);       // byte = c0 + 4 c1 + 16 c2 + 64 c3
@@ -313,7 +314,9 @@ void FastaPacker::feed_piece(const uint8_t *p, size_t n)
             p = static_cast<const uint8_t *>(nl) + 1;
             state_ = LINE_START;
         } else {  // LINE_START
-            if (*p == '>') {
+            // a line that starts with '>' -- or with the byte 0xFF, which the reference's `char c = peek(); c != EOF`
+            // (utils.cpp:709-713) cannot tell from the end of the file -- is a header line and starts a record
+            if (*p == '>' || *p == 0xFF) {
                 acc_ = acc; fill_ = fill; word_idx_ = widx; out_.n_bases = nb;
                 end_record();
                 acc = acc_; fill = fill_; widx = word_idx_; nb = out_.n_bases;

@@ -31,6 +31,9 @@ def build_input(name: str) -> bytes:
     if name == "noheader":                 # first line is always dropped (utils.cpp:708)
         return synth.random_genome(500, 21).tobytes() + b"\n" + synth.random_genome(700, 22).tobytes() + b"\n>x\n" \
             + synth.random_genome(300, 23).tobytes()
+    if name == "ffline":                   # lines that start with the byte 0xFF end a record like '>' lines do
+        g = [synth.random_genome(n, 40 + i).tobytes() for i, n in enumerate((400, 400, 400, 90, 250))]
+        return (b">r1\n" + g[0] + b"\n\xff" + g[1] + b"\n" + g[2] + b"\n\xff\n" + g[3][:45] + b"\xff" + g[3][45:] + b"\n>r2\n\xffNNN\n" + g[4])
     if name == "empty":
         return b""
     if name == "tiny":
@@ -60,6 +63,7 @@ SKETCH_CASES = {
     "multi_k31_m11_s20": ("multi", 31, 11, 20, 1),
     "multi_k21_m9_s5": ("multi", 21, 9, 5, 1),
     "noheader_k31_m11_s4": ("noheader", 31, 11, 4, 1),
+    "ffline_k31_m11_s4": ("ffline", 31, 11, 4, 1),
     "empty_k31_m11_s1000": ("empty", 31, 11, 1000, 1),
     "tiny_k31_m11_s1000": ("tiny", 31, 11, 1000, 1),
     "wrap256_k31_m11_s1": ("wrap256", 31, 11, 1, 1),
