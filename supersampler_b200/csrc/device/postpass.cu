@@ -6,9 +6,10 @@
 //        ──S2 stable sort of the PIECES by bucket (input, minimizer)──▶ B bucket-group kernel:
 //        a CTA stages a run of whole buckets in shared memory and does everything the
 //        reference does per bucket there (k-mer entries, first-occurrence de-dup with uint8
-//        counts, neighbour table, greedy chains, byte sizes, canonical elements), obtains its
-//        global byte / element offsets by decoupled look-back and writes the sketch bytes and
-//        the compare elements at their final place.
+//        counts, neighbour table, greedy chains, byte sizes, canonical elements) and writes the
+//        sketch bytes and the compare elements -- small batches at their final place, found by
+//        decoupled look-back; large batches to ranges drawn from bump allocators that
+//        pp_offsets_kernel + pp_gather_kernel then put in bucket order (see BucketArgs).
 //
 // Sorting pieces (one per super-k-mer) instead of k-mer entries (k-m+1 times as many) and
 // de-duplicating inside a shared-memory table instead of a global one is what makes the pass
