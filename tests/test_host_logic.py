@@ -289,3 +289,20 @@ def test_cpulist_and_numa_binding_is_safe():
     before = os.sched_getaffinity(0)
     info = D.bind_rank_to_gpu_cores(0, 2, ["00000000:FF:1F.7", "00000000:FE:1F.7"])      # no such devices: must stay unbound
     assert info["bound"] is False and os.sched_getaffinity(0) == before
+
+
+def test_truncated_gzip_is_not_a_partial_success(tmp_path, capfd):
+    """A gzip stream that ends early or is corrupt must read as "cannot open", never as a shorter file (the
+    reference's zstr throws there): checked through sortCSV, the CPU-only consumer of the shared reader."""
+    import gzip
+    jac = open(os.path.join(GOLDEN_DIR, "fam12_s100.jaccard.csv"), "rb").read()
+    order = open(os.path.join(GOLDEN_DIR, "fam12_s100.sort_order.txt"), "rb").read()
+    (tmp_path / "names.txt").write_bytes(order)
+    z = gzip.compress(jac * 40)
+    cases = {"cut.csv.gz": z[: len(z) // 2], "flip.csv.gz": z[:200] + bytes(b ^ 0x5A for b in z[200:260]) + z[260:]}
+    for name, data in cases.items():
+        (tmp_path / name).write_bytes(data)
+        out = tmp_path / ("sorted_" + name)
+        S.run_sort_csv([str(tmp_path / name), str(out), str(tmp_path / "names.txt")])
+        assert not out.exists() or out.stat().st_size == 0, name
+    assert "cant open file" in capfd.readouterr().out
